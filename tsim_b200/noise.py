@@ -1,0 +1,137 @@
+"""Host-side error-mechanism sampler feeding the device sampler.
+
+Mirror of the *sampling* half of the reference's ``ChannelSampler``
+(reference ``src/tsim/noise/channels.py:503-658``): per channel, geometric
+skips pick the shots in which the channel fires, a conditional CDF picks the
+non-identity outcome, and that outcome's precomputed f-pattern is XOR-ed into
+the shot's row.  The NumPy ``Generator`` call sequence (one ``geometric`` of
+``int(N*p + 7*sigma) + 100`` draws and one ``uniform`` of ``len(positions)``
+draws per channel, channels in order) is the same, so for equal seeds the
+f-vectors are identical to the reference's -- pinned by
+``tests/golden/channel_sampler_*.npz`` (generated from the reference class).
+
+The channel *algebra* (``simplify_channels`` etc., ``channels.py:201-500``)
+runs once at compile time inside tsim and is out of scope; use
+:meth:`ChannelSampler.from_tsim` to take over an existing tsim sampler's
+precomputed tables and RNG, or :meth:`ChannelSampler.from_sparse` /
+:meth:`ChannelSampler.from_bit_probs` to build one directly.
+
+Beyond the reference: :meth:`sample_packed` writes the same bits straight into
+the 64-bit-word rows the device kernel consumes (8x less host memory traffic
+and PCIe volume than ``uint8[B, num_f]``).
+"""
+
+from __future__ import annotations
+
+from typing import Any, Sequence
+
+import numpy as np
+
+
+class ChannelSampler:
+    """Geometric-skip sampler over precomputed ``(p_fire, cond_cdf, xor_patterns)`` tables."""
+
+    def __init__(
+        self,
+        sparse_data: Sequence[tuple[float, np.ndarray, np.ndarray]],
+        num_f: int,
+        seed: int | None = None,
+        *,
+        rng: np.random.Generator | None = None,
+    ):
+        self.num_f = int(num_f)
+        self._sparse_data = [
+            (float(p), np.asarray(cdf, dtype=np.float64), np.ascontiguousarray(pats, dtype=np.uint8).reshape(-1, self.num_f))
+            for p, cdf, pats in sparse_data
+        ]
+        if rng is None:
+            rng = np.random.default_rng(seed if seed is not None else np.random.default_rng().integers(0, 2**30))
+        self._rng = rng
+        self._words = max(1, (self.num_f + 63) // 64)
+        self._packed_patterns = [self._pack(p) for _, _, p in self._sparse_data]
+
+    # -- constructors ---------------------------------------------------------------------------
+
+    @classmethod
+    def from_sparse(cls, sparse_data, num_f: int, seed: int | None = None) -> "ChannelSampler":
+        return cls(sparse_data, num_f, seed)
+
+    @classmethod
+    def from_bit_probs(cls, probs: Sequence[float], seed: int | None = None) -> "ChannelSampler":
+        """Independent single-bit channels: f_i fires with probability ``probs[i]``.
+
+        Equals the reference sampler built from ``[error_probs(q) for q in probs]`` with an
+        identity ``error_transform`` (channels with ``q <= 1e-15`` are dropped, ``channels.py:607``).
+        """
+        probs = np.asarray(probs, dtype=np.float64)
+        n = len(probs)
+        data = []
+        for i, q in enumerate(probs):
+            p_fire = 1.0 - float(1.0 - q)
+            if p_fire <= 1e-15:
+                continue
+            pat = np.zeros((1, n), dtype=np.uint8)
+            pat[0, i] = 1
+            data.append((p_fire, np.array([1.0]), pat))
+        return cls(data, n, seed)
+
+    @classmethod
+    def from_tsim(cls, sampler: Any) -> "ChannelSampler":
+        """Adopt a tsim ``ChannelSampler``'s tables and RNG (duck typed; shares the Generator)."""
+        num_f = int(sampler.signature_matrix.shape[1])
+        return cls(sampler._sparse_data, num_f, rng=sampler._rng)
+
+    # -- sampling -------------------------------------------------------------------------------
+
+    def _pack(self, pats: np.ndarray) -> np.ndarray:
+        pad = self._words * 64 - self.num_f
+        if pad:
+            pats = np.concatenate([pats, np.zeros((pats.shape[0], pad), np.uint8)], axis=1)
+        return np.packbits(pats, axis=1, bitorder="little").view(np.uint64).reshape(-1, self._words)
+
+    def _fires(self, num_samples: int):
+        """Yield ``(channel, positions, outcome_idx)`` drawing exactly like ``channels.py:638-656``."""
+        rng = self._rng
+        for ci, (p_fire, cond_cdf, _) in enumerate(self._sparse_data):
+            expected = num_samples * p_fire
+            sigma = np.sqrt(expected * (1.0 - p_fire))
+            n_draws = int(expected + 7.0 * sigma) + 100
+            positions = np.cumsum(rng.geometric(p_fire, size=n_draws)) - 1
+            positions = positions[positions < num_samples]
+            if len(positions) == 0:
+                continue
+            outcome_idx = np.searchsorted(cond_cdf, rng.uniform(size=len(positions)))
+            yield ci, positions, outcome_idx
+
+    def sample(self, num_samples: int = 1) -> np.ndarray:
+        """-> ``uint8[num_samples, num_f]`` (0/1), the reference's dense format."""
+        result = np.zeros((num_samples, self.num_f), dtype=np.uint8)
+        for ci, positions, outcome_idx in self._fires(num_samples):
+            result[positions] ^= self._sparse_data[ci][2][outcome_idx]
+        return result
+
+    def sample_packed(self, num_samples: int = 1, out: np.ndarray | None = None) -> np.ndarray:
+        """Same bits as :meth:`sample`, as ``uint64[num_samples, ceil(num_f/64)]`` little-endian rows."""
+        if out is None:
+            out = np.zeros((num_samples, self._words), dtype=np.uint64)
+        else:
+            assert out.shape == (num_samples, self._words) and out.dtype == np.uint64
+            out[...] = 0
+        for ci, positions, outcome_idx in self._fires(num_samples):
+            out[positions] ^= self._packed_patterns[ci][outcome_idx]
+        return out
+
+    @property
+    def words_per_row(self) -> int:
+        return self._words
+
+
+def pack_f_rows(f_params: np.ndarray) -> np.ndarray:
+    """``uint8/bool[B, num_f]`` -> ``uint64[B, ceil(num_f/64)]`` (bit i of the row = f_i)."""
+    f = np.ascontiguousarray(f_params).astype(np.uint8, copy=False)
+    B, n = f.shape
+    words = max(1, (n + 63) // 64)
+    pad = words * 64 - n
+    if pad:
+        f = np.concatenate([f, np.zeros((B, pad), np.uint8)], axis=1)
+    return np.packbits(f, axis=1, bitorder="little").view(np.uint64).reshape(B, words)

@@ -1,0 +1,108 @@
+/*
+ * tsim_b200 -- C ABI of the B200 sampling backend for tsim's compiled sampler.
+ *
+ * Every entry point replaces one piece of the reference's Python/JAX hot path
+ * (paths relative to the tsim repository, v0.1.5):
+ *
+ *   tsb_program_create   <- CompiledProgram / CompiledComponent / CompiledScalarGraphs pytrees handed to
+ *                           jitted code (src/tsim/core/types.py:55-107, src/tsim/compile/compile.py:21-37);
+ *                           here: one flat bit-packed blob (tsim_b200/pack.py) uploaded to HBM once.
+ *   tsb_sample_host      <- sample_program(program, f_params, key) (src/tsim/sampler.py:117-167) including
+ *                           _sample_component (:28-81), evaluate (src/tsim/compile/evaluate.py:15-59), the
+ *                           jnp.asarray H2D (:398) and copy_d2h (src/tsim/utils/cuda_helpers.py:105-141).
+ *   tsb_sample_device    <- same, for callers that already hold device buffers (multi-GPU shards).
+ *   tsb_evaluate_host    <- evaluate(circuit, param_vals) as used by CompiledStateProbs.probability_of
+ *                           (src/tsim/sampler.py:906-953).
+ *   tsb_host_alloc/free  <- alloc_pinned_numpy / _PinnedBuf (src/tsim/utils/cuda_helpers.py:48-102).
+ *   tsb_split_key        <- jax.random.split(key) (call sites src/tsim/sampler.py:74,272,399,482).
+ *
+ * Conventions: plain pointers and sizes only; all functions return 0 on success and a negative
+ * tsb_status otherwise (tsb_last_error() gives the message, thread-local).  A handle owns its device
+ * buffers and streams; calls on one handle are not re-entrant.  There is no CPU fallback: without a
+ * CUDA device every compute entry point fails with TSB_ERR_CUDA.
+ */
+#ifndef TSIM_B200_H
+#define TSIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tsb_program tsb_program;
+
+typedef enum {
+  TSB_OK = 0,
+  TSB_ERR_INVALID = -1, /* bad argument / malformed blob */
+  TSB_ERR_CUDA = -2,    /* CUDA runtime failure (message has the CUDA error string) */
+  TSB_ERR_UNSUPPORTED = -3
+} tsb_status;
+
+/* f_format */
+#define TSB_F_BYTES 0  /* uint8  [B, num_f] row-major, values 0/1 (the reference's f_params) */
+#define TSB_F_PACKED 1 /* uint64 [B, ceil(num_f/64)], bit i of a row = f_i */
+/* out_format */
+#define TSB_OUT_BYTES 0  /* uint8 (numpy bool) [B, num_outputs] -- what sample_program returns */
+#define TSB_OUT_PACKED 1 /* uint64 [B, ceil(num_outputs/64)], bit j = output column j; viewed as bytes this
+                            is np.packbits(..., axis=1, bitorder="little") padded to 8 bytes per row */
+
+typedef struct {
+  int32_t mode;         /* 0 faithful order, 1 reordered-exact ("fast") */
+  int32_t words;        /* 32-bit parameter words per shot */
+  int32_t num_f;
+  int32_t num_outputs;
+  int32_t n_direct;
+  int32_t n_components;
+  int32_t n_draws;      /* compiled (non-direct) outputs = Bernoulli draws per shot */
+  int32_t words_f64;    /* uint64 words per packed f row */
+  int32_t words_out64;  /* uint64 words per packed output row */
+  int32_t resident;     /* 1: all of g_{tki} stays in shared memory; 0: streamed chunk by chunk */
+  int32_t n_chunks;
+  int32_t smem_bytes;   /* dynamic shared memory per CTA */
+  int32_t threads;      /* threads per CTA */
+  int32_t grid;         /* CTAs per launch (persistent) */
+  int64_t data_bytes;   /* packed g_{tki} in HBM */
+} tsb_info;
+
+const char* tsb_last_error(void);
+int tsb_device_count(void);
+
+int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_program** out);
+int tsb_program_destroy(tsb_program* p);
+int tsb_program_info(const tsb_program* p, tsb_info* info);
+
+/* (carry, sub) = jax.random.split(key): carry = out[0..1], sub = out[2..3] */
+void tsb_split_key(uint32_t k0, uint32_t k1, uint32_t out[4]);
+
+/* One batch (or a shard [shot_offset, shot_offset+B) of a batch) with device-resident buffers.
+ * d_f: packed rows; d_out: packed rows; d_norm_dev: float[n_components] (written only by the shard that
+ * holds shot 0 of the batch, i.e. shot_offset == 0).  stream: cudaStream_t (NULL = handle's own stream). */
+int tsb_sample_device(tsb_program* p, const uint64_t* d_f, int64_t B, int64_t shot_offset, uint32_t k0,
+                      uint32_t k1, uint64_t* d_out, float* d_norm_dev, void* stream);
+
+/* Host buffers in, host buffers out; H2D, kernels and D2H are pipelined over slices of the batch.
+ * norm_dev: float[n_components] or NULL. */
+int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int64_t shot_offset, uint32_t k0,
+                    uint32_t k1, void* out, int out_format, float* norm_dev);
+
+/* amp[2*b], amp[2*b+1] = (re, im) of evaluate(component.compiled_scalar_graphs[level], params)[b];
+ * params: uint8 [B, n_params(level)] 0/1. */
+int tsb_evaluate_host(tsb_program* p, int component, int level, const uint8_t* params, int64_t B, float* amp);
+
+/* helpers on device buffers (stream may be NULL) */
+int tsb_pack_f_device(tsb_program* p, const uint8_t* d_bytes, int64_t B, uint64_t* d_packed, void* stream);
+int tsb_unpack_out_device(tsb_program* p, const uint64_t* d_packed, int64_t B, uint8_t* d_bytes, void* stream);
+
+/* device time (ms, CUDA events on the launch stream) of the sampling kernel launches of the last
+ * tsb_sample_device / tsb_sample_host call, and how many launches that was */
+float tsb_last_kernel_ms(tsb_program* p, int* n_launches);
+
+void* tsb_host_alloc(size_t nbytes); /* page-locked host memory, NULL on failure */
+void tsb_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSIM_B200_H */

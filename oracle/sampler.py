@@ -59,8 +59,12 @@ def sample_component(component, f_params: np.ndarray, key, *, shot_offset: int =
     return m, key, dev
 
 
-def sample_program(program, f_params: np.ndarray, key, *, shot_offset: int = 0, return_deviations: bool = False):
-    """-> bool[B, num_outputs] (and the per-component norm deviations if asked)."""
+def sample_program(program, f_params: np.ndarray, key, *, shot_offset: int = 0, return_deviations: bool = False,
+                   check_norm: bool = True):
+    """-> bool[B, num_outputs] (and the per-component norm deviations if asked).
+
+    ``check_norm=False`` skips the ValueError / warning of sampler.py:149-161 (random synthetic programs
+    are not probability trees, so their deviation is meaningless)."""
     f_params = np.asarray(f_params)
     B = f_params.shape[0]
     if program.num_outputs == 0:
@@ -76,13 +80,13 @@ def sample_program(program, f_params: np.ndarray, key, *, shot_offset: int = 0, 
     for component in program.components:
         samples, key, dev = sample_component(component, f_params, key, shot_offset=shot_offset)
         devs.append(dev)
-        if np.isclose(dev, 1):
+        if check_norm and np.isclose(dev, 1):
             raise ValueError(
                 "A vanishing marginal probability distribution was encountered (normalization 0). "
                 "This is likely the result of an underflow error. Please report this "
                 "as a bug at https://github.com/QuEraComputing/tsim/issues/new."
             )
-        if dev > 1e-5:
+        if check_norm and dev > 1e-5:
             warnings.warn(
                 "A marginal probability was not normalized correctly "
                 f"(normalization deviated from 1 by {dev:.1e}). "

@@ -1,0 +1,186 @@
+"""Device-resident program handle: upload once, sample / evaluate many times."""
+
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from typing import Any
+
+import numpy as np
+
+from . import _lib
+from .pack import PackedProgram, pack_program
+from .program import CompiledProgram, from_tsim
+
+
+def key_words(key: Any) -> tuple[int, int]:
+    """Accept ``(k0, k1)``, a uint32[2] array or a jax PRNG key (typed or raw)."""
+    if isinstance(key, tuple) and len(key) == 2:
+        return int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
+    arr = None
+    try:
+        arr = np.asarray(key)
+        if arr.dtype == object or arr.shape != (2,):
+            arr = None
+    except Exception:
+        arr = None
+    if arr is None:
+        import jax  # only reached for typed jax keys
+
+        arr = np.asarray(jax.random.key_data(key))
+    arr = arr.astype(np.uint32).reshape(2)
+    return int(arr[0]), int(arr[1])
+
+
+def split_key(key: tuple[int, int]) -> tuple[tuple[int, int], tuple[int, int]]:
+    """``carry, sub = jax.random.split(key)`` (threefry2x32, host side of the library)."""
+    out = (C.c_uint32 * 4)()
+    _lib.load().tsb_split_key(key[0], key[1], C.byref(out))
+    return (int(out[0]), int(out[1])), (int(out[2]), int(out[3]))
+
+
+class PinnedArray:
+    """Page-locked host buffer exposed as a NumPy array (reference: ``alloc_pinned_numpy``)."""
+
+    def __init__(self, shape, dtype):
+        self.shape = tuple(int(s) for s in np.atleast_1d(shape))
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        lib = _lib.load()
+        self._ptr = lib.tsb_host_alloc(max(nbytes, 1))
+        if not self._ptr:
+            raise RuntimeError("tsim_b200: " + lib.tsb_last_error().decode())
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=np.uint8, count=nbytes).view(self.dtype).reshape(self.shape)
+        self._fin = weakref.finalize(self, lib.tsb_host_free, self._ptr)
+
+
+class DeviceProgram:
+    """A compiled program uploaded to one GPU (``tsb_program`` handle)."""
+
+    def __init__(self, program: CompiledProgram | PackedProgram | Any, *, device: int = 0, mode: str = "auto", joint: bool = False):
+        if isinstance(program, PackedProgram):
+            packed = program
+            self.program = None
+        else:
+            self.program = from_tsim(program)
+            packed = pack_program(self.program, mode=mode, joint=joint)
+        self.packed = packed
+        self.joint = bool(packed.stats.get("joint", joint))
+        lib = _lib.load()
+        self._lib = lib
+        blob = np.ascontiguousarray(packed.blob, dtype=np.uint32)
+        handle = C.c_void_p()
+        _lib.check(lib.tsb_program_create(blob.ctypes.data_as(C.c_void_p), blob.size, int(device), C.byref(handle)))
+        self._h = handle
+        self._fin = weakref.finalize(self, lib.tsb_program_destroy, handle)
+        info = _lib.TsbInfo()
+        _lib.check(lib.tsb_program_info(self._h, C.byref(info)))
+        self.info = info.as_dict()
+        self.device = int(device)
+
+    # ---------------------------------------------------------------------------------------
+    @property
+    def num_f(self) -> int:
+        return self.info["num_f"]
+
+    @property
+    def num_outputs(self) -> int:
+        return self.info["num_outputs"]
+
+    def close(self) -> None:
+        self._fin()
+
+    def last_kernel_ms(self) -> tuple[float, int]:
+        n = C.c_int(0)
+        ms = self._lib.tsb_last_kernel_ms(self._h, C.byref(n))
+        return float(ms), int(n.value)
+
+    # ---------------------------------------------------------------------------------------
+    def sample(self, f_params: np.ndarray, key, *, shot_offset: int = 0, packed_out: bool = False, out: np.ndarray | None = None):
+        """One batch through the device.
+
+        ``f_params``: ``uint8/bool[B, num_f]`` (reference format) or ``uint64[B, ceil(num_f/64)]`` packed.
+        Returns ``(bits, norm_dev)``: ``bool[B, num_outputs]`` (or packed ``uint64`` rows) and the
+        per-component maximum normalisation deviation of shot 0 (``float32[n_components]``).
+        """
+        if self.joint:
+            raise ValueError("a joint-mode program can only be evaluated, not sampled")
+        f = np.asarray(f_params)
+        if f.ndim != 2:
+            raise ValueError("f_params must be 2-D")
+        B = f.shape[0]
+        if f.dtype == np.uint64:
+            if f.shape[1] != self.info["words_f64"]:
+                raise ValueError(f"packed f_params must have {self.info['words_f64']} words per row")
+            fmt = _lib.TSB_F_PACKED
+        else:
+            if f.shape[1] != self.num_f:
+                raise ValueError(f"f_params must have {self.num_f} columns, got {f.shape[1]}")
+            if f.dtype != np.uint8 and f.dtype != np.bool_:
+                f = f.astype(np.uint8)
+            fmt = _lib.TSB_F_BYTES
+        f = np.ascontiguousarray(f)
+        k0, k1 = key_words(key)
+        if packed_out:
+            shape, dtype, ofmt = (B, self.info["words_out64"]), np.uint64, _lib.TSB_OUT_PACKED
+        else:
+            shape, dtype, ofmt = (B, self.num_outputs), np.bool_, _lib.TSB_OUT_BYTES
+        if out is None:
+            out = np.empty(shape, dtype=dtype)
+        elif out.shape != shape or out.dtype != dtype or not out.flags.c_contiguous:
+            raise ValueError("out has the wrong shape, dtype or layout")
+        dev = np.zeros(max(1, self.info["n_components"]), dtype=np.float32)
+        _lib.check(
+            self._lib.tsb_sample_host(
+                self._h,
+                f.ctypes.data_as(C.c_void_p),
+                fmt,
+                B,
+                int(shot_offset),
+                k0,
+                k1,
+                out.ctypes.data_as(C.c_void_p),
+                ofmt,
+                dev.ctypes.data_as(C.c_void_p),
+            )
+        )
+        return out, dev[: self.info["n_components"]]
+
+    def sample_device(self, d_f: int, B: int, key, d_out: int, *, shot_offset: int = 0, d_norm_dev: int = 0, stream: int = 0) -> None:
+        """Launch on device pointers (e.g. ``torch.Tensor.data_ptr()``); asynchronous on ``stream``."""
+        k0, k1 = key_words(key)
+        _lib.check(
+            self._lib.tsb_sample_device(
+                self._h, C.c_void_p(d_f), int(B), int(shot_offset), k0, k1, C.c_void_p(d_out),
+                C.c_void_p(d_norm_dev) if d_norm_dev else None, C.c_void_p(stream) if stream else None,
+            )
+        )
+
+    def level_params(self, component: int, level: int) -> int:
+        """Number of parameters of ``components[component].compiled_scalar_graphs[level]``."""
+        from . import pack as PK
+
+        b = self.packed.blob
+        if not 0 <= component < self.info["n_components"]:
+            raise ValueError("component out of range")
+        comp = b[int(b[PK.H_OFF_COMP]) + component * PK.COMP_WORDS :]
+        if not 0 <= level < int(comp[5]):
+            raise ValueError("level out of range")
+        return int(b[int(b[PK.H_OFF_LEVEL]) + (int(comp[4]) + level) * PK.LEVEL_WORDS + 1])
+
+    def evaluate(self, component: int, level: int, params: np.ndarray) -> np.ndarray:
+        """``evaluate(components[component].compiled_scalar_graphs[level], params)`` -> complex64[B]."""
+        x = np.ascontiguousarray(np.asarray(params).astype(np.uint8))
+        if x.ndim != 2:
+            raise ValueError("params must be 2-D")
+        want = self.level_params(component, level)
+        if x.shape[1] != want:
+            raise ValueError(f"params must have {want} columns, got {x.shape[1]}")
+        amp = np.zeros((x.shape[0], 2), dtype=np.float32)
+        _lib.check(
+            self._lib.tsb_evaluate_host(
+                self._h, int(component), int(level), x.ctypes.data_as(C.c_void_p), x.shape[0], amp.ctypes.data_as(C.c_void_p)
+            )
+        )
+        return amp.view(np.complex64).reshape(-1)

@@ -1,0 +1,760 @@
+// libtsim_b200.so -- C ABI (include/tsim_b200.h) + kernels for sm_100a.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/tsim_b200.h"
+#include "blob.h"
+#include "sampler_kernels.cuh"
+
+namespace tsb {
+
+// =============================================================================================
+// K1: sample kernel
+// =============================================================================================
+//
+// dynamic shared memory (32-bit words):
+//   [0, 64)                      mbarriers (up to 32 x 8 bytes)
+//   [64, 64 + sizeof(Tables)/4)  lookup tables
+//   then  wf32 x kThreads        f row of every shot of the tile   (word-major: [w][tid])
+//   then  wout32 x kThreads      output row of every shot          (word-major)
+//   then  data region (resident) or n_stages x stage_words ring    (128-byte aligned)
+constexpr int kBarWords = 64;
+constexpr int kMaxStages = 32;
+
+template <int W, int MODE>
+__global__ void __launch_bounds__(kThreads, 1) sample_kernel(const KParams prm) {
+  extern __shared__ __align__(128) uint32_t smem[];
+  const uint32_t* __restrict__ blob = prm.blob;
+  const int tid = threadIdx.x;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  Tables* tb = reinterpret_cast<Tables*>(smem + kBarWords);
+  const int wf32 = 2 * (int)blob[H_WF64], wout32 = 2 * (int)blob[H_WOUT64];
+  uint32_t* sf = smem + kBarWords + sizeof(Tables) / 4;
+  uint32_t* so = sf + wf32 * kThreads;
+  uint32_t* sdata = smem + prm.smem_data_off;
+  const SmemSrc src{sdata};
+
+  const int n_comp = (int)blob[H_N_COMP], n_direct = (int)blob[H_N_DIRECT], n_chunks = (int)blob[H_N_CHUNKS];
+  const uint32_t* __restrict__ direct_tab = blob + blob[H_OFF_DIRECT];
+  const uint32_t* __restrict__ comp_tab = blob + blob[H_OFF_COMP];
+  const uint32_t* __restrict__ level_tab = blob + blob[H_OFF_LEVEL];
+  const uint32_t* __restrict__ chunk_tab = blob + blob[H_OFF_CHUNK];
+  const uint32_t* __restrict__ fsel = blob + blob[H_OFF_FSEL];
+  const uint32_t* __restrict__ dest = blob + blob[H_OFF_DEST];
+  const uint32_t* __restrict__ gdata = blob + blob[H_OFF_DATA];
+
+  init_tables(tb, tid, kThreads);
+  const int n_bars = prm.resident ? 1 : prm.n_stages;
+  if (tid == 0) {
+    for (int i = 0; i < n_bars; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+
+  // chunk staging.  q = running chunk sequence number of this CTA (tiles x chunks).
+  const int my_tiles = (prm.n_tiles > (int)blockIdx.x) ? (prm.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const long long total_q = (long long)my_tiles * n_chunks;
+  auto issue = [&](long long q) {  // called by thread 0 only
+    const int ch = (int)(q % n_chunks);
+    const uint32_t* row = chunk_tab + ch * kChunkWords;
+    const int stage = (int)(q % prm.n_stages);
+    const uint32_t bytes = row[K_WORDS] * 4u;
+    mbar_expect_tx(&bars[stage], bytes);
+    tma_bulk_g2s(sdata + (size_t)stage * prm.stage_words, gdata + row[K_OFF], bytes, &bars[stage]);
+  };
+  if (tid == 0 && my_tiles > 0 && n_chunks > 0) {
+    if (prm.resident) {
+      uint32_t total = blob[H_DATA_WORDS] * 4u;
+      mbar_expect_tx(&bars[0], total);
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        const uint32_t* row = chunk_tab + ch * kChunkWords;
+        tma_bulk_g2s(sdata + row[K_OFF], gdata + row[K_OFF], row[K_WORDS] * 4u, &bars[0]);
+      }
+    } else {
+      for (long long q = 0; q < prm.n_stages && q < total_q; ++q) issue(q);
+    }
+  }
+  if (prm.resident && my_tiles > 0 && n_chunks > 0) mbar_wait(&bars[0], 0);
+
+  long long q = 0;  // next chunk sequence number to consume (streaming mode)
+  for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
+    const long long local = (long long)tile * kThreads + tid;  // row in this launch's buffers
+    const bool active = local < prm.B;
+    const unsigned long long shot = (unsigned long long)(prm.shot_offset + local);  // index in the batch (RNG counter)
+    const bool is_check = active && shot == 0ull;
+
+    // stage the f row and clear the output row
+    for (int w = 0; w < wf32 / 2; ++w) {
+      uint64_t v = active ? prm.f[local * (wf32 / 2) + w] : 0ull;
+      sf[(2 * w) * kThreads + tid] = (uint32_t)v;
+      sf[(2 * w + 1) * kThreads + tid] = (uint32_t)(v >> 32);
+    }
+    for (int w = 0; w < wout32; ++w) so[w * kThreads + tid] = 0u;
+
+    // direct outputs: f[:, direct_f_indices] ^ direct_flips  (sampler.py:140-145)
+    for (int j = 0; j < n_direct; ++j) {
+      const uint32_t fi = direct_tab[2 * j], dd = direct_tab[2 * j + 1];
+      const uint32_t bit = ((sf[(fi >> 5) * kThreads + tid] >> (fi & 31u)) & 1u) ^ (dd >> 31);
+      const uint32_t d = dd & 0x7FFFFFFFu;
+      so[(d >> 5) * kThreads + tid] |= bit << (d & 31u);
+    }
+
+    for (int ci = 0; ci < n_comp; ++ci) {
+      const uint32_t* __restrict__ comp = comp_tab + ci * kCompWords;
+      const int F = (int)comp[C_F], n_c = (int)comp[C_NC];
+      const uint32_t* __restrict__ sel = fsel + comp[C_FSEL_OFF];
+      const int first_draw = (int)comp[C_FIRST_DRAW];
+      // gather the selected f bits: f_params[:, f_selection]  (sampler.py:48)
+      uint32_t x[W];
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        uint32_t xv = 0;
+        const int lim = min(32, F - 32 * w);
+        for (int b = 0; b < lim; ++b) {
+          const uint32_t fi = sel[32 * w + b];
+          xv |= ((sf[(fi >> 5) * kThreads + tid] >> (fi & 31u)) & 1u) << b;
+        }
+        x[w] = xv;
+      }
+      if (MODE == kModeFast) x[W - 1] |= 0x80000000u;  // always-one parameter
+
+      float prev = 0.0f, dev = 0.0f;
+      for (int k = 0; k <= n_c; ++k) {
+        const uint32_t* __restrict__ lvl = level_tab + (comp[C_FIRST_LEVEL] + k) * kLevelWords;
+        const bool approx = (lvl[L_FLAGS] & 1u) != 0u;
+        const int pos = F + k - 1;  // parameter index of the bit being tried
+        if (k > 0) {
+#pragma unroll
+          for (int w = 0; w < W; ++w)
+            if (w == (pos >> 5)) x[w] |= 1u << (pos & 31);
+        }
+        LevelAcc acc, acc0;
+        acc.reset();
+        acc0.reset();
+        const int first_chunk = (int)lvl[L_FIRST_CHUNK], nck = (int)lvl[L_N_CHUNKS];
+        for (int c = 0; c < nck; ++c) {
+          const uint32_t* row = chunk_tab + (first_chunk + c) * kChunkWords;
+          uint32_t off;
+          if (prm.resident) {
+            off = row[K_OFF];
+          } else {
+            const int stage = (int)(q % prm.n_stages);
+            mbar_wait(&bars[stage], (uint32_t)((q / prm.n_stages) & 1));
+            off = (uint32_t)stage * (uint32_t)prm.stage_words;
+          }
+          eval_chunk<W, MODE>(src, off, (int)row[K_GRAPHS], lvl, x, acc, tb);
+          if (is_check && k > 0) {
+            // normalisation check row: same prefix, trying bit 0 (sampler.py:66-72)
+            uint32_t x0[W];
+#pragma unroll
+            for (int w = 0; w < W; ++w) x0[w] = (w == (pos >> 5)) ? (x[w] & ~(1u << (pos & 31))) : x[w];
+            eval_chunk<W, MODE>(src, off, (int)row[K_GRAPHS], lvl, x0, acc0, tb);
+          }
+          if (!prm.resident) {
+            __syncthreads();  // everyone is done with this stage
+            if (tid == 0 && q + prm.n_stages < total_q) issue(q + prm.n_stages);
+            ++q;
+          }
+        }
+        float re, im;
+        finish_level<MODE>(acc, approx, (int)lvl[L_P_LO], re, im);
+        if (lvl[L_G] == 0u) { re = 0.0f; im = 0.0f; }  // evaluate.py:34-35
+        const float p1 = complex_abs(re, im);
+        if (k == 0) {
+          prev = p1;
+          continue;
+        }
+        if (is_check) {
+          finish_level<MODE>(acc0, approx, (int)lvl[L_P_LO], re, im);
+          if (lvl[L_G] == 0u) { re = 0.0f; im = 0.0f; }
+          const float p0 = complex_abs(re, im);
+          const float norm = __fdiv_rn(__fadd_rn(p0, p1), prev);
+          const float d = fabsf(__fsub_rn(norm, 1.0f));
+          dev = (dev != dev || d != d) ? __uint_as_float(0x7FC00000u) : fmaxf(dev, d);  // jnp.maximum
+        }
+        // key, subkey = split(key); bits = bernoulli(subkey, p1 / prev)  (sampler.py:74-75)
+        const uint32_t k0 = prm.subkeys[2 * (first_draw + k - 1)], k1 = prm.subkeys[2 * (first_draw + k - 1) + 1];
+        const float u = uniform_f32(k0, k1, shot);
+        const bool bit = u < __fdiv_rn(p1, prev);
+        prev = bit ? p1 : __fsub_rn(prev, p1);  // sampler.py:79
+        if (!bit) {
+#pragma unroll
+          for (int w = 0; w < W; ++w)
+            if (w == (pos >> 5)) x[w] &= ~(1u << (pos & 31));
+        } else {
+          const uint32_t d = dest[first_draw + k - 1];
+          so[(d >> 5) * kThreads + tid] |= 1u << (d & 31u);
+        }
+      }
+      if (is_check) prm.norm_dev[ci] = dev;
+    }
+
+    if (active) {
+      for (int w = 0; w < wout32 / 2; ++w) {
+        uint64_t v = (uint64_t)so[(2 * w) * kThreads + tid] | ((uint64_t)so[(2 * w + 1) * kThreads + tid] << 32);
+        prm.out[local * (wout32 / 2) + w] = v;
+      }
+    }
+  }
+}
+
+// =============================================================================================
+// K3: evaluate-only kernel (marginals / probability_of).  Records are read straight from HBM/L2.
+// =============================================================================================
+template <int W, int MODE>
+__global__ void __launch_bounds__(256) evaluate_kernel(const uint32_t* __restrict__ blob, int level_row,
+                                                       const uint32_t* __restrict__ xwords, long long B,
+                                                       float* __restrict__ amp) {
+  __shared__ Tables tb;
+  init_tables(&tb, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const uint32_t* __restrict__ lvl = blob + blob[H_OFF_LEVEL] + level_row * kLevelWords;
+  const uint32_t* __restrict__ chunk_tab = blob + blob[H_OFF_CHUNK];
+  const GmemSrc src{blob + blob[H_OFF_DATA]};
+  uint32_t x[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) x[w] = xwords[i * W + w];
+  if (MODE == kModeFast) x[W - 1] |= 0x80000000u;
+  LevelAcc acc;
+  acc.reset();
+  const int first_chunk = (int)lvl[L_FIRST_CHUNK], nck = (int)lvl[L_N_CHUNKS];
+  for (int c = 0; c < nck; ++c) {
+    const uint32_t* row = chunk_tab + (first_chunk + c) * kChunkWords;
+    eval_chunk<W, MODE>(src, row[K_OFF], (int)row[K_GRAPHS], lvl, x, acc, &tb);
+  }
+  float re, im;
+  finish_level<MODE>(acc, (lvl[L_FLAGS] & 1u) != 0u, (int)lvl[L_P_LO], re, im);
+  if (lvl[L_G] == 0u) { re = 0.0f; im = 0.0f; }
+  amp[2 * i] = re;
+  amp[2 * i + 1] = im;
+}
+
+// =============================================================================================
+// K0 / K2 helpers: byte rows <-> packed rows
+// =============================================================================================
+__global__ void pack_rows_kernel(const uint8_t* __restrict__ bytes, long long B, int n_cols, int words64,
+                                 uint64_t* __restrict__ packed) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (row, word)
+  if (i >= B * words64) return;
+  const long long row = i / words64;
+  const int w = (int)(i % words64);
+  const uint8_t* p = bytes + row * n_cols + 64 * w;
+  const int lim = min(64, n_cols - 64 * w);
+  uint64_t v = 0;
+  for (int b = 0; b < lim; ++b) v |= (uint64_t)(p[b] & 1u) << b;
+  packed[i] = v;
+}
+
+__global__ void unpack_rows_kernel(const uint64_t* __restrict__ packed, long long B, int n_cols, int words64,
+                                   uint8_t* __restrict__ bytes) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (row, col)
+  if (i >= B * n_cols) return;
+  const long long row = i / n_cols;
+  const int col = (int)(i % n_cols);
+  bytes[i] = (uint8_t)((packed[row * words64 + (col >> 6)] >> (col & 63)) & 1ull);
+}
+
+// params bytes [B, P] -> uint32 [B, W]
+__global__ void pack_params_kernel(const uint8_t* __restrict__ bytes, long long B, int P, int W, uint32_t* __restrict__ xw) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * W) return;
+  const long long row = i / W;
+  const int w = (int)(i % W);
+  const int lim = min(32, P - 32 * w);
+  uint32_t v = 0;
+  for (int b = 0; b < lim; ++b) v |= (uint32_t)(bytes[row * P + 32 * w + b] & 1u) << b;
+  xw[i] = v;
+}
+
+}  // namespace tsb
+
+// =============================================================================================
+// host side
+// =============================================================================================
+using namespace tsb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                                 \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      return fail(TSB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+
+constexpr int kSlots = 3;            // pipeline depth of tsb_sample_host
+constexpr long long kSlice = 1 << 17;  // shots per pipeline slice
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t k_start = nullptr, k_stop = nullptr;
+  uint8_t* d_in_bytes = nullptr;   // raw host rows (bytes format) or packed rows
+  uint64_t* d_f = nullptr;
+  uint64_t* d_out = nullptr;
+  uint8_t* d_out_bytes = nullptr;
+  uint32_t* d_subkeys = nullptr;
+  uint32_t* h_subkeys = nullptr;  // pinned
+  long long cap = 0;
+  bool timed = false;
+};
+
+struct tsb_program {
+  int device = 0;
+  std::vector<uint32_t> host_blob;
+  uint32_t* d_blob = nullptr;
+  float* d_norm_dev = nullptr;
+  float* h_norm_dev = nullptr;  // pinned
+  uint32_t* d_work = nullptr;
+  tsb_info info{};
+  int n_stages = 1, stage_words = 0, smem_data_off = 0;
+  Slot slots[kSlots];
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  uint32_t* d_subkeys = nullptr;
+  uint32_t* h_subkeys = nullptr;
+  float last_ms = 0.f;
+  int last_launches = 0;
+  int sm_count = 0;
+};
+
+const char* tsb_last_error(void) { return g_err.c_str(); }
+
+int tsb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+void tsb_split_key(uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 1;
+  threefry2x32(k0, k1, a0, a1);
+  threefry2x32(k0, k1, b0, b1);
+  out[0] = a0; out[1] = a1; out[2] = b0; out[3] = b1;
+}
+
+static int validate_blob(const uint32_t* b, size_t n) {
+  if (n < (size_t)kHeaderWords) return fail(TSB_ERR_INVALID, "blob shorter than its header");
+  if (b[H_MAGIC] != kMagic) return fail(TSB_ERR_INVALID, "bad magic");
+  if (b[H_VERSION] != kVersion) return fail(TSB_ERR_INVALID, "blob version mismatch");
+  if (b[H_TOTAL_WORDS] != n) return fail(TSB_ERR_INVALID, "blob size does not match header");
+  if (b[H_MODE] > 1u) return fail(TSB_ERR_INVALID, "unknown mode");
+  if (b[H_W] < 1u) return fail(TSB_ERR_INVALID, "W must be >= 1");
+  const uint32_t offs[] = {b[H_OFF_DIRECT], b[H_OFF_COMP], b[H_OFF_LEVEL], b[H_OFF_CHUNK], b[H_OFF_FSEL], b[H_OFF_DEST], b[H_OFF_DATA]};
+  for (uint32_t o : offs)
+    if (o > n) return fail(TSB_ERR_INVALID, "table offset out of range");
+  if ((size_t)b[H_OFF_DATA] + b[H_DATA_WORDS] > n) return fail(TSB_ERR_INVALID, "data region out of range");
+  if (b[H_OFF_DATA] % 4u) return fail(TSB_ERR_INVALID, "data region must be 16-byte aligned");
+  const uint32_t* ch = b + b[H_OFF_CHUNK];
+  for (uint32_t i = 0; i < b[H_N_CHUNKS]; ++i) {
+    if (ch[i * kChunkWords + K_OFF] % 4u || ch[i * kChunkWords + K_WORDS] % 4u)
+      return fail(TSB_ERR_INVALID, "chunk not 16-byte aligned");
+    if ((size_t)ch[i * kChunkWords + K_OFF] + ch[i * kChunkWords + K_WORDS] > b[H_DATA_WORDS])
+      return fail(TSB_ERR_INVALID, "chunk out of range");
+  }
+  return TSB_OK;
+}
+
+// ---- kernel dispatch over (W, MODE) ----------------------------------------------------------
+typedef void (*SampleFn)(const KParams);
+typedef void (*EvalFn)(const uint32_t*, int, const uint32_t*, long long, float*);
+
+template <int MODE>
+static SampleFn sample_fn_for(int W) {
+  switch (W) {
+    case 1: return sample_kernel<1, MODE>;
+    case 2: return sample_kernel<2, MODE>;
+    case 3: return sample_kernel<3, MODE>;
+    case 4: return sample_kernel<4, MODE>;
+    case 5: return sample_kernel<5, MODE>;
+    case 6: return sample_kernel<6, MODE>;
+    case 7: return sample_kernel<7, MODE>;
+    case 8: return sample_kernel<8, MODE>;
+    default: return nullptr;
+  }
+}
+template <int MODE>
+static EvalFn eval_fn_for(int W) {
+  switch (W) {
+    case 1: return evaluate_kernel<1, MODE>;
+    case 2: return evaluate_kernel<2, MODE>;
+    case 3: return evaluate_kernel<3, MODE>;
+    case 4: return evaluate_kernel<4, MODE>;
+    case 5: return evaluate_kernel<5, MODE>;
+    case 6: return evaluate_kernel<6, MODE>;
+    case 7: return evaluate_kernel<7, MODE>;
+    case 8: return evaluate_kernel<8, MODE>;
+    default: return nullptr;
+  }
+}
+static SampleFn sample_fn(int mode, int W) { return mode == kModeFast ? sample_fn_for<kModeFast>(W) : sample_fn_for<kModeFaithful>(W); }
+static EvalFn eval_fn(int mode, int W) { return mode == kModeFast ? eval_fn_for<kModeFast>(W) : eval_fn_for<kModeFaithful>(W); }
+
+int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_program** out) {
+  if (!blob || !out) return fail(TSB_ERR_INVALID, "null argument");
+  int rc = validate_blob(blob, n_words);
+  if (rc) return rc;
+  const int W = (int)blob[H_W], mode = (int)blob[H_MODE];
+  if (!sample_fn(mode, W)) return fail(TSB_ERR_UNSUPPORTED, "more than 256 parameters per component level (W > 8) is not built");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(TSB_ERR_INVALID, "no such CUDA device");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+
+  tsb_program* p = new tsb_program();
+  p->device = device;
+  p->sm_count = prop.multiProcessorCount;
+  p->host_blob.assign(blob, blob + n_words);
+  auto bail = [&](int code) { tsb_program_destroy(p); return code; };
+#define CUB(call)                                                                                \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess) {                                                                     \
+      fail(TSB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                    \
+      return bail(TSB_ERR_CUDA);                                                                 \
+    }                                                                                            \
+  } while (0)
+  CUB(cudaMalloc(&p->d_blob, n_words * 4));
+  CUB(cudaMemcpy(p->d_blob, blob, n_words * 4, cudaMemcpyHostToDevice));
+  const int n_comp = (int)blob[H_N_COMP], n_draws = (int)blob[H_N_DRAWS];
+  CUB(cudaMalloc(&p->d_norm_dev, sizeof(float) * std::max(1, n_comp)));
+  CUB(cudaMemset(p->d_norm_dev, 0, sizeof(float) * std::max(1, n_comp)));
+  CUB(cudaHostAlloc(&p->h_norm_dev, sizeof(float) * std::max(1, n_comp), cudaHostAllocDefault));
+  CUB(cudaMalloc(&p->d_subkeys, 8 * std::max(1, n_draws)));
+  CUB(cudaHostAlloc(&p->h_subkeys, 8 * std::max(1, n_draws), cudaHostAllocDefault));
+  CUB(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  CUB(cudaEventCreate(&p->ev_a));
+  CUB(cudaEventCreate(&p->ev_b));
+
+  // shared-memory plan
+  const int wf32 = 2 * (int)blob[H_WF64], wout32 = 2 * (int)blob[H_WOUT64];
+  int fixed_words = kBarWords + (int)(sizeof(Tables) / 4) + (wf32 + wout32) * kThreads;
+  fixed_words = (fixed_words + 31) & ~31;  // 128-byte align the data region
+  int max_smem = (int)prop.sharedMemPerBlockOptin;
+  if (const char* lim = getenv("TSIM_B200_SMEM_LIMIT")) {  // test knob: force the streamed path on small programs
+    int v = atoi(lim);
+    if (v > 0) max_smem = std::min(max_smem, v);
+  }
+  const long long budget_words = (long long)max_smem / 4 - fixed_words;
+  const long long data_words = blob[H_DATA_WORDS];
+  const int max_chunk = (int)blob[H_MAX_CHUNK];
+  if (budget_words < std::max(max_chunk, 4)) {
+    fail(TSB_ERR_UNSUPPORTED, "a single chunk of the program does not fit in shared memory");
+    return bail(TSB_ERR_UNSUPPORTED);
+  }
+  int resident = data_words <= budget_words ? 1 : 0;
+  long long used;
+  if (resident) {
+    p->n_stages = 1;
+    p->stage_words = (int)data_words;
+    used = data_words;
+  } else {
+    p->stage_words = (max_chunk + 31) & ~31;
+    p->n_stages = (int)std::min<long long>(kMaxStages, budget_words / p->stage_words);
+    used = (long long)p->n_stages * p->stage_words;
+  }
+  p->smem_data_off = fixed_words;
+  const int smem_bytes = (int)((fixed_words + used) * 4);
+  CUB(cudaFuncSetAttribute((const void*)sample_fn(mode, W), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+
+  tsb_info& in = p->info;
+  in.mode = mode; in.words = W; in.num_f = (int)blob[H_NUM_F]; in.num_outputs = (int)blob[H_N_OUT];
+  in.n_direct = (int)blob[H_N_DIRECT]; in.n_components = n_comp; in.n_draws = n_draws;
+  in.words_f64 = (int)blob[H_WF64]; in.words_out64 = (int)blob[H_WOUT64];
+  in.resident = resident; in.n_chunks = (int)blob[H_N_CHUNKS]; in.smem_bytes = smem_bytes;
+  in.threads = kThreads; in.grid = p->sm_count; in.data_bytes = data_words * 4;
+#undef CUB
+  *out = p;
+  return TSB_OK;
+}
+
+static void free_slot(Slot& s) {
+  if (s.d_in_bytes) cudaFree(s.d_in_bytes);
+  if (s.d_f) cudaFree(s.d_f);
+  if (s.d_out) cudaFree(s.d_out);
+  if (s.d_out_bytes) cudaFree(s.d_out_bytes);
+  if (s.d_subkeys) cudaFree(s.d_subkeys);
+  if (s.h_subkeys) cudaFreeHost(s.h_subkeys);
+  if (s.k_start) cudaEventDestroy(s.k_start);
+  if (s.k_stop) cudaEventDestroy(s.k_stop);
+  if (s.stream) cudaStreamDestroy(s.stream);
+  s = Slot();
+}
+
+int tsb_program_destroy(tsb_program* p) {
+  if (!p) return TSB_OK;
+  cudaSetDevice(p->device);
+  cudaDeviceSynchronize();
+  for (auto& s : p->slots) free_slot(s);
+  if (p->d_blob) cudaFree(p->d_blob);
+  if (p->d_norm_dev) cudaFree(p->d_norm_dev);
+  if (p->h_norm_dev) cudaFreeHost(p->h_norm_dev);
+  if (p->d_subkeys) cudaFree(p->d_subkeys);
+  if (p->h_subkeys) cudaFreeHost(p->h_subkeys);
+  if (p->ev_a) cudaEventDestroy(p->ev_a);
+  if (p->ev_b) cudaEventDestroy(p->ev_b);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+  return TSB_OK;
+}
+
+int tsb_program_info(const tsb_program* p, tsb_info* info) {
+  if (!p || !info) return fail(TSB_ERR_INVALID, "null argument");
+  *info = p->info;
+  return TSB_OK;
+}
+
+// draw subkeys: K_0 = batch key; (K_{j+1}, sub_j) = split(K_j)   (sampler.py:74,148)
+static void derive_subkeys(uint32_t k0, uint32_t k1, int n, uint32_t* out) {
+  for (int j = 0; j < n; ++j) {
+    uint32_t o[4];
+    tsb_split_key(k0, k1, o);
+    k0 = o[0]; k1 = o[1];
+    out[2 * j] = o[2]; out[2 * j + 1] = o[3];
+  }
+}
+
+static int launch_sample(tsb_program* p, const uint64_t* d_f, long long B, long long shot_offset, const uint32_t* d_subkeys,
+                         uint64_t* d_out, float* d_norm_dev, cudaStream_t st) {
+  if (B <= 0) return TSB_OK;
+  KParams k;
+  k.blob = p->d_blob; k.f = d_f; k.out = d_out; k.norm_dev = d_norm_dev; k.subkeys = d_subkeys;
+  k.B = B; k.shot_offset = shot_offset;
+  k.n_tiles = (int)((B + kThreads - 1) / kThreads);
+  k.resident = p->info.resident; k.n_stages = p->n_stages; k.stage_words = p->stage_words; k.smem_data_off = p->smem_data_off;
+  const int grid = std::min(k.n_tiles, p->info.grid);
+  sample_fn(p->info.mode, p->info.words)<<<grid, kThreads, p->info.smem_bytes, st>>>(k);
+  CU(cudaGetLastError());
+  return TSB_OK;
+}
+
+int tsb_sample_device(tsb_program* p, const uint64_t* d_f, int64_t B, int64_t shot_offset, uint32_t k0, uint32_t k1,
+                      uint64_t* d_out, float* d_norm_dev, void* stream) {
+  if (!p) return fail(TSB_ERR_INVALID, "null handle");
+  if (B < 0 || shot_offset < 0) return fail(TSB_ERR_INVALID, "negative batch size or offset");
+  if (B > 0 && (!d_f || !d_out)) return fail(TSB_ERR_INVALID, "null device buffer");
+  CU(cudaSetDevice(p->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  // the pinned staging array is reused per call: make sure the previous upload has been consumed
+  CU(cudaEventSynchronize(p->ev_b));
+  derive_subkeys(k0, k1, p->info.n_draws, p->h_subkeys);
+  CU(cudaMemcpyAsync(p->d_subkeys, p->h_subkeys, 8 * (size_t)std::max(1, p->info.n_draws), cudaMemcpyHostToDevice, st));
+  CU(cudaEventRecord(p->ev_a, st));
+  int rc = launch_sample(p, d_f, B, shot_offset, p->d_subkeys, d_out, d_norm_dev ? d_norm_dev : p->d_norm_dev, st);
+  if (rc) return rc;
+  CU(cudaEventRecord(p->ev_b, st));
+  p->last_launches = B > 0 ? 1 : 0;
+  p->last_ms = -1.f;  // resolved lazily in tsb_last_kernel_ms
+  return TSB_OK;
+}
+
+float tsb_last_kernel_ms(tsb_program* p, int* n_launches) {
+  if (!p) return -1.f;
+  if (n_launches) *n_launches = p->last_launches;
+  if (p->last_ms < 0.f) {
+    cudaSetDevice(p->device);
+    if (cudaEventSynchronize(p->ev_b) != cudaSuccess) return -1.f;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p->ev_a, p->ev_b) != cudaSuccess) return -1.f;
+    p->last_ms = ms;
+  }
+  return p->last_ms;
+}
+
+static int ensure_slot(tsb_program* p, Slot& s, long long cap) {
+  const tsb_info& in = p->info;
+  if (!s.stream) {
+    CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&s.k_start));
+    CU(cudaEventCreate(&s.k_stop));
+    CU(cudaMalloc(&s.d_subkeys, 8 * (size_t)std::max(1, in.n_draws)));
+    CU(cudaHostAlloc(&s.h_subkeys, 8 * (size_t)std::max(1, in.n_draws), cudaHostAllocDefault));
+  }
+  if (s.cap >= cap) return TSB_OK;
+  if (s.d_in_bytes) cudaFree(s.d_in_bytes);
+  if (s.d_f) cudaFree(s.d_f);
+  if (s.d_out) cudaFree(s.d_out);
+  if (s.d_out_bytes) cudaFree(s.d_out_bytes);
+  s.d_in_bytes = nullptr; s.d_f = nullptr; s.d_out = nullptr; s.d_out_bytes = nullptr; s.cap = 0;
+  CU(cudaMalloc(&s.d_in_bytes, (size_t)cap * std::max(1, in.num_f)));
+  CU(cudaMalloc(&s.d_f, (size_t)cap * in.words_f64 * 8));
+  CU(cudaMalloc(&s.d_out, (size_t)cap * in.words_out64 * 8));
+  CU(cudaMalloc(&s.d_out_bytes, (size_t)cap * std::max(1, in.num_outputs)));
+  s.cap = cap;
+  return TSB_OK;
+}
+
+int tsb_pack_f_device(tsb_program* p, const uint8_t* d_bytes, int64_t B, uint64_t* d_packed, void* stream) {
+  if (!p) return fail(TSB_ERR_INVALID, "null handle");
+  if (B <= 0) return TSB_OK;
+  CU(cudaSetDevice(p->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  const long long n = (long long)B * p->info.words_f64;
+  if (p->info.num_f == 0) {
+    CU(cudaMemsetAsync(d_packed, 0, (size_t)n * 8, st));
+    return TSB_OK;
+  }
+  pack_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_bytes, B, p->info.num_f, p->info.words_f64, d_packed);
+  CU(cudaGetLastError());
+  return TSB_OK;
+}
+
+int tsb_unpack_out_device(tsb_program* p, const uint64_t* d_packed, int64_t B, uint8_t* d_bytes, void* stream) {
+  if (!p) return fail(TSB_ERR_INVALID, "null handle");
+  if (B <= 0 || p->info.num_outputs == 0) return TSB_OK;
+  CU(cudaSetDevice(p->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  const long long n = (long long)B * p->info.num_outputs;
+  unpack_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_packed, B, p->info.num_outputs, p->info.words_out64, d_bytes);
+  CU(cudaGetLastError());
+  return TSB_OK;
+}
+
+int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int64_t shot_offset, uint32_t k0, uint32_t k1,
+                    void* out, int out_format, float* norm_dev) {
+  if (!p) return fail(TSB_ERR_INVALID, "null handle");
+  if (B < 0 || shot_offset < 0) return fail(TSB_ERR_INVALID, "negative batch size or offset");
+  if (f_format != TSB_F_BYTES && f_format != TSB_F_PACKED) return fail(TSB_ERR_INVALID, "bad f_format");
+  if (out_format != TSB_OUT_BYTES && out_format != TSB_OUT_PACKED) return fail(TSB_ERR_INVALID, "bad out_format");
+  const tsb_info& in = p->info;
+  if (B > 0 && ((!f && in.num_f > 0) || (!out && in.num_outputs > 0))) return fail(TSB_ERR_INVALID, "null host buffer");
+  CU(cudaSetDevice(p->device));
+  p->last_ms = 0.f;
+  p->last_launches = 0;
+  if (norm_dev)
+    for (int i = 0; i < in.n_components; ++i) norm_dev[i] = 0.f;
+  if (B == 0) return TSB_OK;
+  CU(cudaMemsetAsync(p->d_norm_dev, 0, sizeof(float) * std::max(1, in.n_components), p->stream));
+  CU(cudaStreamSynchronize(p->stream));
+
+  const long long slice = std::min<long long>(kSlice, B);
+  const size_t in_row = f_format == TSB_F_BYTES ? (size_t)in.num_f : (size_t)in.words_f64 * 8;
+  const size_t out_row = out_format == TSB_OUT_BYTES ? (size_t)in.num_outputs : (size_t)in.words_out64 * 8;
+  uint32_t subkeys_host[2];
+  (void)subkeys_host;
+  int n_slices = (int)((B + slice - 1) / slice);
+  for (int i = 0; i < n_slices; ++i) {
+    Slot& s = p->slots[i % kSlots];
+    int rc = ensure_slot(p, s, slice);
+    if (rc) return rc;
+    if (i >= kSlots) {
+      CU(cudaStreamSynchronize(s.stream));  // slot reuse: previous slice in this slot has fully drained
+      if (s.timed) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, s.k_start, s.k_stop));
+        p->last_ms += ms;
+        s.timed = false;
+      }
+    }
+    const long long lo = (long long)i * slice, n = std::min<long long>(slice, B - lo);
+    derive_subkeys(k0, k1, in.n_draws, s.h_subkeys);
+    CU(cudaMemcpyAsync(s.d_subkeys, s.h_subkeys, 8 * (size_t)std::max(1, in.n_draws), cudaMemcpyHostToDevice, s.stream));
+    const uint8_t* src = (const uint8_t*)f + (size_t)lo * in_row;
+    if (f_format == TSB_F_BYTES) {
+      if (in.num_f > 0) CU(cudaMemcpyAsync(s.d_in_bytes, src, (size_t)n * in_row, cudaMemcpyHostToDevice, s.stream));
+      rc = tsb_pack_f_device(p, s.d_in_bytes, n, s.d_f, s.stream);
+      if (rc) return rc;
+    } else {
+      CU(cudaMemcpyAsync(s.d_f, src, (size_t)n * in_row, cudaMemcpyHostToDevice, s.stream));
+    }
+    CU(cudaEventRecord(s.k_start, s.stream));
+    rc = launch_sample(p, s.d_f, n, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream);
+    if (rc) return rc;
+    CU(cudaEventRecord(s.k_stop, s.stream));
+    s.timed = true;
+    p->last_launches += 1;
+    uint8_t* dst = (uint8_t*)out + (size_t)lo * out_row;
+    if (out_row > 0) {
+      if (out_format == TSB_OUT_BYTES) {
+        rc = tsb_unpack_out_device(p, s.d_out, n, s.d_out_bytes, s.stream);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(dst, s.d_out_bytes, (size_t)n * out_row, cudaMemcpyDeviceToHost, s.stream));
+      } else {
+        CU(cudaMemcpyAsync(dst, s.d_out, (size_t)n * out_row, cudaMemcpyDeviceToHost, s.stream));
+      }
+    }
+  }
+  for (int i = 0; i < kSlots; ++i) {
+    Slot& s = p->slots[i];
+    if (!s.stream) continue;
+    CU(cudaStreamSynchronize(s.stream));
+    if (s.timed) {
+      float ms = 0.f;
+      CU(cudaEventElapsedTime(&ms, s.k_start, s.k_stop));
+      p->last_ms += ms;
+      s.timed = false;
+    }
+  }
+  if (norm_dev && in.n_components > 0)
+    CU(cudaMemcpy(norm_dev, p->d_norm_dev, sizeof(float) * in.n_components, cudaMemcpyDeviceToHost));
+  return TSB_OK;
+}
+
+int tsb_evaluate_host(tsb_program* p, int component, int level, const uint8_t* params, int64_t B, float* amp) {
+  if (!p) return fail(TSB_ERR_INVALID, "null handle");
+  const uint32_t* b = p->host_blob.data();
+  if (component < 0 || component >= (int)b[H_N_COMP]) return fail(TSB_ERR_INVALID, "component out of range");
+  const uint32_t* comp = b + b[H_OFF_COMP] + component * kCompWords;
+  if (level < 0 || level >= (int)comp[C_N_LEVELS]) return fail(TSB_ERR_INVALID, "level out of range");
+  if (B < 0) return fail(TSB_ERR_INVALID, "negative batch size");
+  if (B == 0) return TSB_OK;
+  if (!amp) return fail(TSB_ERR_INVALID, "null output");
+  const int level_row = (int)comp[C_FIRST_LEVEL] + level;
+  const int P = (int)b[b[H_OFF_LEVEL] + level_row * kLevelWords + L_P];
+  if (P > 0 && !params) return fail(TSB_ERR_INVALID, "null params");
+  const int W = p->info.words;
+  CU(cudaSetDevice(p->device));
+  uint8_t* d_bytes = nullptr;
+  uint32_t* d_x = nullptr;
+  float* d_amp = nullptr;
+  int rc = TSB_OK;
+  cudaError_t e;
+#define CUE(call)                                                                 \
+  if (rc == TSB_OK && (e = (call)) != cudaSuccess)                                \
+    rc = fail(TSB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e));
+  CUE(cudaMalloc(&d_bytes, (size_t)B * std::max(1, P)));
+  CUE(cudaMalloc(&d_x, (size_t)B * W * 4));
+  CUE(cudaMalloc(&d_amp, (size_t)B * 8));
+  if (P > 0) CUE(cudaMemcpyAsync(d_bytes, params, (size_t)B * P, cudaMemcpyHostToDevice, p->stream));
+  if (rc == TSB_OK) {
+    const long long n = (long long)B * W;
+    pack_params_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->stream>>>(d_bytes, B, P, W, d_x);
+    eval_fn(p->info.mode, W)<<<(unsigned)((B + 255) / 256), 256, 0, p->stream>>>(p->d_blob, level_row, d_x, B, d_amp);
+  }
+  CUE(cudaGetLastError());
+  CUE(cudaMemcpyAsync(amp, d_amp, (size_t)B * 8, cudaMemcpyDeviceToHost, p->stream));
+  CUE(cudaStreamSynchronize(p->stream));
+#undef CUE
+  if (d_bytes) cudaFree(d_bytes);
+  if (d_x) cudaFree(d_x);
+  if (d_amp) cudaFree(d_amp);
+  return rc;
+}
+
+void* tsb_host_alloc(size_t nbytes) {
+  void* ptr = nullptr;
+  if (cudaHostAlloc(&ptr, std::max<size_t>(nbytes, 1), cudaHostAllocDefault) != cudaSuccess) {
+    g_err = "cudaHostAlloc failed";
+    return nullptr;
+  }
+  return ptr;
+}
+
+void tsb_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}

@@ -1,0 +1,447 @@
+"""Host-side mirror of tsim's compiled samplers, running the hot path on the B200 library.
+
+Same names, arguments and error behaviour as the reference's ``src/tsim/sampler.py``:
+
+* :func:`sample_program` -- drop-in for ``tsim.sampler.sample_program`` (:117-167); :func:`install`
+  rebinds that module-level name when tsim is importable (the seam the reference's own tests patch,
+  ``test/unit/test_postselection.py:192-245``).
+* :class:`CompiledMeasurementSampler`, :class:`CompiledDetectorSampler`, :class:`CompiledStateProbs`
+  -- batching (:340-420), reference sample (:263-276), post-selection (:422-545), output layout
+  flags and bit packing (:732-868), ``probability_of`` (:906-953).  They are built from an already
+  compiled program plus a channel sampler (``from_tsim`` adopts both from a tsim sampler object),
+  because tsim's compile stages stay in tsim.
+
+Nothing here computes amplitudes or draws bits on the CPU: that is ``DeviceProgram`` (CUDA) only.
+"""
+
+from __future__ import annotations
+
+import warnings
+import weakref
+from math import ceil
+from typing import Any
+
+import numpy as np
+
+from .backend import DeviceProgram, key_words, split_key
+from .noise import ChannelSampler
+from .program import CompiledProgram, from_tsim, program_stats
+
+_VANISHING = (
+    "A vanishing marginal probability distribution was encountered (normalization 0). "
+    "This is likely the result of an underflow error. Please report this "
+    "as a bug at https://github.com/QuEraComputing/tsim/issues/new."
+)
+
+_device_cache: "weakref.WeakKeyDictionary[Any, DeviceProgram]" = weakref.WeakKeyDictionary()
+_device_cache_by_id: dict[int, tuple[Any, DeviceProgram]] = {}
+
+
+def device_program_for(program: Any, *, device: int = 0, mode: str = "auto") -> DeviceProgram:
+    """Upload ``program`` once per object and reuse the handle on later calls."""
+    if isinstance(program, DeviceProgram):
+        return program
+    try:
+        dp = _device_cache.get(program)
+        if dp is None:
+            dp = DeviceProgram(program, device=device, mode=mode)
+            _device_cache[program] = dp
+        return dp
+    except TypeError:  # unhashable / not weak-referenceable (e.g. an equinox module)
+        hit = _device_cache_by_id.get(id(program))
+        if hit is not None and hit[0] is program:
+            return hit[1]
+        dp = DeviceProgram(program, device=device, mode=mode)
+        _device_cache_by_id[id(program)] = (program, dp)
+        return dp
+
+
+def check_norm_deviations(devs) -> None:
+    """The two thresholds of ``sample_program`` (sampler.py:149-161), per component in order."""
+    for dev in devs:
+        if np.isclose(dev, 1):
+            raise ValueError(_VANISHING)
+        if dev > 1e-5:
+            warnings.warn(
+                "A marginal probability was not normalized correctly "
+                f"(normalization deviated from 1 by {dev:.1e}). "
+                "This is likely a floating point precision issue.",
+                stacklevel=3,
+            )
+
+
+def sample_program(program: Any, f_params: Any, key: Any) -> np.ndarray:
+    """Sample all outputs of a compiled program (reference ``sample_program``, sampler.py:117-167).
+
+    ``program``: tsim / tsim_b200 ``CompiledProgram`` or a ``DeviceProgram``; ``f_params``: array
+    ``[batch, num_f]`` of 0/1; ``key``: jax PRNG key or ``(k0, k1)``.  Returns ``bool[batch, num_outputs]``.
+    """
+    dp = device_program_for(program)
+    f = np.asarray(f_params)
+    if dp.num_outputs == 0:
+        return np.zeros((f.shape[0], 0), dtype=np.bool_)
+    bits, devs = dp.sample(f, key)
+    check_norm_deviations(devs)
+    return bits
+
+
+def install() -> bool:
+    """Rebind ``tsim.sampler.sample_program`` to the B200 backend.  False if tsim is not importable."""
+    try:
+        import tsim.sampler as ts
+    except Exception:
+        return False
+    ts.sample_program = sample_program
+    return True
+
+
+class _CompiledSamplerBase:
+    """Reference ``_CompiledSamplerBase`` (sampler.py:170-609) on top of a ``DeviceProgram``."""
+
+    #: upper bound for automatically chosen batches (the reference derives one from free memory,
+    #: sampler.py:308-320; here a shot needs 8*(ceil(num_f/64)+ceil(n_out/64)) bytes of HBM)
+    MAX_AUTO_BATCH = 1 << 22
+
+    def __init__(
+        self,
+        program: Any,
+        channel_sampler: ChannelSampler,
+        *,
+        num_detectors: int | None = None,
+        seed: int | None = None,
+        key: tuple[int, int] | None = None,
+        device: int = 0,
+        mode: str = "auto",
+        joint: bool = False,
+    ):
+        if seed is None and key is None:
+            seed = int(np.random.default_rng().integers(0, 2**30))
+        # jax.random.key(seed) (sampler.py:198)
+        self._key = key_words(key) if key is not None else ((int(seed) >> 32) & 0xFFFFFFFF, int(seed) & 0xFFFFFFFF)
+        self._program: CompiledProgram = from_tsim(program)
+        self._device_program = DeviceProgram(self._program, device=device, mode=mode, joint=joint)
+        self._channel_sampler = channel_sampler
+        self._num_detectors = int(self._program.num_detectors if num_detectors is None else num_detectors)
+
+        prog = self._program
+        self._direct_f_indices = np.asarray(prog.direct_f_indices)
+        self._direct_flips = np.asarray(prog.direct_flips, dtype=np.bool_)
+        self._direct_reindex = np.asarray(prog.output_reindex) if prog.output_reindex is not None else None
+        n_direct = len(self._direct_f_indices)
+        self._direct_zero_copy = (
+            n_direct > 0
+            and self._direct_reindex is None
+            and not self._direct_flips.any()
+            and np.array_equal(self._direct_f_indices, np.arange(n_direct))
+        )
+        self._direct_global_indices = np.asarray(prog.output_order[:n_direct], dtype=np.int32)
+        self._direct_output_mask = np.zeros(prog.num_outputs, dtype=np.bool_)
+        if n_direct > 0:
+            self._direct_output_mask[self._direct_global_indices] = True
+        self._direct_detector_mask = self._direct_output_mask[: self._num_detectors].copy()
+
+    @classmethod
+    def from_tsim(cls, sampler: Any, **kw):
+        """Adopt a tsim sampler's compiled program, channel sampler (shared RNG) and key."""
+        import jax
+
+        key = tuple(int(v) for v in np.asarray(jax.random.key_data(sampler._key)).reshape(2))
+        return cls(
+            sampler._program,
+            ChannelSampler.from_tsim(sampler._channel_sampler),
+            num_detectors=sampler._num_detectors,
+            key=key,
+            **kw,
+        )
+
+    # -- helpers mirrored from the reference ---------------------------------------------------
+    def _next_subkey(self) -> tuple[int, int]:
+        self._key, sub = split_key(self._key)  # sampler.py:399
+        return sub
+
+    def _run(self, f_params_np: np.ndarray) -> np.ndarray:
+        # module-level name looked up at call time, like the reference (sampler.py:274,400,484)
+        return sample_program(self._device_program, f_params_np, self._next_subkey())
+
+    def _compute_direct_outputs(self, f_params_np: np.ndarray) -> np.ndarray:
+        batch = f_params_np.shape[0]
+        num_outputs = self._program.num_outputs
+        n_direct = len(self._direct_f_indices)
+        if n_direct == 0:
+            return np.zeros((batch, num_outputs), dtype=np.bool_)
+        raw = (f_params_np[:, self._direct_f_indices].astype(np.bool_)) ^ self._direct_flips
+        out = np.zeros((batch, num_outputs), dtype=np.bool_)
+        out[:, self._direct_global_indices] = raw
+        return out
+
+    def _compute_reference_sample(self) -> np.ndarray:
+        num_f = self._channel_sampler.num_f
+        f_ref = np.zeros((1, num_f), dtype=np.uint8)
+        if not self._program.components:
+            return self._compute_direct_outputs(f_ref)[0]
+        return np.asarray(self._run(f_ref)[0], dtype=np.bool_)
+
+    def _estimate_batch_size(self) -> int:
+        return self.MAX_AUTO_BATCH
+
+    def _resolve_batch_size(self, shots: int, batch_size: int | None, *, compute_reference: bool) -> int:
+        if batch_size is None:
+            max_batch_size = self._estimate_batch_size()
+            num_batches = max(1, ceil(shots / max_batch_size))
+            batch_size = ceil(shots / num_batches)
+        if compute_reference and batch_size * ceil(shots / batch_size) == shots:
+            batch_size += 1
+        return batch_size
+
+    def _sample_direct(self, shots: int) -> np.ndarray:
+        f_params = self._channel_sampler.sample(shots)
+        result = f_params[:, self._direct_f_indices] ^ self._direct_flips
+        if self._direct_reindex is not None:
+            result = result[:, self._direct_reindex]
+        return result.view(np.bool_)
+
+    def _sample_batches(self, shots: int, batch_size: int | None = None, *, compute_reference: bool = False):
+        if shots < 0:
+            raise ValueError(f"shots must be non-negative, got {shots}")
+        if batch_size is not None and batch_size < 1:
+            raise ValueError(f"batch_size must be at least 1, got {batch_size}")
+        if shots == 0:
+            empty = np.empty((0, self._program.num_outputs), dtype=np.bool_)
+            if compute_reference:
+                return empty, np.zeros(self._program.num_outputs, dtype=np.bool_)
+            return empty
+        if not self._program.components:
+            samples = self._sample_direct(shots)
+            if compute_reference:
+                return samples, self._compute_reference_sample()
+            return samples
+        if batch_size is None:
+            max_batch_size = self._estimate_batch_size()
+            num_batches = max(1, ceil(shots / max_batch_size))
+            batch_size = ceil(shots / num_batches)
+        else:
+            num_batches = ceil(shots / batch_size)
+        if compute_reference and batch_size * num_batches == shots:
+            batch_size += 1
+
+        batches = []
+        reference = None
+        for _ in range(num_batches):
+            f_params_np = self._channel_sampler.sample(batch_size)
+            if compute_reference and reference is None:
+                f_params_np[0] = 0
+            samples = self._run(f_params_np)
+            if compute_reference and reference is None:
+                reference = np.asarray(samples[0]).copy()
+                samples = samples[1:]
+            batches.append(samples)
+        result = (batches[0] if len(batches) == 1 else np.concatenate(batches, axis=0))[:shots]
+        if compute_reference:
+            return result, reference
+        return result
+
+    def _sample_batches_with_postselection(
+        self, shots: int, batch_size: int | None, *, postselection_mask: np.ndarray, compute_reference: bool = False,
+        xor_detector_ref: bool = False,
+    ):
+        if shots < 0:
+            raise ValueError(f"shots must be non-negative, got {shots}")
+        if batch_size is not None and batch_size < 1:
+            raise ValueError(f"batch_size must be at least 1, got {batch_size}")
+        num_outputs = self._program.num_outputs
+        nd = self._num_detectors
+        if shots == 0:
+            empty = np.empty((0, num_outputs), dtype=np.bool_)
+            none_discarded = np.empty(0, dtype=np.bool_)
+            if compute_reference:
+                return empty, np.zeros(num_outputs, dtype=np.bool_), none_discarded
+            return empty, None, none_discarded
+        postselect_direct = postselection_mask & self._direct_detector_mask
+        if not self._program.components:
+            samples = self._sample_direct(shots)
+            if compute_reference:
+                reference = self._compute_reference_sample()
+                if xor_detector_ref:
+                    samples[:, :nd] ^= reference[:nd]
+                return samples, reference, np.zeros(shots, dtype=np.bool_)
+            return samples, None, np.zeros(shots, dtype=np.bool_)
+        if batch_size is None:
+            batch_size = self._resolve_batch_size(shots, batch_size, compute_reference=False)
+        reference = self._compute_reference_sample() if compute_reference else None
+
+        result = np.zeros((shots, num_outputs), dtype=np.bool_)
+        was_discarded = np.zeros(shots, dtype=np.bool_)
+        pending_f: list[np.ndarray] = []  # survivor rows waiting for a full device batch
+        pending_idx: list[np.ndarray] = []
+        n_pending = 0
+
+        def dispatch(f_batch: np.ndarray, indices: np.ndarray, n_valid: int) -> None:
+            out = self._run(f_batch)
+            result[indices[:n_valid]] = out[:n_valid]
+
+        def flush(final: bool = False) -> None:
+            nonlocal pending_f, pending_idx, n_pending
+            if n_pending >= batch_size or (final and n_pending):
+                f_all = np.concatenate(pending_f, axis=0)
+                i_all = np.concatenate(pending_idx)
+                pos = 0
+                while n_pending - pos >= batch_size:
+                    dispatch(f_all[pos : pos + batch_size], i_all[pos : pos + batch_size], batch_size)
+                    pos += batch_size
+                if final and pos < n_pending:
+                    n_valid = n_pending - pos
+                    f_batch = np.empty((batch_size, f_all.shape[1]), dtype=f_all.dtype)
+                    f_batch[:n_valid] = f_all[pos:]
+                    f_batch[n_valid:] = f_all[pos]  # fixed batch shape, padding rows discarded (sampler.py:499-505)
+                    dispatch(f_batch, i_all[pos:], n_valid)
+                    pos = n_pending
+                pending_f = [f_all[pos:]] if pos < n_pending else []
+                pending_idx = [i_all[pos:]] if pos < n_pending else []
+                n_pending -= pos
+
+        shot_idx = 0
+        while shot_idx < shots:
+            chunk = min(batch_size, shots - shot_idx)
+            f_params_np = self._channel_sampler.sample(chunk)
+            direct_full = self._compute_direct_outputs(f_params_np)
+            det_cols = direct_full[:, :nd]
+            if xor_detector_ref and reference is not None:
+                det_cols = det_cols ^ reference[:nd]
+            discarded = (det_cols & postselect_direct).any(axis=1)
+            result[shot_idx : shot_idx + chunk, :nd] = direct_full[:, :nd]
+            was_discarded[shot_idx : shot_idx + chunk] = discarded
+            survivors = np.flatnonzero(~discarded)
+            if survivors.size:
+                pending_f.append(f_params_np[survivors])
+                pending_idx.append(shot_idx + survivors)
+                n_pending += survivors.size
+            shot_idx += chunk
+            flush()
+        flush(final=True)
+
+        if xor_detector_ref and reference is not None:
+            det_ref = reference[:nd]
+            result[~was_discarded, :nd] ^= det_ref
+            result[was_discarded, :nd] ^= det_ref & self._direct_detector_mask
+        if compute_reference:
+            return result, reference, was_discarded
+        return result, None, was_discarded
+
+    def __repr__(self) -> str:
+        s = program_stats(self._program)
+        info = self._device_program.info
+        return (
+            f"{type(self).__name__}({s['direct']} direct, {s['graphs']} graphs, "
+            f"{s['max_outputs_per_component']} outputs for largest cc, ≤ {s['max_params']} parameters, "
+            f"{s['A_terms']} A terms, {s['B_terms']} B terms, {s['C_terms']} C terms, {s['D_terms']} D terms, "
+            f"{info['data_bytes']} B packed on cuda:{self._device_program.device}, "
+            f"{'resident' if info['resident'] else 'streamed'}, mode={'fast' if info['mode'] else 'faithful'})"
+        )
+
+
+class CompiledMeasurementSampler(_CompiledSamplerBase):
+    """Reference ``CompiledMeasurementSampler`` (sampler.py:612-662)."""
+
+    def sample(self, shots: int, *, batch_size: int | None = None) -> np.ndarray:
+        return self._sample_batches(shots, batch_size)
+
+
+def _maybe_bit_pack(array: np.ndarray, *, bit_packed: bool) -> np.ndarray:
+    if not bit_packed:
+        return array
+    return np.packbits(array.astype(np.bool_), axis=1, bitorder="little")
+
+
+class CompiledDetectorSampler(_CompiledSamplerBase):
+    """Reference ``CompiledDetectorSampler`` (sampler.py:672-868)."""
+
+    def sample(
+        self,
+        shots: int,
+        *,
+        batch_size: int | None = None,
+        prepend_observables: bool = False,
+        append_observables: bool = False,
+        separate_observables: bool = False,
+        bit_packed: bool = False,
+        use_detector_reference_sample: bool = False,
+        use_observable_reference_sample: bool = False,
+        postselection_mask: np.ndarray | None = None,
+    ):
+        if separate_observables and (prepend_observables or append_observables):
+            raise ValueError(
+                "Can't specify separate_observables=True with append_observables=True or prepend_observables=True"
+            )
+        compute_reference = use_detector_reference_sample or use_observable_reference_sample
+        nd = self._num_detectors
+        if postselection_mask is not None:
+            mask = np.asarray(postselection_mask, dtype=np.bool_)
+            if mask.shape != (nd,):
+                raise ValueError(f"postselection_mask must have shape ({nd},), got {mask.shape}")
+            postselection_mask = mask
+            if not (mask & self._direct_detector_mask).any() or not self._program.components:
+                postselection_mask = None
+
+        if postselection_mask is not None:
+            if compute_reference:
+                samples, reference, direct_discarded = self._sample_batches_with_postselection(
+                    shots, batch_size, postselection_mask=postselection_mask, compute_reference=True,
+                    xor_detector_ref=use_detector_reference_sample,
+                )
+                if use_observable_reference_sample:
+                    samples[~direct_discarded, nd:] ^= reference[nd:]
+            else:
+                samples, _, _ = self._sample_batches_with_postselection(shots, batch_size, postselection_mask=postselection_mask)
+        elif compute_reference:
+            samples, reference = self._sample_batches(shots, batch_size, compute_reference=True)
+            samples = np.array(samples, copy=True)
+            if use_detector_reference_sample:
+                samples[:, :nd] ^= reference[:nd]
+            if use_observable_reference_sample:
+                samples[:, nd:] ^= reference[nd:]
+        else:
+            samples = self._sample_batches(shots, batch_size)
+
+        det_samples = samples[:, :nd]
+        obs_samples = samples[:, nd:]
+        if prepend_observables and append_observables:
+            return _maybe_bit_pack(np.concatenate([obs_samples, det_samples, obs_samples], axis=1), bit_packed=bit_packed)
+        if append_observables:
+            return _maybe_bit_pack(samples, bit_packed=bit_packed)
+        if prepend_observables:
+            return _maybe_bit_pack(np.concatenate([obs_samples, det_samples], axis=1), bit_packed=bit_packed)
+        if separate_observables:
+            return _maybe_bit_pack(det_samples, bit_packed=bit_packed), _maybe_bit_pack(obs_samples, bit_packed=bit_packed)
+        return _maybe_bit_pack(det_samples, bit_packed=bit_packed)
+
+
+class CompiledStateProbs(_CompiledSamplerBase):
+    """Reference ``CompiledStateProbs`` (sampler.py:871-953): joint-mode programs, two levels per component."""
+
+    def __init__(self, program, channel_sampler, **kw):
+        super().__init__(program, channel_sampler, joint=True, **kw)
+
+    def probability_of(self, state: np.ndarray, *, batch_size: int) -> np.ndarray:
+        if batch_size < 1:
+            raise ValueError(f"batch_size must be at least 1, got {batch_size}")
+        prog = self._program
+        state = np.asarray(state)
+        if state.shape != (prog.num_outputs,):
+            raise ValueError(f"state must have shape ({prog.num_outputs},), got {state.shape}")
+        f_samples = self._channel_sampler.sample(batch_size)
+        p_norm = np.ones(batch_size, dtype=np.float32)
+        p_joint = np.ones(batch_size, dtype=np.float32)
+        n_direct = len(prog.direct_f_indices)
+        if n_direct > 0:
+            direct_bits = f_samples[:, prog.direct_f_indices].astype(np.bool_) ^ prog.direct_flips
+            targets = state[prog.output_order[:n_direct]].astype(np.bool_)
+            p_joint = p_joint * (direct_bits == targets).all(axis=1)
+        for ci, component in enumerate(prog.components):
+            assert len(component.compiled_scalar_graphs) == 2
+            f_selected = f_samples[:, component.f_selection]
+            p_norm = p_norm * np.abs(self._device_program.evaluate(ci, 0, f_selected))
+            component_state = state[list(component.output_indices)]
+            joint_params = np.hstack([f_selected, np.tile(component_state, (batch_size, 1))])
+            p_joint = p_joint * np.abs(self._device_program.evaluate(ci, 1, joint_params))
+        with np.errstate(all="ignore"):
+            return np.asarray(p_joint / p_norm)

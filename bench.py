@@ -350,7 +350,7 @@ def run_gpu(args):
         },
         "clocks": clocks.summary(),
         "e2e": e2e,
-        "gpu_launches": args.steps,
+        "gpu_launches": 2 * args.steps,  # per step: derive_subkeys_kernel + sample_kernel
         "roofline": roofline,
     }
     if cpu is not None:

@@ -78,7 +78,8 @@ void tsb_split_key(uint32_t k0, uint32_t k1, uint32_t out[4]);
 
 /* One batch (or a shard [shot_offset, shot_offset+B) of a batch) with device-resident buffers.
  * d_f: packed rows; d_out: packed rows; d_norm_dev: float[n_components] (written only by the shard that
- * holds shot 0 of the batch, i.e. shot_offset == 0).  stream: cudaStream_t (NULL = handle's own stream). */
+ * holds shot 0 of the batch, i.e. shot_offset == 0; NULL = keep it inside the handle).
+ * stream: cudaStream_t, NULL = the default stream.  Asynchronous: returns after enqueueing. */
 int tsb_sample_device(tsb_program* p, const uint64_t* d_f, int64_t B, int64_t shot_offset, uint32_t k0,
                       uint32_t k1, uint64_t* d_out, float* d_norm_dev, void* stream);
 
@@ -91,7 +92,7 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
  * params: uint8 [B, n_params(level)] 0/1. */
 int tsb_evaluate_host(tsb_program* p, int component, int level, const uint8_t* params, int64_t B, float* amp);
 
-/* helpers on device buffers (stream may be NULL) */
+/* helpers on device buffers (stream NULL = default stream) */
 int tsb_pack_f_device(tsb_program* p, const uint8_t* d_bytes, int64_t B, uint64_t* d_packed, void* stream);
 int tsb_unpack_out_device(tsb_program* p, const uint64_t* d_packed, int64_t B, uint8_t* d_bytes, void* stream);
 

@@ -55,6 +55,45 @@ class PinnedArray:
         self._fin = weakref.finalize(self, lib.tsb_host_free, self._ptr)
 
 
+class PinnedPool:
+    """Recycles page-locked host buffers for results.
+
+    The reference allocates a fresh ``cudaHostAlloc`` region for every result and frees it when the
+    returned array dies (``cuda_helpers.py:48-102``).  Page-locking is slow (milliseconds), so here a
+    dead result's region goes back to a free list instead; an array and every view derived from it keep
+    the region checked out through their common ctypes base object.
+    """
+
+    GRANULE = 1 << 20
+
+    def __init__(self):
+        self._free: dict[int, list[int]] = {}
+        self._lib = None
+
+    def _give_back(self, cap: int, ptr: int) -> None:
+        self._free.setdefault(cap, []).append(ptr)
+
+    def take(self, shape, dtype) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        cap = max(self.GRANULE, -(-nbytes // self.GRANULE) * self.GRANULE)
+        if self._lib is None:
+            self._lib = _lib.load()
+        stack = self._free.get(cap)
+        if stack:
+            ptr = stack.pop()
+        else:
+            ptr = self._lib.tsb_host_alloc(cap)
+            if not ptr:
+                raise RuntimeError("tsim_b200: " + self._lib.tsb_last_error().decode())
+        carr = (C.c_uint8 * cap).from_address(ptr)
+        weakref.finalize(carr, self._give_back, cap, ptr)
+        return np.frombuffer(carr, dtype=np.uint8, count=nbytes).view(dtype).reshape(shape)
+
+
+_result_pool = PinnedPool()
+
+
 class DeviceProgram:
     """A compiled program uploaded to one GPU (``tsb_program`` handle)."""
 
@@ -127,7 +166,7 @@ class DeviceProgram:
         else:
             shape, dtype, ofmt = (B, self.num_outputs), np.bool_, _lib.TSB_OUT_BYTES
         if out is None:
-            out = np.empty(shape, dtype=dtype)
+            out = _result_pool.take(shape, dtype) if B > 0 else np.empty(shape, dtype=dtype)
         elif out.shape != shape or out.dtype != dtype or not out.flags.c_contiguous:
             raise ValueError("out has the wrong shape, dtype or layout")
         dev = np.zeros(max(1, self.info["n_components"]), dtype=np.float32)

@@ -265,6 +265,18 @@ __global__ void unpack_rows_kernel(const uint64_t* __restrict__ packed, long lon
   bytes[i] = (uint8_t)((packed[row * words64 + (col >> 6)] >> (col & 63)) & 1ull);
 }
 
+// draw subkeys on the device: K_0 = batch key; (K_{j+1}, sub_j) = split(K_j)   (sampler.py:74,148)
+__global__ void derive_subkeys_kernel(uint32_t k0, uint32_t k1, int n, uint32_t* __restrict__ out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  for (int j = 0; j < n; ++j) {
+    uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 1;
+    threefry2x32(k0, k1, a0, a1);
+    threefry2x32(k0, k1, b0, b1);
+    k0 = a0; k1 = a1;
+    out[2 * j] = b0; out[2 * j + 1] = b1;
+  }
+}
+
 // params bytes [B, P] -> uint32 [B, W]
 __global__ void pack_params_kernel(const uint8_t* __restrict__ bytes, long long B, int P, int W, uint32_t* __restrict__ xw) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -307,7 +319,6 @@ struct Slot {
   uint64_t* d_out = nullptr;
   uint8_t* d_out_bytes = nullptr;
   uint32_t* d_subkeys = nullptr;
-  uint32_t* h_subkeys = nullptr;  // pinned
   long long cap = 0;
   bool timed = false;
 };
@@ -325,7 +336,6 @@ struct tsb_program {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   uint32_t* d_subkeys = nullptr;
-  uint32_t* h_subkeys = nullptr;
   float last_ms = 0.f;
   int last_launches = 0;
   int sm_count = 0;
@@ -436,7 +446,6 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
   CUB(cudaMemset(p->d_norm_dev, 0, sizeof(float) * std::max(1, n_comp)));
   CUB(cudaHostAlloc(&p->h_norm_dev, sizeof(float) * std::max(1, n_comp), cudaHostAllocDefault));
   CUB(cudaMalloc(&p->d_subkeys, 8 * std::max(1, n_draws)));
-  CUB(cudaHostAlloc(&p->h_subkeys, 8 * std::max(1, n_draws), cudaHostAllocDefault));
   CUB(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   CUB(cudaEventCreate(&p->ev_a));
   CUB(cudaEventCreate(&p->ev_b));
@@ -489,7 +498,6 @@ static void free_slot(Slot& s) {
   if (s.d_out) cudaFree(s.d_out);
   if (s.d_out_bytes) cudaFree(s.d_out_bytes);
   if (s.d_subkeys) cudaFree(s.d_subkeys);
-  if (s.h_subkeys) cudaFreeHost(s.h_subkeys);
   if (s.k_start) cudaEventDestroy(s.k_start);
   if (s.k_stop) cudaEventDestroy(s.k_stop);
   if (s.stream) cudaStreamDestroy(s.stream);
@@ -505,7 +513,6 @@ int tsb_program_destroy(tsb_program* p) {
   if (p->d_norm_dev) cudaFree(p->d_norm_dev);
   if (p->h_norm_dev) cudaFreeHost(p->h_norm_dev);
   if (p->d_subkeys) cudaFree(p->d_subkeys);
-  if (p->h_subkeys) cudaFreeHost(p->h_subkeys);
   if (p->ev_a) cudaEventDestroy(p->ev_a);
   if (p->ev_b) cudaEventDestroy(p->ev_b);
   if (p->stream) cudaStreamDestroy(p->stream);
@@ -517,16 +524,6 @@ int tsb_program_info(const tsb_program* p, tsb_info* info) {
   if (!p || !info) return fail(TSB_ERR_INVALID, "null argument");
   *info = p->info;
   return TSB_OK;
-}
-
-// draw subkeys: K_0 = batch key; (K_{j+1}, sub_j) = split(K_j)   (sampler.py:74,148)
-static void derive_subkeys(uint32_t k0, uint32_t k1, int n, uint32_t* out) {
-  for (int j = 0; j < n; ++j) {
-    uint32_t o[4];
-    tsb_split_key(k0, k1, o);
-    k0 = o[0]; k1 = o[1];
-    out[2 * j] = o[2]; out[2 * j + 1] = o[3];
-  }
 }
 
 static int launch_sample(tsb_program* p, const uint64_t* d_f, long long B, long long shot_offset, const uint32_t* d_subkeys,
@@ -549,16 +546,16 @@ int tsb_sample_device(tsb_program* p, const uint64_t* d_f, int64_t B, int64_t sh
   if (B < 0 || shot_offset < 0) return fail(TSB_ERR_INVALID, "negative batch size or offset");
   if (B > 0 && (!d_f || !d_out)) return fail(TSB_ERR_INVALID, "null device buffer");
   CU(cudaSetDevice(p->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
-  // the pinned staging array is reused per call: make sure the previous upload has been consumed
-  CU(cudaEventSynchronize(p->ev_b));
-  derive_subkeys(k0, k1, p->info.n_draws, p->h_subkeys);
-  CU(cudaMemcpyAsync(p->d_subkeys, p->h_subkeys, 8 * (size_t)std::max(1, p->info.n_draws), cudaMemcpyHostToDevice, st));
+  cudaStream_t st = (cudaStream_t)stream;  // NULL = the default stream, as everywhere in CUDA
   CU(cudaEventRecord(p->ev_a, st));
+  if (B > 0) {
+    derive_subkeys_kernel<<<1, 32, 0, st>>>(k0, k1, p->info.n_draws, p->d_subkeys);
+    CU(cudaGetLastError());
+  }
   int rc = launch_sample(p, d_f, B, shot_offset, p->d_subkeys, d_out, d_norm_dev ? d_norm_dev : p->d_norm_dev, st);
   if (rc) return rc;
   CU(cudaEventRecord(p->ev_b, st));
-  p->last_launches = B > 0 ? 1 : 0;
+  p->last_launches = B > 0 ? 2 : 0;
   p->last_ms = -1.f;  // resolved lazily in tsb_last_kernel_ms
   return TSB_OK;
 }
@@ -583,7 +580,6 @@ static int ensure_slot(tsb_program* p, Slot& s, long long cap) {
     CU(cudaEventCreate(&s.k_start));
     CU(cudaEventCreate(&s.k_stop));
     CU(cudaMalloc(&s.d_subkeys, 8 * (size_t)std::max(1, in.n_draws)));
-    CU(cudaHostAlloc(&s.h_subkeys, 8 * (size_t)std::max(1, in.n_draws), cudaHostAllocDefault));
   }
   if (s.cap >= cap) return TSB_OK;
   if (s.d_in_bytes) cudaFree(s.d_in_bytes);
@@ -603,7 +599,7 @@ int tsb_pack_f_device(tsb_program* p, const uint8_t* d_bytes, int64_t B, uint64_
   if (!p) return fail(TSB_ERR_INVALID, "null handle");
   if (B <= 0) return TSB_OK;
   CU(cudaSetDevice(p->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  cudaStream_t st = (cudaStream_t)stream;
   const long long n = (long long)B * p->info.words_f64;
   if (p->info.num_f == 0) {
     CU(cudaMemsetAsync(d_packed, 0, (size_t)n * 8, st));
@@ -618,7 +614,7 @@ int tsb_unpack_out_device(tsb_program* p, const uint64_t* d_packed, int64_t B, u
   if (!p) return fail(TSB_ERR_INVALID, "null handle");
   if (B <= 0 || p->info.num_outputs == 0) return TSB_OK;
   CU(cudaSetDevice(p->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+  cudaStream_t st = (cudaStream_t)stream;
   const long long n = (long long)B * p->info.num_outputs;
   unpack_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_packed, B, p->info.num_outputs, p->info.words_out64, d_bytes);
   CU(cudaGetLastError());
@@ -645,8 +641,6 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
   const long long slice = std::min<long long>(kSlice, B);
   const size_t in_row = f_format == TSB_F_BYTES ? (size_t)in.num_f : (size_t)in.words_f64 * 8;
   const size_t out_row = out_format == TSB_OUT_BYTES ? (size_t)in.num_outputs : (size_t)in.words_out64 * 8;
-  uint32_t subkeys_host[2];
-  (void)subkeys_host;
   int n_slices = (int)((B + slice - 1) / slice);
   for (int i = 0; i < n_slices; ++i) {
     Slot& s = p->slots[i % kSlots];
@@ -662,8 +656,8 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
       }
     }
     const long long lo = (long long)i * slice, n = std::min<long long>(slice, B - lo);
-    derive_subkeys(k0, k1, in.n_draws, s.h_subkeys);
-    CU(cudaMemcpyAsync(s.d_subkeys, s.h_subkeys, 8 * (size_t)std::max(1, in.n_draws), cudaMemcpyHostToDevice, s.stream));
+    derive_subkeys_kernel<<<1, 32, 0, s.stream>>>(k0, k1, in.n_draws, s.d_subkeys);
+    CU(cudaGetLastError());
     const uint8_t* src = (const uint8_t*)f + (size_t)lo * in_row;
     if (f_format == TSB_F_BYTES) {
       if (in.num_f > 0) CU(cudaMemcpyAsync(s.d_in_bytes, src, (size_t)n * in_row, cudaMemcpyHostToDevice, s.stream));
@@ -677,7 +671,7 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
     if (rc) return rc;
     CU(cudaEventRecord(s.k_stop, s.stream));
     s.timed = true;
-    p->last_launches += 1;
+    p->last_launches += 2 + (f_format == TSB_F_BYTES ? 1 : 0) + (out_format == TSB_OUT_BYTES ? 1 : 0);
     uint8_t* dst = (uint8_t*)out + (size_t)lo * out_row;
     if (out_row > 0) {
       if (out_format == TSB_OUT_BYTES) {

@@ -100,6 +100,26 @@ int tsb_unpack_out_device(tsb_program* p, const uint64_t* d_packed, int64_t B, u
  * tsb_sample_device / tsb_sample_host call, and how many launches that was */
 float tsb_last_kernel_ms(tsb_program* p, int* n_launches);
 
+/* ---- K5: error-mechanism sampler on the device (statistical parity with ChannelSampler.sample,
+ * src/tsim/noise/channels.py:624-658; tables as produced by _precompute_sparse, :578-622) ----
+ * Channel c has n_outcomes[c] non-identity outcomes; thresholds (concatenated over channels) are the cumulative
+ * outcome probabilities scaled to 2^64 (the channel fires iff u64 < last threshold of the channel); patterns are
+ * the outcomes' packed f rows, [sum n_outcomes][words_f64]. */
+typedef struct tsb_noise tsb_noise;
+int tsb_noise_create(int n_channels, const int32_t* n_outcomes, const uint64_t* thresholds, const uint64_t* patterns,
+                     int words_f64, int device, tsb_noise** out);
+int tsb_noise_destroy(tsb_noise* n);
+/* f rows for in-batch shots [shot_offset, shot_offset + B): a pure function of (seed, call, shot index, channel),
+ * so any partition of a batch over calls or GPUs gives the same rows.  skip_shot0: leave shot 0 noiseless. */
+int tsb_noise_sample_device(tsb_noise* n, int64_t B, int64_t shot_offset, uint64_t seed, uint64_t call, int skip_shot0,
+                            uint64_t* d_f, void* stream);
+int tsb_noise_sample_host(tsb_noise* n, int64_t B, int64_t shot_offset, uint64_t seed, uint64_t call, int skip_shot0,
+                          uint64_t* f_host);
+/* noise -> sample -> D2H without the f rows ever leaving the GPU (f_out: optional copy of the packed rows). */
+int tsb_sample_noisy_host(tsb_program* p, tsb_noise* n, int64_t B, int64_t shot_offset, uint32_t k0, uint32_t k1,
+                          uint64_t noise_seed, uint64_t noise_call, int skip_shot0, void* out, int out_format,
+                          float* norm_dev, uint64_t* f_out);
+
 void* tsb_host_alloc(size_t nbytes); /* page-locked host memory, NULL on failure */
 void tsb_host_free(void* ptr);
 

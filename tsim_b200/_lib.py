@@ -30,6 +30,11 @@ EXPORTS = (
     "tsb_last_kernel_ms",
     "tsb_host_alloc",
     "tsb_host_free",
+    "tsb_noise_create",
+    "tsb_noise_destroy",
+    "tsb_noise_sample_device",
+    "tsb_noise_sample_host",
+    "tsb_sample_noisy_host",
 )
 
 
@@ -99,6 +104,17 @@ def load() -> C.CDLL:
     lib.tsb_host_alloc.argtypes = [C.c_size_t]
     lib.tsb_host_free.restype = None
     lib.tsb_host_free.argtypes = [vp]
+    u64 = C.c_uint64
+    lib.tsb_noise_create.restype = i32
+    lib.tsb_noise_create.argtypes = [i32, vp, vp, vp, i32, i32, C.POINTER(vp)]
+    lib.tsb_noise_destroy.restype = i32
+    lib.tsb_noise_destroy.argtypes = [vp]
+    lib.tsb_noise_sample_device.restype = i32
+    lib.tsb_noise_sample_device.argtypes = [vp, i64, i64, u64, u64, i32, vp, vp]
+    lib.tsb_noise_sample_host.restype = i32
+    lib.tsb_noise_sample_host.argtypes = [vp, i64, i64, u64, u64, i32, vp]
+    lib.tsb_sample_noisy_host.restype = i32
+    lib.tsb_sample_noisy_host.argtypes = [vp, vp, i64, i64, u32, u32, u64, u64, i32, vp, i32, vp, vp]
     _lib = lib
     return lib
 

@@ -186,6 +186,36 @@ class DeviceProgram:
         )
         return out, dev[: self.info["n_components"]]
 
+    def sample_noisy(self, noise, B: int, key, *, shot_offset: int = 0, call: int | None = None, skip_shot0: bool = False,
+                     packed_out: bool = False, return_f: bool = False):
+        """Noise sampling + program sampling in one device pipeline (``noise``: ``DeviceChannelSampler``).
+
+        Returns ``(bits, norm_dev)`` or ``(bits, norm_dev, f_packed)`` with ``return_f``."""
+        if self.joint:
+            raise ValueError("a joint-mode program can only be evaluated, not sampled")
+        if noise.num_f != self.num_f:
+            raise ValueError(f"noise sampler produces {noise.num_f} f bits, the program expects {self.num_f}")
+        if call is None:
+            call = noise.next_call()
+        k0, k1 = key_words(key)
+        B = int(B)
+        if packed_out:
+            shape, dtype, ofmt = (B, self.info["words_out64"]), np.uint64, _lib.TSB_OUT_PACKED
+        else:
+            shape, dtype, ofmt = (B, self.num_outputs), np.bool_, _lib.TSB_OUT_BYTES
+        out = _result_pool.take(shape, dtype) if B > 0 else np.empty(shape, dtype=dtype)
+        f_out = np.zeros((B, self.info["words_f64"]), dtype=np.uint64) if return_f else None
+        dev = np.zeros(max(1, self.info["n_components"]), dtype=np.float32)
+        _lib.check(
+            self._lib.tsb_sample_noisy_host(
+                self._h, noise._h, B, int(shot_offset), k0, k1, int(noise.seed), int(call), int(skip_shot0),
+                out.ctypes.data_as(C.c_void_p), ofmt, dev.ctypes.data_as(C.c_void_p),
+                f_out.ctypes.data_as(C.c_void_p) if return_f else None,
+            )
+        )
+        dev = dev[: self.info["n_components"]]
+        return (out, dev, f_out) if return_f else (out, dev)
+
     def sample_device(self, d_f: int, B: int, key, d_out: int, *, shot_offset: int = 0, d_norm_dev: int = 0, stream: int = 0) -> None:
         """Launch on device pointers (e.g. ``torch.Tensor.data_ptr()``); asynchronous on ``stream``."""
         k0, k1 = key_words(key)

@@ -11,6 +11,7 @@
 
 #include "../../include/tsim_b200.h"
 #include "blob.h"
+#include "noise_kernels.cuh"
 #include "sampler_kernels.cuh"
 
 namespace tsb {
@@ -751,4 +752,195 @@ void* tsb_host_alloc(size_t nbytes) {
 
 void tsb_host_free(void* ptr) {
   if (ptr) cudaFreeHost(ptr);
+}
+
+// =============================================================================================
+// K5: device channel sampler
+// =============================================================================================
+struct tsb_noise {
+  int device = 0;
+  int n_channels = 0, words = 0, n_outcomes = 0;
+  uint32_t* d_chan = nullptr;
+  uint64_t* d_thr = nullptr;
+  uint64_t* d_pat = nullptr;
+  uint64_t* d_f = nullptr;  // scratch for tsb_noise_sample_host
+  long long cap = 0;
+  cudaStream_t stream = nullptr;
+};
+
+int tsb_noise_create(int n_channels, const int32_t* n_outcomes, const uint64_t* thresholds, const uint64_t* patterns,
+                     int words_f64, int device, tsb_noise** out) {
+  if (!out || n_channels < 0 || words_f64 < 1) return fail(TSB_ERR_INVALID, "bad argument");
+  if (n_channels > 0 && (!n_outcomes || !thresholds || !patterns)) return fail(TSB_ERR_INVALID, "null table");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(TSB_ERR_INVALID, "no such CUDA device");
+  CU(cudaSetDevice(device));
+  std::vector<uint32_t> chan(2 * (size_t)std::max(1, n_channels));
+  long long total = 0;
+  for (int c = 0; c < n_channels; ++c) {
+    if (n_outcomes[c] < 1) return fail(TSB_ERR_INVALID, "a channel needs at least one non-identity outcome");
+    chan[2 * c] = (uint32_t)total;
+    chan[2 * c + 1] = (uint32_t)n_outcomes[c];
+    for (int k = 1; k < n_outcomes[c]; ++k)
+      if (thresholds[total + k] < thresholds[total + k - 1]) return fail(TSB_ERR_INVALID, "thresholds must be cumulative");
+    total += n_outcomes[c];
+  }
+  tsb_noise* n = new tsb_noise();
+  n->device = device; n->n_channels = n_channels; n->words = words_f64; n->n_outcomes = (int)total;
+  cudaError_t e = cudaSuccess;
+  auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  chk(cudaMalloc(&n->d_chan, chan.size() * 4));
+  chk(cudaMalloc(&n->d_thr, 8 * (size_t)std::max<long long>(1, total)));
+  chk(cudaMalloc(&n->d_pat, 8 * (size_t)std::max<long long>(1, total) * words_f64));
+  chk(cudaStreamCreateWithFlags(&n->stream, cudaStreamNonBlocking));
+  if (e == cudaSuccess) chk(cudaMemcpy(n->d_chan, chan.data(), chan.size() * 4, cudaMemcpyHostToDevice));
+  if (e == cudaSuccess && total > 0) {
+    chk(cudaMemcpy(n->d_thr, thresholds, 8 * (size_t)total, cudaMemcpyHostToDevice));
+    chk(cudaMemcpy(n->d_pat, patterns, 8 * (size_t)total * words_f64, cudaMemcpyHostToDevice));
+  }
+  if (e != cudaSuccess) {
+    fail(TSB_ERR_CUDA, std::string("tsb_noise_create: ") + cudaGetErrorString(e));
+    tsb_noise_destroy(n);
+    return TSB_ERR_CUDA;
+  }
+  *out = n;
+  return TSB_OK;
+}
+
+int tsb_noise_destroy(tsb_noise* n) {
+  if (!n) return TSB_OK;
+  cudaSetDevice(n->device);
+  if (n->stream) { cudaStreamSynchronize(n->stream); cudaStreamDestroy(n->stream); }
+  if (n->d_chan) cudaFree(n->d_chan);
+  if (n->d_thr) cudaFree(n->d_thr);
+  if (n->d_pat) cudaFree(n->d_pat);
+  if (n->d_f) cudaFree(n->d_f);
+  delete n;
+  return TSB_OK;
+}
+
+int tsb_noise_sample_device(tsb_noise* n, int64_t B, int64_t shot_offset, uint64_t seed, uint64_t call, int skip_shot0,
+                            uint64_t* d_f, void* stream) {
+  if (!n) return fail(TSB_ERR_INVALID, "null handle");
+  if (B < 0 || shot_offset < 0) return fail(TSB_ERR_INVALID, "negative batch size or offset");
+  if (B == 0) return TSB_OK;
+  if (!d_f) return fail(TSB_ERR_INVALID, "null device buffer");
+  CU(cudaSetDevice(n->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaMemsetAsync(d_f, 0, (size_t)B * n->words * 8, st));
+  if (n->n_channels == 0) return TSB_OK;
+  NoiseParams k;
+  k.chan = n->d_chan; k.thresholds = n->d_thr; k.patterns = n->d_pat; k.f = d_f;
+  k.B = B; k.shot_offset = shot_offset; k.n_channels = n->n_channels; k.words = n->words;
+  k.seed_lo = (uint32_t)seed; k.seed_hi = (uint32_t)(seed >> 32);
+  k.call_lo = (uint32_t)call; k.call_hi = (uint32_t)(call >> 32);
+  k.skip_shot0 = skip_shot0;
+  // enough threads to fill the chip: split the channels over grid.y when the batch alone is too small
+  const long long bx = (B + 255) / 256;
+  int groups = 1;
+  while (bx * groups < 4 * 148 && groups * 2 <= (n->n_channels + 1) / 2) groups *= 2;
+  groups = std::max(groups, (n->n_channels + 255) / 256);  // at most 256 channels per thread
+  int cpt = (n->n_channels + groups - 1) / groups;
+  cpt += cpt & 1;
+  k.chan_per_thread = cpt;
+  groups = (n->n_channels + cpt - 1) / cpt;
+  dim3 grid((unsigned)bx, (unsigned)groups);
+  noise_kernel<<<grid, 256, 0, st>>>(k);
+  CU(cudaGetLastError());
+  return TSB_OK;
+}
+
+int tsb_noise_sample_host(tsb_noise* n, int64_t B, int64_t shot_offset, uint64_t seed, uint64_t call, int skip_shot0,
+                          uint64_t* f_host) {
+  if (!n) return fail(TSB_ERR_INVALID, "null handle");
+  if (B < 0) return fail(TSB_ERR_INVALID, "negative batch size");
+  if (B == 0) return TSB_OK;
+  if (!f_host) return fail(TSB_ERR_INVALID, "null host buffer");
+  CU(cudaSetDevice(n->device));
+  if (n->cap < B) {
+    if (n->d_f) cudaFree(n->d_f);
+    n->d_f = nullptr; n->cap = 0;
+    CU(cudaMalloc(&n->d_f, (size_t)B * n->words * 8));
+    n->cap = B;
+  }
+  int rc = tsb_noise_sample_device(n, B, shot_offset, seed, call, skip_shot0, n->d_f, n->stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(f_host, n->d_f, (size_t)B * n->words * 8, cudaMemcpyDeviceToHost, n->stream));
+  CU(cudaStreamSynchronize(n->stream));
+  return TSB_OK;
+}
+
+// noise -> sample -> (unpack) -> D2H, all on the device: CompiledDetectorSampler.sample() without host noise
+int tsb_sample_noisy_host(tsb_program* p, tsb_noise* n, int64_t B, int64_t shot_offset, uint32_t k0, uint32_t k1,
+                          uint64_t noise_seed, uint64_t noise_call, int skip_shot0, void* out, int out_format,
+                          float* norm_dev, uint64_t* f_out) {
+  if (!p || !n) return fail(TSB_ERR_INVALID, "null handle");
+  if (B < 0 || shot_offset < 0) return fail(TSB_ERR_INVALID, "negative batch size or offset");
+  if (out_format != TSB_OUT_BYTES && out_format != TSB_OUT_PACKED) return fail(TSB_ERR_INVALID, "bad out_format");
+  const tsb_info& in = p->info;
+  if (n->device != p->device) return fail(TSB_ERR_INVALID, "noise sampler and program live on different devices");
+  if (n->words != in.words_f64) return fail(TSB_ERR_INVALID, "noise sampler row width does not match the program");
+  if (B > 0 && !out && in.num_outputs > 0) return fail(TSB_ERR_INVALID, "null host buffer");
+  CU(cudaSetDevice(p->device));
+  p->last_ms = 0.f;
+  p->last_launches = 0;
+  if (norm_dev)
+    for (int i = 0; i < in.n_components; ++i) norm_dev[i] = 0.f;
+  if (B == 0) return TSB_OK;
+  CU(cudaMemsetAsync(p->d_norm_dev, 0, sizeof(float) * std::max(1, in.n_components), p->stream));
+  CU(cudaStreamSynchronize(p->stream));
+  const long long slice = std::min<long long>(kSlice, B);
+  const size_t out_row = out_format == TSB_OUT_BYTES ? (size_t)in.num_outputs : (size_t)in.words_out64 * 8;
+  const int n_slices = (int)((B + slice - 1) / slice);
+  for (int i = 0; i < n_slices; ++i) {
+    Slot& s = p->slots[i % kSlots];
+    int rc = ensure_slot(p, s, slice);
+    if (rc) return rc;
+    if (i >= kSlots) {
+      CU(cudaStreamSynchronize(s.stream));
+      if (s.timed) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, s.k_start, s.k_stop));
+        p->last_ms += ms;
+        s.timed = false;
+      }
+    }
+    const long long lo = (long long)i * slice, cnt = std::min<long long>(slice, B - lo);
+    rc = tsb_noise_sample_device(n, cnt, shot_offset + lo, noise_seed, noise_call, skip_shot0, s.d_f, s.stream);
+    if (rc) return rc;
+    derive_subkeys_kernel<<<1, 32, 0, s.stream>>>(k0, k1, in.n_draws, s.d_subkeys);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(s.k_start, s.stream));
+    rc = launch_sample(p, s.d_f, cnt, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream);
+    if (rc) return rc;
+    CU(cudaEventRecord(s.k_stop, s.stream));
+    s.timed = true;
+    p->last_launches += 3 + (out_format == TSB_OUT_BYTES ? 1 : 0);
+    if (f_out) CU(cudaMemcpyAsync(f_out + (size_t)lo * in.words_f64, s.d_f, (size_t)cnt * in.words_f64 * 8, cudaMemcpyDeviceToHost, s.stream));
+    uint8_t* dst = (uint8_t*)out + (size_t)lo * out_row;
+    if (out_row > 0) {
+      if (out_format == TSB_OUT_BYTES) {
+        rc = tsb_unpack_out_device(p, s.d_out, cnt, s.d_out_bytes, s.stream);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(dst, s.d_out_bytes, (size_t)cnt * out_row, cudaMemcpyDeviceToHost, s.stream));
+      } else {
+        CU(cudaMemcpyAsync(dst, s.d_out, (size_t)cnt * out_row, cudaMemcpyDeviceToHost, s.stream));
+      }
+    }
+  }
+  for (int i = 0; i < kSlots; ++i) {
+    Slot& s = p->slots[i];
+    if (!s.stream) continue;
+    CU(cudaStreamSynchronize(s.stream));
+    if (s.timed) {
+      float ms = 0.f;
+      CU(cudaEventElapsedTime(&ms, s.k_start, s.k_stop));
+      p->last_ms += ms;
+      s.timed = false;
+    }
+  }
+  if (norm_dev && in.n_components > 0)
+    CU(cudaMemcpy(norm_dev, p->d_norm_dev, sizeof(float) * in.n_components, cudaMemcpyDeviceToHost));
+  return TSB_OK;
 }

@@ -135,3 +135,98 @@ def pack_f_rows(f_params: np.ndarray) -> np.ndarray:
     if pad:
         f = np.concatenate([f, np.zeros((B, pad), np.uint8)], axis=1)
     return np.packbits(f, axis=1, bitorder="little").view(np.uint64).reshape(B, words)
+
+
+class DeviceChannelSampler:
+    """Error-mechanism sampler that runs on the GPU (``tsb_noise``; kernel K5).
+
+    Same distribution as :class:`ChannelSampler` / the reference's ``ChannelSampler.sample``
+    (``channels.py:624-658``) but a different random stream: each (shot, channel) pair draws one 64-bit
+    uniform from a counter-based generator keyed by ``(seed, call number)``, so parity with the reference is
+    statistical (its own tests use 5-10 % tolerances at 1e5 samples, ``test/unit/noise/test_channels.py:987-1048``).
+    With a ``DeviceProgram`` the f rows never leave the GPU (:meth:`DeviceProgram.sample_noisy`).
+    """
+
+    def __init__(self, sparse_data, num_f: int, seed: int | None = None, *, device: int = 0):
+        import ctypes as C
+
+        from . import _lib
+
+        self.num_f = int(num_f)
+        self._words = max(1, (self.num_f + 63) // 64)
+        self.seed = int(seed if seed is not None else np.random.default_rng().integers(0, 2**30))
+        self.calls = 0  # number of batches drawn so far (part of the generator key)
+        self.device = int(device)
+        n_out, thr, pats = [], [], []
+        for p_fire, cond_cdf, xor_patterns in sparse_data:
+            cdf = np.asarray(cond_cdf, dtype=np.float64)
+            pat = np.ascontiguousarray(xor_patterns, dtype=np.uint8).reshape(-1, self.num_f)
+            if len(cdf) != len(pat) or len(cdf) < 1:
+                raise ValueError("cond_cdf and xor_patterns must have one row per non-identity outcome")
+            n_out.append(len(cdf))
+            for c in cdf:
+                thr.append(min(int(float(p_fire) * float(c) * 2.0**64), 2**64 - 1))
+            pats.append(pack_f_rows(pat))
+        self.n_channels = len(n_out)
+        self._n_out = np.asarray(n_out, dtype=np.int32)
+        self._thr = np.asarray(thr, dtype=np.uint64)
+        self._pat = np.concatenate(pats, axis=0) if pats else np.zeros((0, self._words), np.uint64)
+        lib = _lib.load()
+        self._lib = lib
+        h = C.c_void_p()
+        _lib.check(
+            lib.tsb_noise_create(
+                self.n_channels,
+                self._n_out.ctypes.data_as(C.c_void_p),
+                self._thr.ctypes.data_as(C.c_void_p),
+                np.ascontiguousarray(self._pat).ctypes.data_as(C.c_void_p),
+                self._words,
+                self.device,
+                C.byref(h),
+            )
+        )
+        self._h = h
+        import weakref
+
+        self._fin = weakref.finalize(self, lib.tsb_noise_destroy, h)
+
+    @classmethod
+    def from_bit_probs(cls, probs, seed: int | None = None, *, device: int = 0) -> "DeviceChannelSampler":
+        host = ChannelSampler.from_bit_probs(probs, seed=0)
+        return cls(host._sparse_data, host.num_f, seed, device=device)
+
+    @classmethod
+    def from_host(cls, sampler, seed: int | None = None, *, device: int = 0) -> "DeviceChannelSampler":
+        """From a :class:`ChannelSampler` or a tsim ``ChannelSampler`` (uses its precomputed tables)."""
+        num_f = int(getattr(sampler, "num_f", None) or sampler.signature_matrix.shape[1])
+        return cls(sampler._sparse_data, num_f, seed, device=device)
+
+    @property
+    def words_per_row(self) -> int:
+        return self._words
+
+    def next_call(self) -> int:
+        c = self.calls
+        self.calls += 1
+        return c
+
+    def sample_packed(self, num_samples: int = 1, *, shot_offset: int = 0, call: int | None = None, skip_shot0: bool = False) -> np.ndarray:
+        """``uint64[num_samples, ceil(num_f/64)]`` rows, generated on the GPU and copied back."""
+        import ctypes as C
+
+        from . import _lib
+
+        if call is None:
+            call = self.next_call()
+        out = np.zeros((num_samples, self._words), dtype=np.uint64)
+        _lib.check(
+            self._lib.tsb_noise_sample_host(
+                self._h, int(num_samples), int(shot_offset), self.seed, int(call), int(skip_shot0), out.ctypes.data_as(C.c_void_p)
+            )
+        )
+        return out
+
+    def sample(self, num_samples: int = 1, **kw) -> np.ndarray:
+        """Dense ``uint8[num_samples, num_f]`` (the reference's format)."""
+        packed = self.sample_packed(num_samples, **kw)
+        return np.unpackbits(packed.view(np.uint8), axis=1, bitorder="little", count=self.num_f) if self.num_f else np.zeros((num_samples, 0), np.uint8)

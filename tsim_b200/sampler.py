@@ -24,7 +24,7 @@ from typing import Any
 import numpy as np
 
 from .backend import DeviceProgram, key_words, split_key
-from .noise import ChannelSampler
+from .noise import ChannelSampler, DeviceChannelSampler
 from .program import CompiledProgram, from_tsim, program_stats
 
 _VANISHING = (
@@ -226,11 +226,23 @@ class _CompiledSamplerBase:
 
         batches = []
         reference = None
+        on_device = isinstance(self._channel_sampler, DeviceChannelSampler)
+        packed_host = hasattr(self._channel_sampler, "sample_packed")
         for _ in range(num_batches):
-            f_params_np = self._channel_sampler.sample(batch_size)
-            if compute_reference and reference is None:
-                f_params_np[0] = 0
-            samples = self._run(f_params_np)
+            if on_device:
+                # noise, sampling and packing all on the GPU; the f rows never reach the host
+                samples, devs = self._device_program.sample_noisy(
+                    self._channel_sampler, batch_size, self._next_subkey(), skip_shot0=compute_reference and reference is None
+                )
+                check_norm_deviations(devs)
+            else:
+                # same bits either way; packed rows move 8x fewer bytes than the reference's uint8 matrix
+                f_params_np = (
+                    self._channel_sampler.sample_packed(batch_size) if packed_host else self._channel_sampler.sample(batch_size)
+                )
+                if compute_reference and reference is None:
+                    f_params_np[0] = 0
+                samples = self._run(f_params_np)
             if compute_reference and reference is None:
                 reference = np.asarray(samples[0]).copy()
                 samples = samples[1:]

@@ -73,6 +73,12 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
 int tsb_program_destroy(tsb_program* p);
 int tsb_program_info(const tsb_program* p, tsb_info* info);
 
+/* Optional pattern cache (no reference counterpart): tabulate |E_k(pattern, prefix)| for every
+ * selected-f pattern of weight <= max_weight (0, 1 or 2; -1 switches the cache off) with the sampling kernel's own
+ * evaluator, so that shots with such a pattern only walk the table.  Bits are identical with and without the cache.
+ * max_entries <= 0: default budget (2^24 floats).  entries_out: table size actually built. */
+int tsb_program_set_pattern_cache(tsb_program* p, int max_weight, int64_t max_entries, int64_t* entries_out);
+
 /* (carry, sub) = jax.random.split(key): carry = out[0..1], sub = out[2..3] */
 void tsb_split_key(uint32_t k0, uint32_t k1, uint32_t out[4]);
 

@@ -35,6 +35,7 @@ EXPORTS = (
     "tsb_noise_sample_device",
     "tsb_noise_sample_host",
     "tsb_sample_noisy_host",
+    "tsb_program_set_pattern_cache",
 )
 
 
@@ -115,6 +116,8 @@ def load() -> C.CDLL:
     lib.tsb_noise_sample_host.argtypes = [vp, i64, i64, u64, u64, i32, vp]
     lib.tsb_sample_noisy_host.restype = i32
     lib.tsb_sample_noisy_host.argtypes = [vp, vp, i64, i64, u32, u32, u64, u64, i32, vp, i32, vp, vp]
+    lib.tsb_program_set_pattern_cache.restype = i32
+    lib.tsb_program_set_pattern_cache.argtypes = [vp, i32, i64, C.POINTER(i64)]
     _lib = lib
     return lib
 

@@ -117,6 +117,7 @@ class DeviceProgram:
         _lib.check(lib.tsb_program_info(self._h, C.byref(info)))
         self.info = info.as_dict()
         self.device = int(device)
+        self.pattern_cache = None
 
     # ---------------------------------------------------------------------------------------
     @property
@@ -126,6 +127,14 @@ class DeviceProgram:
     @property
     def num_outputs(self) -> int:
         return self.info["num_outputs"]
+
+    def set_pattern_cache(self, max_weight: int | None, max_entries: int = 0) -> int:
+        """Tabulate the probability trees of all selected-f patterns of weight <= ``max_weight`` (0, 1, 2;
+        ``None`` switches the cache off).  Purely a speed-up: sampled bits do not change.  Returns the table size."""
+        n = C.c_int64(0)
+        _lib.check(self._lib.tsb_program_set_pattern_cache(self._h, -1 if max_weight is None else int(max_weight), int(max_entries), C.byref(n)))
+        self.pattern_cache = max_weight
+        return int(n.value)
 
     def close(self) -> None:
         self._fin()

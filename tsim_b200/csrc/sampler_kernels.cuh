@@ -37,6 +37,9 @@ struct KParams {
   int n_stages;     // streaming ring depth
   int stage_words;  // words per stage
   int smem_data_off;  // word offset of the data region / stage ring inside dynamic smem
+  // optional indirection (pattern-cache pass 2): process rows rows[0 .. *n_rows) instead of 0 .. B-1
+  const uint32_t* __restrict__ rows;
+  const uint32_t* __restrict__ n_rows;
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -62,7 +62,9 @@ __global__ void __launch_bounds__(kThreads, 1) sample_kernel(const KParams prm) 
   __syncthreads();
 
   // chunk staging.  q = running chunk sequence number of this CTA (tiles x chunks).
-  const int my_tiles = (prm.n_tiles > (int)blockIdx.x) ? (prm.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const long long n_rows = prm.rows ? (long long)*prm.n_rows : prm.B;
+  const int n_tiles = prm.rows ? (int)((n_rows + kThreads - 1) / kThreads) : prm.n_tiles;
+  const int my_tiles = (n_tiles > (int)blockIdx.x) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const long long total_q = (long long)my_tiles * n_chunks;
   auto issue = [&](long long q) {  // called by thread 0 only
     const int ch = (int)(q % n_chunks);
@@ -87,9 +89,10 @@ __global__ void __launch_bounds__(kThreads, 1) sample_kernel(const KParams prm) 
   if (prm.resident && my_tiles > 0 && n_chunks > 0) mbar_wait(&bars[0], 0);
 
   long long q = 0;  // next chunk sequence number to consume (streaming mode)
-  for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
-    const long long local = (long long)tile * kThreads + tid;  // row in this launch's buffers
-    const bool active = local < prm.B;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long slot = (long long)tile * kThreads + tid;
+    const bool active = slot < n_rows;
+    const long long local = (prm.rows && active) ? (long long)prm.rows[slot] : slot;  // row in this launch's buffers
     const unsigned long long shot = (unsigned long long)(prm.shot_offset + local);  // index in the batch (RNG counter)
     const bool is_check = active && shot == 0ull;
 
@@ -290,6 +293,154 @@ __global__ void pack_params_kernel(const uint8_t* __restrict__ bytes, long long 
   xw[i] = v;
 }
 
+
+// =============================================================================================
+// Pattern cache (optional): shots whose selected f bits have weight <= wmax share their probability
+// tree with every other shot of the same pattern.  |E_k(pattern, prefix, 1)| is a pure function of
+// (program, pattern, prefix), so it is tabulated once per program with the very same evaluator the
+// sampling kernel uses (bit-identical values); a light shot then needs only table walks + its draws.
+// Table of one component: [pattern][node], node(k, prefix) = k == 0 ? 0 : 2^(k-1) + prefix.
+// Pattern ids: 0 = no bit, 1 + i = bit i, 1 + F + j(j-1)/2 + i = bits i < j.
+// =============================================================================================
+constexpr int kCacheMetaWords = 4;  // per component: table offset (floats), F, n_c, wmax (0xFFFFFFFF = no table)
+constexpr int kCacheMaxWords64 = 8;
+
+template <int W, int MODE>
+__global__ void __launch_bounds__(256) cache_build_kernel(const uint32_t* __restrict__ blob, int comp_index, int wmax,
+                                                          float* __restrict__ table, long long n_entries) {
+  __shared__ Tables tb;
+  init_tables(&tb, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_entries) return;
+  const uint32_t* __restrict__ comp = blob + blob[H_OFF_COMP] + comp_index * kCompWords;
+  const int F = (int)comp[C_F], n_c = (int)comp[C_NC];
+  const int nodes = 1 << n_c;
+  const int pid = (int)(t / nodes), node = (int)(t % nodes);
+  const int k = node == 0 ? 0 : 32 - __clz(node);
+  const int prefix = node == 0 ? 0 : node - (1 << (k - 1));
+  int b0 = -1, b1 = -1;
+  if (pid >= 1 && pid <= F) {
+    b0 = pid - 1;
+  } else if (pid > F) {
+    int t2 = pid - 1 - F, j = 1;
+    while ((j + 1) * j / 2 <= t2) ++j;
+    b1 = j;
+    b0 = t2 - j * (j - 1) / 2;
+  }
+  (void)wmax;
+  uint32_t x[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    uint32_t v = 0;
+    if (b0 >= 0 && (b0 >> 5) == w) v |= 1u << (b0 & 31);
+    if (b1 >= 0 && (b1 >> 5) == w) v |= 1u << (b1 & 31);
+    for (int j = 0; j < k; ++j) {  // prefix bits m_0 .. m_{k-2}, then the trying bit 1
+      const int pos = F + j;
+      const uint32_t bit = (j == k - 1) ? 1u : (uint32_t)((prefix >> j) & 1);
+      if ((pos >> 5) == w) v |= bit << (pos & 31);
+    }
+    x[w] = v;
+  }
+  if (MODE == kModeFast) x[W - 1] |= 0x80000000u;
+  const uint32_t* __restrict__ lvl = blob + blob[H_OFF_LEVEL] + (comp[C_FIRST_LEVEL] + k) * kLevelWords;
+  const uint32_t* __restrict__ chunk_tab = blob + blob[H_OFF_CHUNK];
+  const GmemSrc src{blob + blob[H_OFF_DATA]};
+  LevelAcc acc;
+  acc.reset();
+  const int first_chunk = (int)lvl[L_FIRST_CHUNK], nck = (int)lvl[L_N_CHUNKS];
+  for (int c = 0; c < nck; ++c) {
+    const uint32_t* row = chunk_tab + (first_chunk + c) * kChunkWords;
+    eval_chunk<W, MODE>(src, row[K_OFF], (int)row[K_GRAPHS], lvl, x, acc, &tb);
+  }
+  float re, im;
+  finish_level<MODE>(acc, (lvl[L_FLAGS] & 1u) != 0u, (int)lvl[L_P_LO], re, im);
+  if (lvl[L_G] == 0u) { re = 0.0f; im = 0.0f; }
+  table[t] = complex_abs(re, im);
+}
+
+struct LightParams {
+  const uint32_t* __restrict__ blob;
+  const uint64_t* __restrict__ f;
+  uint64_t* __restrict__ out;
+  const uint32_t* __restrict__ subkeys;
+  const float* __restrict__ cache;
+  const uint32_t* __restrict__ cache_meta;
+  uint32_t* __restrict__ heavy_rows;
+  uint32_t* __restrict__ heavy_count;
+  long long B;
+  long long shot_offset;
+};
+
+// pass 1: table walks for light shots; everything else (and shot 0, which carries the norm check) is queued
+__global__ void __launch_bounds__(256) light_kernel(const LightParams prm) {
+  const uint32_t* __restrict__ blob = prm.blob;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < prm.B;
+  const unsigned long long shot = (unsigned long long)(prm.shot_offset + i);
+  const int wf = (int)blob[H_WF64], wo = (int)blob[H_WOUT64];
+  const int n_comp = (int)blob[H_N_COMP], n_direct = (int)blob[H_N_DIRECT];
+  bool heavy = active && shot == 0ull;
+  uint64_t fw[kCacheMaxWords64], ow[kCacheMaxWords64];
+  if (active && !heavy) {
+    for (int w = 0; w < wf; ++w) fw[w] = prm.f[i * wf + w];
+    for (int w = 0; w < wo; ++w) ow[w] = 0ull;
+    const uint32_t* __restrict__ direct_tab = blob + blob[H_OFF_DIRECT];
+    for (int j = 0; j < n_direct; ++j) {
+      const uint32_t fi = direct_tab[2 * j], dd = direct_tab[2 * j + 1];
+      const uint64_t bit = ((fw[fi >> 6] >> (fi & 63u)) & 1ull) ^ (uint64_t)(dd >> 31);
+      const uint32_t d = dd & 0x7FFFFFFFu;
+      ow[d >> 6] |= bit << (d & 63u);
+    }
+    const uint32_t* __restrict__ comp_tab = blob + blob[H_OFF_COMP];
+    const uint32_t* __restrict__ fsel = blob + blob[H_OFF_FSEL];
+    const uint32_t* __restrict__ dest = blob + blob[H_OFF_DEST];
+    for (int ci = 0; ci < n_comp && !heavy; ++ci) {
+      const uint32_t* __restrict__ comp = comp_tab + ci * kCompWords;
+      const uint32_t* __restrict__ meta = prm.cache_meta + ci * kCacheMetaWords;
+      const int F = (int)comp[C_F], n_c = (int)comp[C_NC], wmax = (int)meta[3];
+      const uint32_t* __restrict__ sel = fsel + comp[C_FSEL_OFF];
+      int wgt = 0, p0 = 0, p1 = 0;
+      for (int b = 0; b < F; ++b) {
+        const uint32_t fi = sel[b];
+        if ((fw[fi >> 6] >> (fi & 63u)) & 1ull) {
+          if (wgt == 0) p0 = b;
+          else if (wgt == 1) p1 = b;
+          ++wgt;
+        }
+      }
+      if (wgt > wmax) { heavy = true; break; }  // wmax == -1: no table for this component
+      const int pid = wgt == 0 ? 0 : (wgt == 1 ? 1 + p0 : 1 + F + p1 * (p1 - 1) / 2 + p0);
+      const float* __restrict__ T = prm.cache + meta[0] + ((size_t)pid << n_c);
+      float prev = T[0];
+      uint32_t prefix = 0;
+      const int first_draw = (int)comp[C_FIRST_DRAW];
+      for (int k = 1; k <= n_c; ++k) {
+        const float p1v = T[(1u << (k - 1)) + prefix];
+        const float u = uniform_f32(prm.subkeys[2 * (first_draw + k - 1)], prm.subkeys[2 * (first_draw + k - 1) + 1], shot);
+        const bool bit = u < __fdiv_rn(p1v, prev);
+        prev = bit ? p1v : __fsub_rn(prev, p1v);
+        if (bit) {
+          prefix |= 1u << (k - 1);
+          const uint32_t d = dest[first_draw + k - 1];
+          ow[d >> 6] |= 1ull << (d & 63u);
+        }
+      }
+    }
+  }
+  // warp-aggregated append of heavy rows
+  const unsigned ballot = __ballot_sync(0xFFFFFFFFu, heavy);
+  if (ballot) {
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == __ffs(ballot) - 1) base = atomicAdd(prm.heavy_count, (uint32_t)__popc(ballot));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(ballot) - 1);
+    if (heavy) prm.heavy_rows[base + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)i;
+  }
+  if (active && !heavy)
+    for (int w = 0; w < wo; ++w) prm.out[i * wo + w] = ow[w];
+}
+
 }  // namespace tsb
 
 // =============================================================================================
@@ -320,6 +471,7 @@ struct Slot {
   uint64_t* d_out = nullptr;
   uint8_t* d_out_bytes = nullptr;
   uint32_t* d_subkeys = nullptr;
+  uint32_t* d_heavy = nullptr;  // [cap + 1]: count, then row indices (pattern-cache pass 2)
   long long cap = 0;
   bool timed = false;
 };
@@ -340,6 +492,13 @@ struct tsb_program {
   float last_ms = 0.f;
   int last_launches = 0;
   int sm_count = 0;
+  // pattern cache
+  int cache_wmax = -1;  // -1: off
+  float* d_cache = nullptr;
+  uint32_t* d_cache_meta = nullptr;
+  long long cache_entries = 0;
+  uint32_t* d_heavy = nullptr;  // for tsb_sample_device
+  long long heavy_cap = 0;
 };
 
 const char* tsb_last_error(void) { return g_err.c_str(); }
@@ -499,6 +658,7 @@ static void free_slot(Slot& s) {
   if (s.d_out) cudaFree(s.d_out);
   if (s.d_out_bytes) cudaFree(s.d_out_bytes);
   if (s.d_subkeys) cudaFree(s.d_subkeys);
+  if (s.d_heavy) cudaFree(s.d_heavy);
   if (s.k_start) cudaEventDestroy(s.k_start);
   if (s.k_stop) cudaEventDestroy(s.k_stop);
   if (s.stream) cudaStreamDestroy(s.stream);
@@ -514,6 +674,9 @@ int tsb_program_destroy(tsb_program* p) {
   if (p->d_norm_dev) cudaFree(p->d_norm_dev);
   if (p->h_norm_dev) cudaFreeHost(p->h_norm_dev);
   if (p->d_subkeys) cudaFree(p->d_subkeys);
+  if (p->d_cache) cudaFree(p->d_cache);
+  if (p->d_cache_meta) cudaFree(p->d_cache_meta);
+  if (p->d_heavy) cudaFree(p->d_heavy);
   if (p->ev_a) cudaEventDestroy(p->ev_a);
   if (p->ev_b) cudaEventDestroy(p->ev_b);
   if (p->stream) cudaStreamDestroy(p->stream);
@@ -527,17 +690,117 @@ int tsb_program_info(const tsb_program* p, tsb_info* info) {
   return TSB_OK;
 }
 
-static int launch_sample(tsb_program* p, const uint64_t* d_f, long long B, long long shot_offset, const uint32_t* d_subkeys,
-                         uint64_t* d_out, float* d_norm_dev, cudaStream_t st) {
+static int launch_sample_rows(tsb_program* p, const uint64_t* d_f, long long B, long long shot_offset, const uint32_t* d_subkeys,
+                              uint64_t* d_out, float* d_norm_dev, cudaStream_t st, const uint32_t* rows, const uint32_t* n_rows) {
   if (B <= 0) return TSB_OK;
   KParams k;
   k.blob = p->d_blob; k.f = d_f; k.out = d_out; k.norm_dev = d_norm_dev; k.subkeys = d_subkeys;
   k.B = B; k.shot_offset = shot_offset;
   k.n_tiles = (int)((B + kThreads - 1) / kThreads);
   k.resident = p->info.resident; k.n_stages = p->n_stages; k.stage_words = p->stage_words; k.smem_data_off = p->smem_data_off;
+  k.rows = rows; k.n_rows = n_rows;
   const int grid = std::min(k.n_tiles, p->info.grid);
   sample_fn(p->info.mode, p->info.words)<<<grid, kThreads, p->info.smem_bytes, st>>>(k);
   CU(cudaGetLastError());
+  return TSB_OK;
+}
+
+static int launch_light(tsb_program* p, const uint64_t* d_f, long long B, long long shot_offset, const uint32_t* d_subkeys,
+                        uint64_t* d_out, uint32_t* heavy_rows, uint32_t* heavy_count, cudaStream_t st);
+
+// One batch slice: either the full evaluation for every shot, or (pattern cache on) table walks for light shots
+// followed by the full evaluation of the remaining rows.
+static int launch_sample(tsb_program* p, const uint64_t* d_f, long long B, long long shot_offset, const uint32_t* d_subkeys,
+                         uint64_t* d_out, float* d_norm_dev, cudaStream_t st, uint32_t* heavy_rows = nullptr,
+                         uint32_t* heavy_count = nullptr) {
+  if (B <= 0) return TSB_OK;
+  if (p->cache_wmax < 0 || !heavy_rows) return launch_sample_rows(p, d_f, B, shot_offset, d_subkeys, d_out, d_norm_dev, st, nullptr, nullptr);
+  int rc = launch_light(p, d_f, B, shot_offset, d_subkeys, d_out, heavy_rows, heavy_count, st);
+  if (rc) return rc;
+  return launch_sample_rows(p, d_f, B, shot_offset, d_subkeys, d_out, d_norm_dev, st, heavy_rows, heavy_count);
+}
+
+
+static int launch_light(tsb_program* p, const uint64_t* d_f, long long B, long long shot_offset, const uint32_t* d_subkeys,
+                        uint64_t* d_out, uint32_t* heavy_rows, uint32_t* heavy_count, cudaStream_t st) {
+  CU(cudaMemsetAsync(heavy_count, 0, 4, st));
+  LightParams k;
+  k.blob = p->d_blob; k.f = d_f; k.out = d_out; k.subkeys = d_subkeys; k.cache = p->d_cache; k.cache_meta = p->d_cache_meta;
+  k.heavy_rows = heavy_rows; k.heavy_count = heavy_count; k.B = B; k.shot_offset = shot_offset;
+  const unsigned blocks = (unsigned)((B + 255) / 256);
+  light_kernel<<<blocks, 256, 0, st>>>(k);
+  CU(cudaGetLastError());
+  return TSB_OK;
+}
+
+typedef void (*CacheFn)(const uint32_t*, int, int, float*, long long);
+template <int MODE>
+static CacheFn cache_fn_for(int W) {
+  switch (W) {
+    case 1: return cache_build_kernel<1, MODE>;
+    case 2: return cache_build_kernel<2, MODE>;
+    case 3: return cache_build_kernel<3, MODE>;
+    case 4: return cache_build_kernel<4, MODE>;
+    case 5: return cache_build_kernel<5, MODE>;
+    case 6: return cache_build_kernel<6, MODE>;
+    case 7: return cache_build_kernel<7, MODE>;
+    case 8: return cache_build_kernel<8, MODE>;
+    default: return nullptr;
+  }
+}
+
+int tsb_program_set_pattern_cache(tsb_program* p, int max_weight, int64_t max_entries, int64_t* entries_out) {
+  if (!p) return fail(TSB_ERR_INVALID, "null handle");
+  if (max_weight > 2) return fail(TSB_ERR_INVALID, "pattern cache supports weights 0, 1 and 2");
+  CU(cudaSetDevice(p->device));
+  CU(cudaDeviceSynchronize());
+  if (p->d_cache) cudaFree(p->d_cache);
+  if (p->d_cache_meta) cudaFree(p->d_cache_meta);
+  p->d_cache = nullptr; p->d_cache_meta = nullptr; p->cache_wmax = -1; p->cache_entries = 0;
+  if (entries_out) *entries_out = 0;
+  if (max_weight < 0) return TSB_OK;
+  const tsb_info& in = p->info;
+  if (in.words_f64 > kCacheMaxWords64 || in.words_out64 > kCacheMaxWords64)
+    return fail(TSB_ERR_UNSUPPORTED, "pattern cache needs num_f <= 512 and num_outputs <= 512");
+  if (max_entries <= 0) max_entries = 1ll << 24;
+  const uint32_t* b = p->host_blob.data();
+  const int n_comp = in.n_components;
+  std::vector<uint32_t> meta((size_t)std::max(1, n_comp) * kCacheMetaWords, 0);
+  std::vector<long long> offs(n_comp), counts(n_comp);
+  long long total = 0;
+  for (int c = 0; c < n_comp; ++c) {
+    const uint32_t* comp = b + b[H_OFF_COMP] + c * kCompWords;
+    const long long F = comp[C_F], n_c = comp[C_NC];
+    int w = -1;
+    long long cnt = 0;
+    if (n_c <= 20) {
+      for (int cand = max_weight; cand >= 0; --cand) {
+        const long long pats = 1 + (cand >= 1 ? F : 0) + (cand >= 2 ? F * (F - 1) / 2 : 0);
+        if (pats * (1ll << n_c) <= max_entries - total) { w = cand; cnt = pats * (1ll << n_c); break; }
+      }
+    }
+    offs[c] = total; counts[c] = cnt;
+    meta[c * kCacheMetaWords + 0] = (uint32_t)total;
+    meta[c * kCacheMetaWords + 1] = (uint32_t)F;
+    meta[c * kCacheMetaWords + 2] = (uint32_t)n_c;
+    meta[c * kCacheMetaWords + 3] = (uint32_t)w;
+    total += cnt;
+  }
+  if (total >= (1ll << 32)) return fail(TSB_ERR_UNSUPPORTED, "pattern cache too large");
+  CU(cudaMalloc(&p->d_cache, sizeof(float) * (size_t)std::max<long long>(1, total)));
+  CU(cudaMalloc(&p->d_cache_meta, meta.size() * 4));
+  CU(cudaMemcpy(p->d_cache_meta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
+  CacheFn fn = in.mode == kModeFast ? cache_fn_for<kModeFast>(in.words) : cache_fn_for<kModeFaithful>(in.words);
+  for (int c = 0; c < n_comp; ++c) {
+    if (counts[c] == 0) continue;
+    const unsigned blocks = (unsigned)((counts[c] + 255) / 256);
+    fn<<<blocks, 256, 0, p->stream>>>(p->d_blob, c, (int)meta[c * kCacheMetaWords + 3], p->d_cache + offs[c], counts[c]);
+    CU(cudaGetLastError());
+  }
+  CU(cudaStreamSynchronize(p->stream));
+  p->cache_wmax = max_weight;
+  p->cache_entries = total;
+  if (entries_out) *entries_out = total;
   return TSB_OK;
 }
 
@@ -553,7 +816,14 @@ int tsb_sample_device(tsb_program* p, const uint64_t* d_f, int64_t B, int64_t sh
     derive_subkeys_kernel<<<1, 32, 0, st>>>(k0, k1, p->info.n_draws, p->d_subkeys);
     CU(cudaGetLastError());
   }
-  int rc = launch_sample(p, d_f, B, shot_offset, p->d_subkeys, d_out, d_norm_dev ? d_norm_dev : p->d_norm_dev, st);
+  if (p->cache_wmax >= 0 && p->heavy_cap < B) {
+    if (p->d_heavy) cudaFree(p->d_heavy);
+    p->d_heavy = nullptr; p->heavy_cap = 0;
+    CU(cudaMalloc(&p->d_heavy, 4 * ((size_t)B + 1)));
+    p->heavy_cap = B;
+  }
+  int rc = launch_sample(p, d_f, B, shot_offset, p->d_subkeys, d_out, d_norm_dev ? d_norm_dev : p->d_norm_dev, st,
+                         p->d_heavy ? p->d_heavy + 1 : nullptr, p->d_heavy);
   if (rc) return rc;
   CU(cudaEventRecord(p->ev_b, st));
   p->last_launches = B > 0 ? 2 : 0;
@@ -587,11 +857,13 @@ static int ensure_slot(tsb_program* p, Slot& s, long long cap) {
   if (s.d_f) cudaFree(s.d_f);
   if (s.d_out) cudaFree(s.d_out);
   if (s.d_out_bytes) cudaFree(s.d_out_bytes);
-  s.d_in_bytes = nullptr; s.d_f = nullptr; s.d_out = nullptr; s.d_out_bytes = nullptr; s.cap = 0;
+  if (s.d_heavy) cudaFree(s.d_heavy);
+  s.d_in_bytes = nullptr; s.d_f = nullptr; s.d_out = nullptr; s.d_out_bytes = nullptr; s.d_heavy = nullptr; s.cap = 0;
   CU(cudaMalloc(&s.d_in_bytes, (size_t)cap * std::max(1, in.num_f)));
   CU(cudaMalloc(&s.d_f, (size_t)cap * in.words_f64 * 8));
   CU(cudaMalloc(&s.d_out, (size_t)cap * in.words_out64 * 8));
   CU(cudaMalloc(&s.d_out_bytes, (size_t)cap * std::max(1, in.num_outputs)));
+  CU(cudaMalloc(&s.d_heavy, 4 * ((size_t)cap + 1)));
   s.cap = cap;
   return TSB_OK;
 }
@@ -668,7 +940,7 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
       CU(cudaMemcpyAsync(s.d_f, src, (size_t)n * in_row, cudaMemcpyHostToDevice, s.stream));
     }
     CU(cudaEventRecord(s.k_start, s.stream));
-    rc = launch_sample(p, s.d_f, n, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream);
+    rc = launch_sample(p, s.d_f, n, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream, s.d_heavy + 1, s.d_heavy);
     if (rc) return rc;
     CU(cudaEventRecord(s.k_stop, s.stream));
     s.timed = true;
@@ -912,7 +1184,7 @@ int tsb_sample_noisy_host(tsb_program* p, tsb_noise* n, int64_t B, int64_t shot_
     derive_subkeys_kernel<<<1, 32, 0, s.stream>>>(k0, k1, in.n_draws, s.d_subkeys);
     CU(cudaGetLastError());
     CU(cudaEventRecord(s.k_start, s.stream));
-    rc = launch_sample(p, s.d_f, cnt, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream);
+    rc = launch_sample(p, s.d_f, cnt, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream, s.d_heavy + 1, s.d_heavy);
     if (rc) return rc;
     CU(cudaEventRecord(s.k_stop, s.stream));
     s.timed = true;

@@ -284,6 +284,16 @@ def test_detector_sampler_layout_flags_and_reference_sample(no_norm_check):
         assert np.array_equal(pre, np.concatenate([base[:, 5:], base[:, :5]], axis=1))
         packed = mk().sample(50, batch_size=16, append_observables=True, bit_packed=True)
         assert np.array_equal(packed, np.packbits(base, axis=1, bitorder="little"))
+        # every layout, packed end to end == packbits of the bool result
+        for kw in (dict(), dict(prepend_observables=True), dict(prepend_observables=True, append_observables=True),
+                   dict(use_detector_reference_sample=True, append_observables=True),
+                   dict(use_observable_reference_sample=True, prepend_observables=True)):
+            a = mk().sample(50, batch_size=16, **kw)
+            b = mk().sample(50, batch_size=16, bit_packed=True, **kw)
+            assert np.array_equal(b, np.packbits(a, axis=1, bitorder="little")), kw
+        d1, o1 = mk().sample(50, batch_size=16, separate_observables=True, use_detector_reference_sample=True)
+        d2, o2 = mk().sample(50, batch_size=16, separate_observables=True, use_detector_reference_sample=True, bit_packed=True)
+        assert np.array_equal(d2, np.packbits(d1, axis=1, bitorder="little")) and np.array_equal(o2, np.packbits(o1, axis=1, bitorder="little"))
         with pytest.raises(ValueError):
             mk().sample(5, separate_observables=True, append_observables=True)
         with pytest.raises(ValueError):

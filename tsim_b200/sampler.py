@@ -26,6 +26,7 @@ import numpy as np
 from .backend import DeviceProgram, key_words, split_key
 from .noise import ChannelSampler, DeviceChannelSampler
 from .program import CompiledProgram, from_tsim, program_stats
+from .shard import pack_bool_rows
 
 _VANISHING = (
     "A vanishing marginal probability distribution was encountered (normalization 0). "
@@ -159,7 +160,11 @@ class _CompiledSamplerBase:
         self._key, sub = split_key(self._key)  # sampler.py:399
         return sub
 
-    def _run(self, f_params_np: np.ndarray) -> np.ndarray:
+    def _run(self, f_params_np: np.ndarray, *, packed: bool = False) -> np.ndarray:
+        if packed:
+            bits, devs = self._device_program.sample(f_params_np, self._next_subkey(), packed_out=True)
+            check_norm_deviations(devs)
+            return bits
         # module-level name looked up at call time, like the reference (sampler.py:274,400,484)
         return sample_program(self._device_program, f_params_np, self._next_subkey())
 
@@ -200,7 +205,15 @@ class _CompiledSamplerBase:
             result = result[:, self._direct_reindex]
         return result.view(np.bool_)
 
-    def _sample_batches(self, shots: int, batch_size: int | None = None, *, compute_reference: bool = False):
+    def _sample_batches(self, shots: int, batch_size: int | None = None, *, compute_reference: bool = False,
+                        packed: bool = False):
+        """Reference ``_sample_batches`` (sampler.py:340-420).  ``packed=True`` (not in the reference) keeps the
+        result as the device's ``uint64[shots, ceil(n_out/64)]`` rows; the reference row is still ``bool[n_out]``."""
+        if packed and (shots == 0 or not self._program.components):
+            res = self._sample_batches(shots, batch_size, compute_reference=compute_reference)
+            if compute_reference:
+                return pack_bool_rows(res[0]), res[1]
+            return pack_bool_rows(res)
         if shots < 0:
             raise ValueError(f"shots must be non-negative, got {shots}")
         if batch_size is not None and batch_size < 1:
@@ -232,7 +245,8 @@ class _CompiledSamplerBase:
             if on_device:
                 # noise, sampling and packing all on the GPU; the f rows never reach the host
                 samples, devs = self._device_program.sample_noisy(
-                    self._channel_sampler, batch_size, self._next_subkey(), skip_shot0=compute_reference and reference is None
+                    self._channel_sampler, batch_size, self._next_subkey(), skip_shot0=compute_reference and reference is None,
+                    packed_out=packed,
                 )
                 check_norm_deviations(devs)
             else:
@@ -242,9 +256,11 @@ class _CompiledSamplerBase:
                 )
                 if compute_reference and reference is None:
                     f_params_np[0] = 0
-                samples = self._run(f_params_np)
+                samples = self._run(f_params_np, packed=packed)
             if compute_reference and reference is None:
                 reference = np.asarray(samples[0]).copy()
+                if packed:
+                    reference = np.unpackbits(reference.view(np.uint8), bitorder="little", count=self._program.num_outputs).astype(np.bool_)
                 samples = samples[1:]
             batches.append(samples)
         result = (batches[0] if len(batches) == 1 else np.concatenate(batches, axis=0))[:shots]
@@ -358,6 +374,35 @@ class CompiledMeasurementSampler(_CompiledSamplerBase):
         return self._sample_batches(shots, batch_size)
 
 
+def _packed_columns(rows: np.ndarray, lo: int, hi: int) -> np.ndarray:
+    """Columns ``[lo, hi)`` of packed ``uint64[B, W]`` rows as ``np.packbits(..., bitorder="little")`` bytes."""
+    B, W = rows.shape
+    n = hi - lo
+    n_words = max(1, (n + 63) // 64)
+    out = np.zeros((B, n_words), dtype=np.uint64)
+    for k in range(n_words if n > 0 else 0):
+        off = lo + 64 * k
+        w, sh = divmod(off, 64)
+        if w >= W:
+            break
+        v = rows[:, w] >> np.uint64(sh)
+        if sh and w + 1 < W:
+            v = v | (rows[:, w + 1] << np.uint64(64 - sh))
+        out[:, k] = v
+    tail = n - 64 * (n_words - 1)
+    if 0 <= tail < 64:
+        out[:, n_words - 1] &= np.uint64((1 << tail) - 1)
+    return np.ascontiguousarray(out.view(np.uint8)[:, : (n + 7) // 8])
+
+
+def _concat_packed(parts: list[tuple[np.ndarray, int]]) -> np.ndarray:
+    """Concatenate bit-packed column blocks ``(bytes[B, ceil(n/8)], n)`` along the bit axis."""
+    if len(parts) == 1:
+        return parts[0][0]
+    bits = [np.unpackbits(a, axis=1, bitorder="little", count=n) for a, n in parts]
+    return np.packbits(np.concatenate(bits, axis=1), axis=1, bitorder="little")
+
+
 def _maybe_bit_pack(array: np.ndarray, *, bit_packed: bool) -> np.ndarray:
     if not bit_packed:
         return array
@@ -404,6 +449,29 @@ class CompiledDetectorSampler(_CompiledSamplerBase):
                     samples[~direct_discarded, nd:] ^= reference[nd:]
             else:
                 samples, _, _ = self._sample_batches_with_postselection(shots, batch_size, postselection_mask=postselection_mask)
+        elif bit_packed and self._program.components and shots > 0:
+            # packed end to end: the device's uint64 rows are sliced with word shifts, never expanded to bools
+            n_out = self._program.num_outputs
+            if compute_reference:
+                rows, reference = self._sample_batches(shots, batch_size, compute_reference=True, packed=True)
+                ref = reference.copy()
+                if not use_detector_reference_sample:
+                    ref[:nd] = False
+                if not use_observable_reference_sample:
+                    ref[nd:] = False
+                rows = rows ^ pack_bool_rows(ref[None, :])
+            else:
+                rows = self._sample_batches(shots, batch_size, packed=True)
+            det, obs = (lambda: _packed_columns(rows, 0, nd)), (lambda: _packed_columns(rows, nd, n_out))
+            if prepend_observables and append_observables:
+                return _concat_packed([(obs(), n_out - nd), (det(), nd), (obs(), n_out - nd)])
+            if append_observables:
+                return _packed_columns(rows, 0, n_out)
+            if prepend_observables:
+                return _concat_packed([(obs(), n_out - nd), (det(), nd)])
+            if separate_observables:
+                return det(), obs()
+            return det()
         elif compute_reference:
             samples, reference = self._sample_batches(shots, batch_size, compute_reference=True)
             samples = np.array(samples, copy=True)

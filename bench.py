@@ -201,7 +201,8 @@ def run_gpu(args):
     f_host = [rng_cs.sample_packed(shots) for _ in range(min(n_buf, 3))]
     d_f = [torch.from_numpy(f_host[i % len(f_host)].view(np.int64)).to(dev) for i in range(n_buf)]
     d_out = [torch.empty((shots, wo), dtype=torch.int64, device=dev) for _ in range(n_buf)]
-    d_all = torch.empty((world * shots, wo), dtype=torch.int64, device=dev) if world > 1 else None
+    d_all = [torch.empty((world * shots, wo), dtype=torch.int64, device=dev) for _ in range(2)] if world > 1 else None
+    pending = []  # in-flight gathers: step i's gather overlaps step i+1's kernel
     stream = torch.cuda.current_stream().cuda_stream
     key = (0, 42)
     shot_offset = rank * shots  # weak scaling: the global batch is world * shots, this rank owns one slice
@@ -211,11 +212,19 @@ def run_gpu(args):
         b = i % n_buf
         dp.sample_device(d_f[b].data_ptr(), shots, sub, d_out[b].data_ptr(), shot_offset=shot_offset, stream=stream)
         if world > 1:
-            dist.all_gather_into_tensor(d_all, d_out[b])  # the single gather of output bitstrings
+            if len(pending) >= 2:
+                pending.pop(0).wait()  # frees the gather buffer about to be reused
+            # the single gather of output bitstrings (NCCL), asynchronous w.r.t. the next step's kernel
+            pending.append(dist.all_gather_into_tensor(d_all[i % 2], d_out[b], async_op=True))
         return key
+
+    def drain():
+        while pending:
+            pending.pop(0).wait()
 
     for i in range(args.warmup):
         key = step(i, key)
+    drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -226,6 +235,7 @@ def run_gpu(args):
         ev0.record()
         for i in range(args.steps):
             key = step(args.warmup + i, key)
+        drain()
         ev1.record()
         torch.cuda.synchronize()
     total_ms = ev0.elapsed_time(ev1)

@@ -49,7 +49,7 @@ typedef enum {
                             is np.packbits(..., axis=1, bitorder="little") padded to 8 bytes per row */
 
 typedef struct {
-  int32_t mode;         /* 0 faithful order, 1 reordered-exact ("fast") */
+  int32_t mode;         /* 0 faithful order, 1 reordered-exact per row ("fast"), 2 reordered-exact bit-sliced ("sliced") */
   int32_t words;        /* 32-bit parameter words per shot */
   int32_t num_f;
   int32_t num_outputs;
@@ -72,6 +72,11 @@ int tsb_device_count(void);
 int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_program** out);
 int tsb_program_destroy(tsb_program* p);
 int tsb_program_info(const tsb_program* p, tsb_info* info);
+
+/* A bit-sliced (mode 2) program samples 32 shots per thread and cannot evaluate single rows; the normalisation
+ * check of shot 0 (sampler.py:66-72) and tsb_evaluate_host run on a companion per-row program of the same
+ * CompiledProgram.  The companion is not owned: destroy it after the sliced program. */
+int tsb_program_set_aux(tsb_program* p, tsb_program* aux);
 
 /* Optional pattern cache (no reference counterpart): tabulate |E_k(pattern, prefix)| for every
  * selected-f pattern of weight <= max_weight (0, 1 or 2; -1 switches the cache off) with the sampling kernel's own

@@ -1,0 +1,169 @@
+"""Pure-Python model of the MODE_SLICED device evaluation (bit-sliced over an arbitrary number of shots).
+
+Words are Python integers with one bit per shot, so the model follows the kernel's plane arithmetic literally
+(XOR of rows per parity, 3-plane adder for ``a``, ripple counter for ``b``, OR-plane for vanishing factors) and
+then decodes per shot exactly like the kernel's second phase.  CPU test infrastructure only.
+"""
+
+import numpy as np
+
+from fast_model import M32, PAIR, PELL, _mul, _s32
+from oracle.exact_scalar import pow2_f32, to_complex_parts
+from tsim_b200 import pack as PK
+from tsim_b200.pack_sliced import SLICED_HEADER_WORDS
+
+
+def _rot(v, a):
+    c0, c1, c2, c3 = v
+    if a & 1:
+        c0, c1, c2, c3 = c3, c0, c1, -c2
+    if a & 2:
+        c0, c1, c2, c3 = -c2, c3, c0, -c1
+    if a & 4:
+        c0, c1, c2, c3 = -c0, -c1, -c2, -c3
+    return tuple(x & M32 for x in (c0, c1, c2, c3))
+
+
+def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarray):
+    """x_bits: uint8 [N, P].  -> list over shots of ("exact", coeffs, power) / ("approx", re, im)."""
+    blob = pp.blob
+    assert pp.mode == PK.MODE_SLICED
+    N, P = x_bits.shape
+    full = (1 << N) - 1
+    one_row, zero_row = int(blob[PK.H_ONE_ROW]), int(blob[PK.H_ZERO_ROW])
+    rows = {i: int("".join("1" if x_bits[s, i] else "0" for s in reversed(range(N))) or "0", 2) for i in range(P)}
+    rows[one_row] = full
+    rows[zero_row] = 0
+    comp_row = blob[int(blob[PK.H_OFF_COMP]) + comp * PK.COMP_WORDS :]
+    lrow = int(comp_row[4]) + level
+    lvl = blob[int(blob[PK.H_OFF_LEVEL]) + lrow * PK.LEVEL_WORDS :][: PK.LEVEL_WORDS]
+    approx = bool(lvl[6] & 1)
+    p_lo = _s32(int(lvl[9]))
+    data = blob[int(blob[PK.H_OFF_DATA]) :]
+    chunks = blob[int(blob[PK.H_OFF_CHUNK]) :][: int(blob[PK.H_N_CHUNKS]) * PK.CHUNK_WORDS].reshape(-1, PK.CHUNK_WORDS)
+    S = [[0, 0, 0, 0] for _ in range(N)]
+    RE = [np.float32(0)] * N
+    IM = [np.float32(0)] * N
+    if int(lvl[0]) == 0:
+        return [("approx", np.float32(0), np.float32(0))] * N
+
+    def parity(o, n):
+        acc = 0
+        for w in range(n):
+            iw = int(data[o + w])
+            for k in range(4):
+                acc ^= rows.get((iw >> (8 * k)) & 255, 0)
+        return acc
+
+    for c in range(int(lvl[7]), int(lvl[7]) + int(lvl[8])):
+        off, _, ng, _ = (int(v) for v in chunks[c])
+        for _g in range(ng):
+            h = [int(v) for v in data[off : off + SLICED_HEADER_WORDS]]
+            n_terms, n_gen = h[0] & 0xFFFF, h[0] >> 16
+            b_base64, nb = h[1] & 0xFF, (h[1] >> 8) & 0xFF
+            A = [0, 0, 0]
+            Bp = [0] * 5
+            Z = 0
+            gen = {}
+
+            def add_a(da, p):
+                if da & 1:
+                    c0 = A[0] & p
+                    A[0] ^= p
+                    c1 = A[1] & c0
+                    A[1] ^= c0
+                    A[2] ^= c1
+                if da & 2:
+                    c1 = A[1] & p
+                    A[1] ^= p
+                    A[2] ^= c1
+                if da & 4:
+                    A[2] ^= p
+
+            def add_cnt(wd):
+                cy = wd
+                for k in range(nb):
+                    t = Bp[k] & cy
+                    Bp[k] ^= cy
+                    cy = t
+
+            o = off + SLICED_HEADER_WORDS
+            for _t in range(n_terms):
+                cw = int(data[o])
+                typ, n1, n2 = cw & 3, (cw >> 2) & 63, (cw >> 8) & 63
+                if typ == 0:
+                    p = parity(o + 1, n1)
+                    add_a((cw >> 14) & 7, p)
+                    bm, zm = (cw >> 17) & 3, (cw >> 19) & 3
+                    if bm == 1:
+                        add_cnt(p)
+                    elif bm == 2:
+                        add_cnt(~p & full)
+                    if zm == 1:
+                        Z |= p
+                    elif zm == 2:
+                        Z |= ~p & full
+                    o += 1 + n1
+                elif typ == 1:
+                    A[2] ^= parity(o + 1, n1) & parity(o + 1 + n1, n2)
+                    o += 1 + n1 + n2
+                elif typ == 2:
+                    gen[(cw >> 14) & 15] = (parity(o + 1, n1), parity(o + 1 + n1, n2))
+                    o += 1 + n1 + n2
+                else:
+                    ex = int(data[o + 1])
+                    pa, pb = parity(o + 2, n1), parity(o + 2 + n1, n2)
+                    for v, wd in enumerate((pa, pb, pa & pb)):
+                        add_a((ex >> (6 * v)) & 7, wd)
+                        db = ((ex >> (6 * v + 3)) & 7) - 3
+                        for _ in range(abs(db)):
+                            add_cnt(wd if db > 0 else (~wd & full))
+                    ztt = (ex >> 18) & 15
+                    for combo in range(4):
+                        if (ztt >> combo) & 1:
+                            wa = pa if combo & 1 else ~pa & full
+                            wb = pb if combo & 2 else ~pb & full
+                            Z |= wa & wb
+                    o += 2 + n1 + n2
+            k1, k2 = h[8:12], h[12:16]
+            for s in range(N):
+                if (Z >> s) & 1:
+                    continue
+                a = ((A[0] >> s) & 1) | (((A[1] >> s) & 1) << 1) | (((A[2] >> s) & 1) << 2)
+                cnt = sum(((Bp[k] >> s) & 1) << k for k in range(5))
+                Pb, Qb = PELL[(b_base64 + cnt) & 127]
+                v = tuple((k1[i] * Pb + k2[i] * Qb) & M32 for i in range(4))
+                v = _rot(v, a)
+                for slot in range(n_gen):
+                    ctl = (h[16 + slot // 4] >> (8 * (slot % 4))) & 63
+                    pa, pb = gen[slot]
+                    v = _mul(v, PAIR[(ctl ^ (((pa >> s) & 1) << 2) ^ (((pb >> s) & 1) << 5)) & 63])
+                if not approx:
+                    sc = 1 << h[4]
+                    S[s] = [(S[s][i] + v[i] * sc) & M32 for i in range(4)]
+                else:
+                    vc = np.array([_s32(t) for t in v], dtype=np.int32)
+                    tre, tim = to_complex_parts(vc[None, :], np.array([_s32(h[2])], np.int32))
+                    are = np.array([h[5]], np.uint32).view(np.float32)[0]
+                    aim = np.array([h[6]], np.uint32).view(np.float32)[0]
+                    with np.errstate(all="ignore"):
+                        ure = np.float32(np.float32(tre[0] * are) - np.float32(tim[0] * aim))
+                        uim = np.float32(np.float32(tre[0] * aim) + np.float32(tim[0] * are))
+                        pw = pow2_f32(np.array([_s32(h[3])]))[0]
+                        RE[s] = np.float32(RE[s] + np.float32(ure * pw))
+                        IM[s] = np.float32(IM[s] + np.float32(uim * pw))
+            off += h[7]
+    out = []
+    for s in range(N):
+        if approx:
+            out.append(("approx", RE[s], IM[s]))
+            continue
+        cs = [_s32(v) for v in S[s]]
+        p = p_lo
+        t = (cs[0] | cs[1] | cs[2] | cs[3]) & M32
+        if t:
+            sh = (t & -t).bit_length() - 1
+            cs = [v >> sh for v in cs]
+            p += sh
+        out.append(("exact", np.array(cs, np.int32), p))
+    return out

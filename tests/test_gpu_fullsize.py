@@ -10,12 +10,12 @@ from tsim_b200.synthetic import noise_probs, synthetic_program
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def cfg2():
+@pytest.fixture(scope="module", params=["fast", "sliced"])
+def cfg2(request):
     from tsim_b200.backend import DeviceProgram
 
     prog = synthetic_program("cfg2_distill35")
-    return prog, DeviceProgram(prog, mode="auto")
+    return prog, DeviceProgram(prog, mode=request.param)
 
 
 def test_million_shots_deterministic_sharded_and_spot_checked(cfg2):
@@ -59,12 +59,13 @@ def test_byte_and_packed_interfaces_agree_at_size(cfg2):
     assert np.array_equal(np.packbits(bits, axis=1, bitorder="little"), packed.view(np.uint8)[:, : (prog.num_outputs + 7) // 8])
 
 
+@pytest.mark.parametrize("mode", ["fast", "sliced"])
 @pytest.mark.parametrize("name,B", [("cfg4_cultivation_d3", 4096), ("cfg5_distill85", 4096), ("cfg3_surface_d5", 200_000)])
-def test_other_baseline_configs_match_oracle(name, B):
+def test_other_baseline_configs_match_oracle(name, B, mode):
     from tsim_b200.backend import DeviceProgram
 
     prog = synthetic_program(name)
-    dp = DeviceProgram(prog, mode="auto")
+    dp = DeviceProgram(prog, mode=mode)
     f = ChannelSampler.from_bit_probs(noise_probs(prog.infer_num_f()), seed=3).sample(B)
     got, dev = dp.sample(f, (1, 1))
     n = min(B, 1024)

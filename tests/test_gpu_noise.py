@@ -67,7 +67,7 @@ def test_rows_are_a_function_of_seed_call_and_shot_index():
     assert not (full[:, 2] >> np.uint64(130 - 128)).any()
 
 
-@pytest.mark.parametrize("mode", ["fast", "faithful"])
+@pytest.mark.parametrize("mode", ["fast", "faithful", "sliced"])
 def test_fused_pipeline_is_bit_exact_given_its_own_f_rows(mode):
     from tsim_b200.backend import DeviceProgram
 

@@ -15,7 +15,7 @@ from tsim_b200.synthetic import noise_probs, random_level, synthetic_component, 
 
 pytestmark = pytest.mark.gpu
 
-MODES = ("faithful", "fast")
+MODES = ("faithful", "fast", "sliced")
 
 
 def _device_program(prog, mode, **kw):
@@ -134,7 +134,7 @@ def test_cfg2_shape_matches_oracle_resident_and_streamed(mode, monkeypatch):
     gotp, _ = dp.sample(pack_f_rows(f), key, packed_out=True)
     assert np.array_equal(np.unpackbits(gotp.view(np.uint8), axis=1, bitorder="little", count=prog.num_outputs).astype(bool), want)
     # same program through the streamed path (shared memory capped -> chunk ring)
-    monkeypatch.setenv("TSIM_B200_SMEM_LIMIT", str(64 * 1024))
+    monkeypatch.setenv("TSIM_B200_SMEM_LIMIT", str((140 if mode == "sliced" else 64) * 1024))
     dps = _device_program(prog, mode)
     assert dps.info["resident"] == 0
     got2, dev2 = dps.sample(f, key)

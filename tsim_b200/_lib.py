@@ -36,6 +36,7 @@ EXPORTS = (
     "tsb_noise_sample_host",
     "tsb_sample_noisy_host",
     "tsb_program_set_pattern_cache",
+    "tsb_program_set_aux",
 )
 
 
@@ -116,6 +117,8 @@ def load() -> C.CDLL:
     lib.tsb_noise_sample_host.argtypes = [vp, i64, i64, u64, u64, i32, vp]
     lib.tsb_sample_noisy_host.restype = i32
     lib.tsb_sample_noisy_host.argtypes = [vp, vp, i64, i64, u32, u32, u64, u64, i32, vp, i32, vp, vp]
+    lib.tsb_program_set_aux.restype = i32
+    lib.tsb_program_set_aux.argtypes = [vp, vp]
     lib.tsb_program_set_pattern_cache.restype = i32
     lib.tsb_program_set_pattern_cache.argtypes = [vp, i32, i64, C.POINTER(i64)]
     _lib = lib

@@ -9,7 +9,7 @@ from typing import Any
 import numpy as np
 
 from . import _lib
-from .pack import PackedProgram, pack_program
+from .pack import MODE_SLICED, PackedProgram, pack_program
 from .program import CompiledProgram, from_tsim
 
 
@@ -98,6 +98,11 @@ class DeviceProgram:
     """A compiled program uploaded to one GPU (``tsb_program`` handle)."""
 
     def __init__(self, program: CompiledProgram | PackedProgram | Any, *, device: int = 0, mode: str = "auto", joint: bool = False):
+        lib = _lib.load()
+        self._lib = lib
+        self.device = int(device)
+        self.pattern_cache = None
+        self._aux = None
         if isinstance(program, PackedProgram):
             packed = program
             self.program = None
@@ -106,18 +111,22 @@ class DeviceProgram:
             packed = pack_program(self.program, mode=mode, joint=joint)
         self.packed = packed
         self.joint = bool(packed.stats.get("joint", joint))
-        lib = _lib.load()
-        self._lib = lib
-        blob = np.ascontiguousarray(packed.blob, dtype=np.uint32)
-        handle = C.c_void_p()
-        _lib.check(lib.tsb_program_create(blob.ctypes.data_as(C.c_void_p), blob.size, int(device), C.byref(handle)))
-        self._h = handle
-        self._fin = weakref.finalize(self, lib.tsb_program_destroy, handle)
+        self._h, self._fin = self._create(packed)
+        if packed.mode == MODE_SLICED:
+            if self.program is None:
+                raise ValueError("a sliced program needs the CompiledProgram to build its per-row companion")
+            # companion per-row program: normalisation check of shot 0, evaluate(), pattern cache
+            self._aux = DeviceProgram(self.program, device=device, mode="auto" if mode == "sliced" else "faithful")
+            _lib.check(lib.tsb_program_set_aux(self._h, self._aux._h))
         info = _lib.TsbInfo()
         _lib.check(lib.tsb_program_info(self._h, C.byref(info)))
         self.info = info.as_dict()
-        self.device = int(device)
-        self.pattern_cache = None
+
+    def _create(self, packed: PackedProgram):
+        blob = np.ascontiguousarray(packed.blob, dtype=np.uint32)
+        handle = C.c_void_p()
+        _lib.check(self._lib.tsb_program_create(blob.ctypes.data_as(C.c_void_p), blob.size, self.device, C.byref(handle)))
+        return handle, weakref.finalize(self, self._lib.tsb_program_destroy, handle)
 
     # ---------------------------------------------------------------------------------------
     @property
@@ -131,6 +140,8 @@ class DeviceProgram:
     def set_pattern_cache(self, max_weight: int | None, max_entries: int = 0) -> int:
         """Tabulate the probability trees of all selected-f patterns of weight <= ``max_weight`` (0, 1, 2;
         ``None`` switches the cache off).  Purely a speed-up: sampled bits do not change.  Returns the table size."""
+        if self._aux is not None and max_weight is not None:
+            raise NotImplementedError("tsim_b200: the pattern cache works with per-row programs (mode='fast' or 'faithful')")
         n = C.c_int64(0)
         _lib.check(self._lib.tsb_program_set_pattern_cache(self._h, -1 if max_weight is None else int(max_weight), int(max_entries), C.byref(n)))
         self.pattern_cache = max_weight

@@ -13,6 +13,7 @@
 #include "blob.h"
 #include "noise_kernels.cuh"
 #include "sampler_kernels.cuh"
+#include "sliced_kernels.cuh"
 
 namespace tsb {
 
@@ -472,6 +473,8 @@ struct Slot {
   uint8_t* d_out_bytes = nullptr;
   uint32_t* d_subkeys = nullptr;
   uint32_t* d_heavy = nullptr;  // [cap + 1]: count, then row indices (pattern-cache pass 2)
+  uint32_t* d_xt = nullptr;     // sliced mode: transposed parameters [total_F][cap/32]
+  uint32_t* d_ot = nullptr;     // sliced mode: bit-sliced outputs [n_draws][cap/32]
   long long cap = 0;
   bool timed = false;
 };
@@ -499,6 +502,12 @@ struct tsb_program {
   long long cache_entries = 0;
   uint32_t* d_heavy = nullptr;  // for tsb_sample_device
   long long heavy_cap = 0;
+  // MODE_SLICED
+  int is_sliced = 0, s_has_exact = 0, s_rows = 0, s_xt_off = 0, s_pw_off = 0, total_F = 0, max_nc = 0;
+  tsb_program* aux = nullptr;   // companion per-row program (norm check); not owned
+  uint32_t* d_xt = nullptr;     // scratch for tsb_sample_device
+  uint32_t* d_ot = nullptr;
+  long long scratch_slabs = 0;
 };
 
 const char* tsb_last_error(void) { return g_err.c_str(); }
@@ -521,7 +530,7 @@ static int validate_blob(const uint32_t* b, size_t n) {
   if (b[H_MAGIC] != kMagic) return fail(TSB_ERR_INVALID, "bad magic");
   if (b[H_VERSION] != kVersion) return fail(TSB_ERR_INVALID, "blob version mismatch");
   if (b[H_TOTAL_WORDS] != n) return fail(TSB_ERR_INVALID, "blob size does not match header");
-  if (b[H_MODE] > 1u) return fail(TSB_ERR_INVALID, "unknown mode");
+  if (b[H_MODE] > 2u) return fail(TSB_ERR_INVALID, "unknown mode");
   if (b[H_W] < 1u) return fail(TSB_ERR_INVALID, "W must be >= 1");
   const uint32_t offs[] = {b[H_OFF_DIRECT], b[H_OFF_COMP], b[H_OFF_LEVEL], b[H_OFF_CHUNK], b[H_OFF_FSEL], b[H_OFF_DEST], b[H_OFF_DATA]};
   for (uint32_t o : offs)
@@ -578,7 +587,8 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
   int rc = validate_blob(blob, n_words);
   if (rc) return rc;
   const int W = (int)blob[H_W], mode = (int)blob[H_MODE];
-  if (!sample_fn(mode, W)) return fail(TSB_ERR_UNSUPPORTED, "more than 256 parameters per component level (W > 8) is not built");
+  if (mode != kModeSliced && !sample_fn(mode, W))
+    return fail(TSB_ERR_UNSUPPORTED, "more than 256 parameters per component level (W > 8) is not built");
   int ndev = 0;
   CU(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(TSB_ERR_INVALID, "no such CUDA device");
@@ -613,6 +623,21 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
   // shared-memory plan
   const int wf32 = 2 * (int)blob[H_WF64], wout32 = 2 * (int)blob[H_WOUT64];
   int fixed_words = kBarWords + (int)(sizeof(Tables) / 4) + (wf32 + wout32) * kThreads;
+  if (mode == kModeSliced) {
+    p->is_sliced = 1;
+    p->s_rows = (int)blob[H_ZERO_ROW] + 1;
+    p->s_xt_off = (kBarWords + (int)(sizeof(SlicedTables) / 4) + 31) & ~31;
+    p->s_pw_off = p->s_xt_off + p->s_rows * kSlicedThreads;
+    fixed_words = p->s_pw_off + 2 * kMaxGeneralPairs * kSlicedThreads;
+    const uint32_t* lv = blob + blob[H_OFF_LEVEL];
+    for (uint32_t i = 0; i < blob[H_N_LEVELS]; ++i)
+      if (!(lv[i * kLevelWords + L_FLAGS] & 1u) && lv[i * kLevelWords + L_G] > 0u) p->s_has_exact = 1;
+    const uint32_t* ct = blob + blob[H_OFF_COMP];
+    for (int c = 0; c < n_comp; ++c) {
+      p->total_F += (int)ct[c * kCompWords + C_F];
+      p->max_nc = std::max(p->max_nc, (int)ct[c * kCompWords + C_NC]);
+    }
+  }
   fixed_words = (fixed_words + 31) & ~31;  // 128-byte align the data region
   int max_smem = (int)prop.sharedMemPerBlockOptin;
   if (const char* lim = getenv("TSIM_B200_SMEM_LIMIT")) {  // test knob: force the streamed path on small programs
@@ -639,14 +664,19 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
   }
   p->smem_data_off = fixed_words;
   const int smem_bytes = (int)((fixed_words + used) * 4);
-  CUB(cudaFuncSetAttribute((const void*)sample_fn(mode, W), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  if (mode == kModeSliced) {
+    CUB(cudaFuncSetAttribute((const void*)sample_sliced_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CUB(cudaFuncSetAttribute((const void*)sample_sliced_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  } else {
+    CUB(cudaFuncSetAttribute((const void*)sample_fn(mode, W), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  }
 
   tsb_info& in = p->info;
   in.mode = mode; in.words = W; in.num_f = (int)blob[H_NUM_F]; in.num_outputs = (int)blob[H_N_OUT];
   in.n_direct = (int)blob[H_N_DIRECT]; in.n_components = n_comp; in.n_draws = n_draws;
   in.words_f64 = (int)blob[H_WF64]; in.words_out64 = (int)blob[H_WOUT64];
   in.resident = resident; in.n_chunks = (int)blob[H_N_CHUNKS]; in.smem_bytes = smem_bytes;
-  in.threads = kThreads; in.grid = p->sm_count; in.data_bytes = data_words * 4;
+  in.threads = mode == kModeSliced ? kSlicedThreads : kThreads; in.grid = p->sm_count; in.data_bytes = data_words * 4;
 #undef CUB
   *out = p;
   return TSB_OK;
@@ -659,6 +689,8 @@ static void free_slot(Slot& s) {
   if (s.d_out_bytes) cudaFree(s.d_out_bytes);
   if (s.d_subkeys) cudaFree(s.d_subkeys);
   if (s.d_heavy) cudaFree(s.d_heavy);
+  if (s.d_xt) cudaFree(s.d_xt);
+  if (s.d_ot) cudaFree(s.d_ot);
   if (s.k_start) cudaEventDestroy(s.k_start);
   if (s.k_stop) cudaEventDestroy(s.k_stop);
   if (s.stream) cudaStreamDestroy(s.stream);
@@ -677,6 +709,8 @@ int tsb_program_destroy(tsb_program* p) {
   if (p->d_cache) cudaFree(p->d_cache);
   if (p->d_cache_meta) cudaFree(p->d_cache_meta);
   if (p->d_heavy) cudaFree(p->d_heavy);
+  if (p->d_xt) cudaFree(p->d_xt);
+  if (p->d_ot) cudaFree(p->d_ot);
   if (p->ev_a) cudaEventDestroy(p->ev_a);
   if (p->ev_b) cudaEventDestroy(p->ev_b);
   if (p->stream) cudaStreamDestroy(p->stream);
@@ -714,6 +748,7 @@ static int launch_sample(tsb_program* p, const uint64_t* d_f, long long B, long 
                          uint64_t* d_out, float* d_norm_dev, cudaStream_t st, uint32_t* heavy_rows = nullptr,
                          uint32_t* heavy_count = nullptr) {
   if (B <= 0) return TSB_OK;
+  if (p->is_sliced) return fail(TSB_ERR_INVALID, "internal: sliced programs go through launch_sliced");
   if (p->cache_wmax < 0 || !heavy_rows) return launch_sample_rows(p, d_f, B, shot_offset, d_subkeys, d_out, d_norm_dev, st, nullptr, nullptr);
   int rc = launch_light(p, d_f, B, shot_offset, d_subkeys, d_out, heavy_rows, heavy_count, st);
   if (rc) return rc;
@@ -752,6 +787,7 @@ static CacheFn cache_fn_for(int W) {
 int tsb_program_set_pattern_cache(tsb_program* p, int max_weight, int64_t max_entries, int64_t* entries_out) {
   if (!p) return fail(TSB_ERR_INVALID, "null handle");
   if (max_weight > 2) return fail(TSB_ERR_INVALID, "pattern cache supports weights 0, 1 and 2");
+  if (p->is_sliced && max_weight >= 0) return fail(TSB_ERR_UNSUPPORTED, "the pattern cache works with per-row (fast / faithful) programs");
   CU(cudaSetDevice(p->device));
   CU(cudaDeviceSynchronize());
   if (p->d_cache) cudaFree(p->d_cache);
@@ -804,6 +840,72 @@ int tsb_program_set_pattern_cache(tsb_program* p, int max_weight, int64_t max_en
   return TSB_OK;
 }
 
+
+typedef void (*NormFn)(const uint32_t*, const uint64_t*, const uint64_t*, float*);
+template <int MODE>
+static NormFn norm_fn_for(int W) {
+  switch (W) {
+    case 1: return norm_check_kernel<1, MODE>;
+    case 2: return norm_check_kernel<2, MODE>;
+    case 3: return norm_check_kernel<3, MODE>;
+    case 4: return norm_check_kernel<4, MODE>;
+    case 5: return norm_check_kernel<5, MODE>;
+    case 6: return norm_check_kernel<6, MODE>;
+    case 7: return norm_check_kernel<7, MODE>;
+    case 8: return norm_check_kernel<8, MODE>;
+    default: return nullptr;
+  }
+}
+
+// K0t -> K1s -> K2a -> K1c on one stream
+static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long long shot_offset, const uint32_t* d_subkeys,
+                         uint64_t* d_out, float* d_norm_dev, cudaStream_t st, uint32_t* d_xt, uint32_t* d_ot, long long slab_cap) {
+  if (B <= 0) return TSB_OK;
+  const tsb_info& in = p->info;
+  const int n_slabs = (int)((B + 31) / 32);
+  if (n_slabs > slab_cap) return fail(TSB_ERR_INVALID, "internal: sliced scratch too small");
+  const unsigned tblocks = (unsigned)(((long long)n_slabs * 32 + 255) / 256);
+  if (p->total_F > 0) {
+    transpose_in_kernel<<<tblocks, 256, 0, st>>>(p->d_blob, d_f, B, n_slabs, (int)slab_cap, d_xt);
+    CU(cudaGetLastError());
+  }
+  if (in.n_draws > 0) {
+    SParams k;
+    k.blob = p->d_blob; k.xt = d_xt; k.ot = d_ot; k.subkeys = d_subkeys; k.B = B; k.shot_offset = shot_offset;
+    k.n_slabs = n_slabs; k.slab_cap = (int)slab_cap;
+    const int grid = std::max(1, std::min(p->sm_count, (n_slabs + 31) / 32));
+    k.rounds = (n_slabs + grid * kSlicedThreads - 1) / (grid * kSlicedThreads);
+    k.per_cta = (n_slabs + grid * k.rounds - 1) / (grid * k.rounds);
+    k.resident = in.resident; k.n_stages = p->n_stages; k.stage_words = p->stage_words;
+    k.smem_xt_off = p->s_xt_off; k.smem_pw_off = p->s_pw_off; k.smem_data_off = p->smem_data_off; k.rows = p->s_rows;
+    if (p->s_has_exact) sample_sliced_kernel<true><<<grid, kSlicedThreads, in.smem_bytes, st>>>(k);
+    else sample_sliced_kernel<false><<<grid, kSlicedThreads, in.smem_bytes, st>>>(k);
+    CU(cudaGetLastError());
+  }
+  assemble_out_kernel<<<tblocks, 256, 0, st>>>(p->d_blob, d_f, d_ot, B, n_slabs, (int)slab_cap, d_out);
+  CU(cudaGetLastError());
+  if (shot_offset == 0 && in.n_components > 0 && p->aux) {
+    const tsb_program* a = p->aux;
+    NormFn fn = a->info.mode == kModeFast ? norm_fn_for<kModeFast>(a->info.words) : norm_fn_for<kModeFaithful>(a->info.words);
+    fn<<<in.n_components, 128, (2 * p->max_nc + 1) * sizeof(float), st>>>(a->d_blob, d_f, d_out, d_norm_dev);
+    CU(cudaGetLastError());
+  }
+  return TSB_OK;
+}
+
+int tsb_program_set_aux(tsb_program* p, tsb_program* aux) {
+  if (!p) return fail(TSB_ERR_INVALID, "null handle");
+  if (aux) {
+    if (aux->is_sliced) return fail(TSB_ERR_INVALID, "the companion program must be a per-row (fast or faithful) program");
+    if (aux->device != p->device) return fail(TSB_ERR_INVALID, "companion program lives on another device");
+    const tsb_info &a = aux->info, &b = p->info;
+    if (a.num_f != b.num_f || a.num_outputs != b.num_outputs || a.n_components != b.n_components || a.n_draws != b.n_draws)
+      return fail(TSB_ERR_INVALID, "companion program does not describe the same compiled program");
+  }
+  p->aux = aux;
+  return TSB_OK;
+}
+
 int tsb_sample_device(tsb_program* p, const uint64_t* d_f, int64_t B, int64_t shot_offset, uint32_t k0, uint32_t k1,
                       uint64_t* d_out, float* d_norm_dev, void* stream) {
   if (!p) return fail(TSB_ERR_INVALID, "null handle");
@@ -815,6 +917,24 @@ int tsb_sample_device(tsb_program* p, const uint64_t* d_f, int64_t B, int64_t sh
   if (B > 0) {
     derive_subkeys_kernel<<<1, 32, 0, st>>>(k0, k1, p->info.n_draws, p->d_subkeys);
     CU(cudaGetLastError());
+  }
+  if (p->is_sliced) {
+    const long long slabs = (B + 31) / 32;
+    if (p->scratch_slabs < slabs) {
+      if (p->d_xt) cudaFree(p->d_xt);
+      if (p->d_ot) cudaFree(p->d_ot);
+      p->d_xt = nullptr; p->d_ot = nullptr; p->scratch_slabs = 0;
+      CU(cudaMalloc(&p->d_xt, 4 * (size_t)slabs * std::max(1, p->total_F)));
+      CU(cudaMalloc(&p->d_ot, 4 * (size_t)slabs * std::max(1, p->info.n_draws)));
+      p->scratch_slabs = slabs;
+    }
+    int rc = launch_sliced(p, d_f, B, shot_offset, p->d_subkeys, d_out, d_norm_dev ? d_norm_dev : p->d_norm_dev, st, p->d_xt,
+                           p->d_ot, p->scratch_slabs);
+    if (rc) return rc;
+    CU(cudaEventRecord(p->ev_b, st));
+    p->last_launches = B > 0 ? 5 : 0;
+    p->last_ms = -1.f;
+    return TSB_OK;
   }
   if (p->cache_wmax >= 0 && p->heavy_cap < B) {
     if (p->d_heavy) cudaFree(p->d_heavy);
@@ -858,12 +978,20 @@ static int ensure_slot(tsb_program* p, Slot& s, long long cap) {
   if (s.d_out) cudaFree(s.d_out);
   if (s.d_out_bytes) cudaFree(s.d_out_bytes);
   if (s.d_heavy) cudaFree(s.d_heavy);
-  s.d_in_bytes = nullptr; s.d_f = nullptr; s.d_out = nullptr; s.d_out_bytes = nullptr; s.d_heavy = nullptr; s.cap = 0;
+  if (s.d_xt) cudaFree(s.d_xt);
+  if (s.d_ot) cudaFree(s.d_ot);
+  s.d_in_bytes = nullptr; s.d_f = nullptr; s.d_out = nullptr; s.d_out_bytes = nullptr; s.d_heavy = nullptr;
+  s.d_xt = nullptr; s.d_ot = nullptr; s.cap = 0;
   CU(cudaMalloc(&s.d_in_bytes, (size_t)cap * std::max(1, in.num_f)));
   CU(cudaMalloc(&s.d_f, (size_t)cap * in.words_f64 * 8));
   CU(cudaMalloc(&s.d_out, (size_t)cap * in.words_out64 * 8));
   CU(cudaMalloc(&s.d_out_bytes, (size_t)cap * std::max(1, in.num_outputs)));
   CU(cudaMalloc(&s.d_heavy, 4 * ((size_t)cap + 1)));
+  if (p->is_sliced) {
+    const size_t slabs = (size_t)((cap + 31) / 32);
+    CU(cudaMalloc(&s.d_xt, 4 * slabs * (size_t)std::max(1, p->total_F)));
+    CU(cudaMalloc(&s.d_ot, 4 * slabs * (size_t)std::max(1, in.n_draws)));
+  }
   s.cap = cap;
   return TSB_OK;
 }
@@ -940,7 +1068,8 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
       CU(cudaMemcpyAsync(s.d_f, src, (size_t)n * in_row, cudaMemcpyHostToDevice, s.stream));
     }
     CU(cudaEventRecord(s.k_start, s.stream));
-    rc = launch_sample(p, s.d_f, n, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream, s.d_heavy + 1, s.d_heavy);
+    rc = p->is_sliced ? launch_sliced(p, s.d_f, n, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream, s.d_xt, s.d_ot, (s.cap + 31) / 32)
+                      : launch_sample(p, s.d_f, n, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream, s.d_heavy + 1, s.d_heavy);
     if (rc) return rc;
     CU(cudaEventRecord(s.k_stop, s.stream));
     s.timed = true;
@@ -974,6 +1103,10 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
 
 int tsb_evaluate_host(tsb_program* p, int component, int level, const uint8_t* params, int64_t B, float* amp) {
   if (!p) return fail(TSB_ERR_INVALID, "null handle");
+  if (p->is_sliced) {
+    if (!p->aux) return fail(TSB_ERR_UNSUPPORTED, "a sliced program evaluates rows through its companion program (tsb_program_set_aux)");
+    return tsb_evaluate_host(p->aux, component, level, params, B, amp);
+  }
   const uint32_t* b = p->host_blob.data();
   if (component < 0 || component >= (int)b[H_N_COMP]) return fail(TSB_ERR_INVALID, "component out of range");
   const uint32_t* comp = b + b[H_OFF_COMP] + component * kCompWords;
@@ -1184,7 +1317,8 @@ int tsb_sample_noisy_host(tsb_program* p, tsb_noise* n, int64_t B, int64_t shot_
     derive_subkeys_kernel<<<1, 32, 0, s.stream>>>(k0, k1, in.n_draws, s.d_subkeys);
     CU(cudaGetLastError());
     CU(cudaEventRecord(s.k_start, s.stream));
-    rc = launch_sample(p, s.d_f, cnt, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream, s.d_heavy + 1, s.d_heavy);
+    rc = p->is_sliced ? launch_sliced(p, s.d_f, cnt, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream, s.d_xt, s.d_ot, (s.cap + 31) / 32)
+                      : launch_sample(p, s.d_f, cnt, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream, s.d_heavy + 1, s.d_heavy);
     if (rc) return rc;
     CU(cudaEventRecord(s.k_stop, s.stream));
     s.timed = true;

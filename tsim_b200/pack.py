@@ -36,6 +36,7 @@ MAGIC = 0x32425354  # "TSB2"
 VERSION = 3
 MODE_FAITHFUL = 0
 MODE_FAST = 1
+MODE_SLICED = 2
 
 HEADER_WORDS = 32
 COMP_WORDS = 8
@@ -51,6 +52,7 @@ H_OFF_DIRECT, H_OFF_COMP, H_OFF_LEVEL, H_OFF_CHUNK = 12, 13, 14, 15
 H_OFF_FSEL, H_OFF_DEST, H_OFF_DATA, H_DATA_WORDS = 16, 17, 18, 19
 H_TOTAL_WORDS, H_WF64, H_WOUT64, H_OFF_TABLES = 20, 21, 22, 23
 H_TABLE_WORDS = 24
+H_ONE_ROW, H_ZERO_ROW = 25, 26
 
 
 @dataclass
@@ -228,12 +230,12 @@ def pack_program(
         mode_id = MODE_FAITHFUL
     elif mode in ("faithful", MODE_FAITHFUL):
         mode_id = MODE_FAITHFUL
-    elif mode in ("fast", MODE_FAST):
+    elif mode in ("fast", MODE_FAST, "sliced", MODE_SLICED):
         if not exact_ok:
             raise ValueError(
                 f"fast mode is not provably exact for this program (log2 bound {bound_info['log2_bound']:.1f} >= 30.5)"
             )
-        mode_id = MODE_FAST
+        mode_id = MODE_SLICED if mode in ("sliced", MODE_SLICED) else MODE_FAST
     else:
         raise ValueError(f"unknown mode {mode!r}")
 
@@ -247,6 +249,8 @@ def pack_program(
 
     # parameter words per shot: widest level over all components (+1 constant-one bit in fast mode)
     extra = 1 if mode_id == MODE_FAST else 0
+    if joint and mode_id == MODE_SLICED:
+        raise ValueError("joint-mode programs are evaluated per row: use the fast or faithful records")
     max_p = 0
     for c in comps:
         for lv in c.compiled_scalar_graphs:
@@ -299,6 +303,10 @@ def pack_program(
                 C, D = lv.pi_products.psi_const.shape[1], lv.phase_pairs.alpha.shape[1]
                 graph_lists = [recs[g] for g in range(lv.num_graphs)]
                 p_lo = 0
+            elif mode_id == MODE_SLICED:
+                from .pack_sliced import sliced_level_records
+
+                graph_lists, (A, H, C, D), p_lo = sliced_level_records(lv, max_p, max_p + 1)
             else:
                 from .pack_fast import fast_level_records  # local import: keeps this module lean
 
@@ -364,6 +372,8 @@ def pack_program(
     header[H_MAX_CHUNK] = int(chunk_tab[:, 1].max()) if len(chunk_rows) else 0
     header[H_WF64] = max(1, (num_f + 63) // 64)
     header[H_WOUT64] = max(1, (n_out + 63) // 64)
+    header[H_ONE_ROW] = max_p
+    header[H_ZERO_ROW] = max_p + 1
 
     blob = np.zeros(total, dtype=np.uint32)
     blob[:HEADER_WORDS] = header

@@ -311,7 +311,7 @@ def run_gpu(args):
         det_dev = S.CompiledDetectorSampler(prog, DeviceChannelSampler.from_bit_probs(q, seed=1, device=local), seed=2)
         extras["sample_api_host_noise_shots_per_s"] = shots / timed(lambda: det_host.sample(shots, batch_size=shots, bit_packed=True), 2)
         extras["sample_api_device_noise_shots_per_s"] = shots / timed(lambda: det_dev.sample(shots, batch_size=shots, bit_packed=True))
-        for wmax in (0, 1, 2):
+        for wmax in ((0, 1, 2) if info["mode"] != 2 else ()):
             entries = dp.set_pattern_cache(wmax)
             ev = []
             for i in range(5):
@@ -330,9 +330,10 @@ def run_gpu(args):
                 "device_shots_per_s": shots / (float(np.mean(ev[1:])) * 1e-3),
                 "e2e_shots_per_s": shots / t,
             }
-        det_dev._device_program.set_pattern_cache(2)
-        extras["sample_api_device_noise_cache_w2_shots_per_s"] = shots / timed(lambda: det_dev.sample(shots, batch_size=shots, bit_packed=True))
-        dp.set_pattern_cache(None)
+        if info["mode"] != 2:
+            det_dev._device_program.set_pattern_cache(2)
+            extras["sample_api_device_noise_cache_w2_shots_per_s"] = shots / timed(lambda: det_dev.sample(shots, batch_size=shots, bit_packed=True))
+            dp.set_pattern_cache(None)
         extras["note"] = ("bit-identical speed-ups outside the headline: pattern_cache tabulates the probability trees of light "
                           "f patterns; sample_api = CompiledDetectorSampler.sample(shots, bit_packed=True) including noise sampling")
 
@@ -399,7 +400,7 @@ def run_gpu(args):
             "num_f": info["num_f"],
             "num_outputs": n_out,
             "stabiliser_terms": 148,
-            "kernel_mode": "fast" if info["mode"] else "faithful",
+            "kernel_mode": ("faithful", "fast", "sliced")[info["mode"]],
             "g_resident_in_smem": bool(info["resident"]),
             "l2": f"inputs/outputs rotate over {n_buf} buffer pairs ({n_buf * per_step_bytes / 1e6:.0f} MB > 126 MB L2)",
             "parallelism": f"shots sharded over {world} GPU(s), one all-gather of packed outputs per step" if world > 1 else "single GPU",
@@ -427,7 +428,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--shots", type=int, default=1_000_000)
     ap.add_argument("--cpu-shots", type=int, default=16384)
-    ap.add_argument("--mode", default="auto", choices=["auto", "fast", "faithful"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "fast", "faithful", "sliced"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()

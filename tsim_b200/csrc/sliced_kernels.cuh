@@ -20,7 +20,7 @@
 
 namespace tsb {
 
-constexpr int kSlicedThreads = 256;
+constexpr int kSlicedMaxThreads = 256;
 constexpr int kSlicedHeaderWords = 20;
 constexpr int kMaxGeneralPairs = 8;
 
@@ -40,6 +40,8 @@ struct SParams {
   int stage_words;
   int smem_xt_off;    // word offsets inside dynamic shared memory
   int smem_pw_off;
+  int smem_s_off;
+  int smem_prev_off;
   int smem_data_off;
   int rows;           // zero_row + 1
 };
@@ -118,6 +120,10 @@ __global__ void __launch_bounds__(256) assemble_out_kernel(const uint32_t* __res
 // ---------------------------------------------------------------------------------------------
 // K1s
 // ---------------------------------------------------------------------------------------------
+// Per-thread state lives in private shared-memory columns (index [row][tid], so a warp access is one conflict-free
+// wavefront): the transposed parameters xt, the parity words of general pairs pw, the per-shot level accumulators S and
+// the chain-rule state prev.  Keeping S / prev out of registers lets the per-shot loops stay rolled: the hot loop
+// body must fit the 32 KB instruction cache (a 32x unrolled body ran at 26 % issue, stalled on instruction fetch).
 __device__ __forceinline__ void add_a3(uint32_t& A0, uint32_t& A1, uint32_t& A2, uint32_t da, uint32_t p) {
   if (da & 1u) {
     const uint32_t c0 = A0 & p;
@@ -143,30 +149,44 @@ __device__ __forceinline__ void add_cnt5(uint32_t (&Bp)[5], uint32_t w) {
   }
 }
 
-// XOR of the rows named by n index words starting at smem word offset o
-__device__ __forceinline__ uint32_t sliced_parity(const uint32_t* __restrict__ sdata, uint32_t o, int n,
-                                                  const uint32_t* __restrict__ xcol) {
-  uint32_t acc = 0;
-  for (int w = 0; w < n; ++w) {
-    const uint32_t iw = sdata[o + w];
-    const uint32_t r0 = xcol[(iw & 255u) * kSlicedThreads], r1 = xcol[((iw >> 8) & 255u) * kSlicedThreads];
-    const uint32_t r2 = xcol[((iw >> 16) & 255u) * kSlicedThreads], r3 = xcol[(iw >> 24) * kSlicedThreads];
-    acc ^= r0 ^ r1;
-    acc ^= r2 ^ r3;
-  }
-  return acc;
+// XOR of the rows named by n index words starting at smem word offset o.  xbytes = byte address (shared window) of
+// this thread's column; row r sits at xbytes + r * 4T.
+template <int T>
+__device__ __forceinline__ uint32_t ld_row(uint32_t xbytes, uint32_t row) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(xbytes + row * (uint32_t)(4 * T)));
+  return v;
 }
 
-template <bool HAS_EXACT>
-struct SlabAcc {
-  // exact: four int32 coefficients per shot; approximate: (re, im) per shot in the first two
-  uint32_t v[32][HAS_EXACT ? 4 : 2];
-};
+template <int T>
+__device__ __forceinline__ uint32_t sliced_parity(const uint32_t* __restrict__ sdata, uint32_t o, int n, uint32_t xbytes) {
+  uint32_t acc0 = 0, acc1 = 0;
+  int w = 0;
+  for (; w + 1 < n; w += 2) {
+    const uint32_t i0 = sdata[o + w], i1 = sdata[o + w + 1];
+    const uint32_t a0 = ld_row<T>(xbytes, i0 & 255u), a1 = ld_row<T>(xbytes, __byte_perm(i0, 0, 0x4441));
+    const uint32_t a2 = ld_row<T>(xbytes, __byte_perm(i0, 0, 0x4442)), a3 = ld_row<T>(xbytes, i0 >> 24);
+    const uint32_t b0 = ld_row<T>(xbytes, i1 & 255u), b1 = ld_row<T>(xbytes, __byte_perm(i1, 0, 0x4441));
+    const uint32_t b2 = ld_row<T>(xbytes, __byte_perm(i1, 0, 0x4442)), b3 = ld_row<T>(xbytes, i1 >> 24);
+    acc0 ^= a0 ^ a1;
+    acc1 ^= b0 ^ b1;
+    acc0 ^= a2 ^ a3;
+    acc1 ^= b2 ^ b3;
+  }
+  if (w < n) {
+    const uint32_t i0 = sdata[o + w];
+    const uint32_t a0 = ld_row<T>(xbytes, i0 & 255u), a1 = ld_row<T>(xbytes, __byte_perm(i0, 0, 0x4441));
+    const uint32_t a2 = ld_row<T>(xbytes, __byte_perm(i0, 0, 0x4442)), a3 = ld_row<T>(xbytes, i0 >> 24);
+    acc0 ^= a0 ^ a1;
+    acc1 ^= a2 ^ a3;
+  }
+  return acc0 ^ acc1;
+}
 
-template <bool HAS_EXACT>
+template <int T, bool HAS_EXACT>
 __device__ __forceinline__ void sliced_graphs(const uint32_t* __restrict__ sdata, uint32_t off, int n_graphs, bool approx,
-                                              const uint32_t* __restrict__ xcol, uint32_t* __restrict__ pwcol,
-                                              const SlicedTables* __restrict__ tb, SlabAcc<HAS_EXACT>& S) {
+                                              uint32_t xbytes, uint32_t* __restrict__ pwcol, uint32_t* __restrict__ scol,
+                                              const SlicedTables* __restrict__ tb) {
   for (int g = 0; g < n_graphs; ++g) {
     const uint4 h0 = *reinterpret_cast<const uint4*>(sdata + off);
     const uint4 h1 = *reinterpret_cast<const uint4*>(sdata + off + 4);
@@ -181,26 +201,26 @@ __device__ __forceinline__ void sliced_graphs(const uint32_t* __restrict__ sdata
       const uint32_t type = cw & 3u;
       const int n1 = (int)((cw >> 2) & 63u), n2 = (int)((cw >> 8) & 63u);
       if (type == 0u) {
-        const uint32_t p = sliced_parity(sdata, o + 1, n1, xcol);
+        const uint32_t p = sliced_parity<T>(sdata, o + 1, n1, xbytes);
         add_a3(A0, A1, A2, (cw >> 14) & 7u, p);
         const uint32_t bm = (cw >> 17) & 3u, zm = (cw >> 19) & 3u;
         if (bm) add_cnt5(Bp, bm == 1u ? p : ~p);
         if (zm) Z |= (zm == 1u ? p : ~p);
         o += 1 + n1;
       } else if (type == 1u) {
-        const uint32_t p1 = sliced_parity(sdata, o + 1, n1, xcol);
-        const uint32_t p2 = sliced_parity(sdata, o + 1 + n1, n2, xcol);
+        const uint32_t p1 = sliced_parity<T>(sdata, o + 1, n1, xbytes);
+        const uint32_t p2 = sliced_parity<T>(sdata, o + 1 + n1, n2, xbytes);
         A2 ^= p1 & p2;
         o += 1 + n1 + n2;
       } else if (type == 2u) {
         const uint32_t slot = (cw >> 14) & 15u;
-        pwcol[(2 * slot) * kSlicedThreads] = sliced_parity(sdata, o + 1, n1, xcol);
-        pwcol[(2 * slot + 1) * kSlicedThreads] = sliced_parity(sdata, o + 1 + n1, n2, xcol);
+        pwcol[(2 * slot) * T] = sliced_parity<T>(sdata, o + 1, n1, xbytes);
+        pwcol[(2 * slot + 1) * T] = sliced_parity<T>(sdata, o + 1 + n1, n2, xbytes);
         o += 1 + n1 + n2;
       } else {
         const uint32_t ex = sdata[o + 1];
-        const uint32_t pa = sliced_parity(sdata, o + 2, n1, xcol);
-        const uint32_t pb = sliced_parity(sdata, o + 2 + n1, n2, xcol);
+        const uint32_t pa = sliced_parity<T>(sdata, o + 2, n1, xbytes);
+        const uint32_t pb = sliced_parity<T>(sdata, o + 2 + n1, n2, xbytes);
         const uint32_t wd[3] = {pa, pb, pa & pb};
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
@@ -217,14 +237,15 @@ __device__ __forceinline__ void sliced_graphs(const uint32_t* __restrict__ sdata
         o += 2 + n1 + n2;
       }
     }
-    // ---- phase 2: per-shot decode and accumulation (unrolled over the slab)
+    // ---- phase 2: per-shot decode and accumulation
     const uint4 k1 = *reinterpret_cast<const uint4*>(sdata + off + 8);
     const uint4 k2 = *reinterpret_cast<const uint4*>(sdata + off + 12);
     const uint2 ctlw = *reinterpret_cast<const uint2*>(sdata + off + 16);
     const float are = __uint_as_float(h1.y), aim = __uint_as_float(h1.z);
     const float sc = pow2_f32((int)h0.z), pw = pow2_f32((int)h0.w);
     const uint32_t fx = 1u << (h1.x & 31u);
-#pragma unroll
+    // cnt: five count planes -> one word per plane; a: three planes
+#pragma unroll 2
     for (int s = 0; s < 32; ++s) {
       if ((Z >> s) & 1u) continue;
       const uint32_t a = ((A0 >> s) & 1u) | (((A1 >> s) & 1u) << 1) | (((A2 >> s) & 1u) << 2);
@@ -236,13 +257,16 @@ __device__ __forceinline__ void sliced_graphs(const uint32_t* __restrict__ sdata
       v = zw_rotate(v, a);
       for (int slot = 0; slot < n_gen; ++slot) {
         const uint32_t ctl = ((slot < 4 ? ctlw.x : ctlw.y) >> (8 * (slot & 3))) & 63u;
-        const uint32_t pa = (pwcol[(2 * slot) * kSlicedThreads] >> s) & 1u;
-        const uint32_t pb = (pwcol[(2 * slot + 1) * kSlicedThreads] >> s) & 1u;
+        const uint32_t pa = (pwcol[(2 * slot) * T] >> s) & 1u;
+        const uint32_t pb = (pwcol[(2 * slot + 1) * T] >> s) & 1u;
         v = zw_mul(v, zw_from(tb->pair[(ctl ^ (pa << 2) ^ (pb << 5)) & 63u]));
       }
       if (!approx) {
         if constexpr (HAS_EXACT) {
-          S.v[s][0] += v.c0 * fx; S.v[s][1] += v.c1 * fx; S.v[s][2] += v.c2 * fx; S.v[s][3] += v.c3 * fx;
+          uint4* sp = reinterpret_cast<uint4*>(scol) + s * T;
+          uint4 acc = *sp;
+          acc.x += v.c0 * fx; acc.y += v.c1 * fx; acc.z += v.c2 * fx; acc.w += v.c3 * fx;
+          *sp = acc;
         }
       } else {
         const float s2 = TSB_SQRT1_2;
@@ -253,23 +277,32 @@ __device__ __forceinline__ void sliced_graphs(const uint32_t* __restrict__ sdata
         const float tim = __fmul_rn(__fsub_rn(__fadd_rn(t1, f2), t3), sc);
         const float ure = __fsub_rn(__fmul_rn(tre, are), __fmul_rn(tim, aim));
         const float uim = __fadd_rn(__fmul_rn(tre, aim), __fmul_rn(tim, are));
-        S.v[s][0] = __float_as_uint(__fadd_rn(__uint_as_float(S.v[s][0]), __fmul_rn(ure, pw)));
-        S.v[s][1] = __float_as_uint(__fadd_rn(__uint_as_float(S.v[s][1]), __fmul_rn(uim, pw)));
+        float2* sp = reinterpret_cast<float2*>(scol) + s * (HAS_EXACT ? 2 : 1) * T;
+        float2 acc = *sp;
+        acc.x = __fadd_rn(acc.x, __fmul_rn(ure, pw));
+        acc.y = __fadd_rn(acc.y, __fmul_rn(uim, pw));
+        *sp = acc;
       }
     }
     off += h1.w;
   }
 }
 
-template <bool HAS_EXACT>
-__global__ void __launch_bounds__(kSlicedThreads, 1) sample_sliced_kernel(const SParams prm) {
+// dynamic shared memory (32-bit words): [0,64) mbarriers | SlicedTables | xt [rows][T] | pw [16][T] |
+// S [32][T] x (uint4 if HAS_EXACT else float2) | prev [32][T] | data region / stage ring
+template <int T, bool HAS_EXACT>
+__global__ void __launch_bounds__(T, 1) sample_sliced_kernel(const SParams prm) {
   extern __shared__ __align__(128) uint32_t smem[];
   const uint32_t* __restrict__ blob = prm.blob;
   const int tid = threadIdx.x;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   SlicedTables* tb = reinterpret_cast<SlicedTables*>(smem + 64);
-  uint32_t* xcol = smem + prm.smem_xt_off + tid;   // this thread's column: row r at xcol[r * T]
+  uint32_t* xcol = smem + prm.smem_xt_off + tid;  // this thread's column: row r at xcol[r * T]
+  const uint32_t xbytes = smem_u32(xcol);
   uint32_t* pwcol = smem + prm.smem_pw_off + tid;
+  // S: element (s, tid) at scol + s * stride * T words, stride = 4 (exact) or 2 (approx) words; vector accesses
+  uint32_t* scol = smem + prm.smem_s_off + tid * (HAS_EXACT ? 4 : 2);
+  float* pcol = reinterpret_cast<float*>(smem + prm.smem_prev_off) + tid;
   uint32_t* sdata = smem + prm.smem_data_off;
 
   const int n_comp = (int)blob[H_N_COMP], n_chunks = (int)blob[H_N_CHUNKS];
@@ -279,21 +312,16 @@ __global__ void __launch_bounds__(kSlicedThreads, 1) sample_sliced_kernel(const 
   const uint32_t* __restrict__ gdata = blob + blob[H_OFF_DATA];
   const int one_row = (int)blob[H_ONE_ROW];
 
-  // tables
-  {
-    Tables* full = nullptr;
-    (void)full;
-    for (int i = tid; i < 64; i += kSlicedThreads) {
-      int a = i & 7, b = i >> 3;
-      int4 ua = unit_phase(a), ub = unit_phase(b), uc = unit_phase(a + b);
-      tb->pair[i] = make_int4(1 + ua.x + ub.x - uc.x, ua.y + ub.y - uc.y, ua.z + ub.z - uc.z, ua.w + ub.w - uc.w);
-    }
-    if (tid == 0) {
-      uint32_t P = 1, Q = 0;
-      for (int e = 0; e < 64; ++e) { tb->pell[64 + e] = make_int2((int)P, (int)Q); uint32_t nP = P + 2u * Q, nQ = P + Q; P = nP; Q = nQ; }
-      P = 1; Q = 0;
-      for (int e = 0; e <= 64; ++e) { tb->pell[64 - e] = make_int2((int)P, (int)Q); uint32_t nP = 2u * Q - P, nQ = P - Q; P = nP; Q = nQ; }
-    }
+  for (int i = tid; i < 64; i += T) {
+    int a = i & 7, b = i >> 3;
+    int4 ua = unit_phase(a), ub = unit_phase(b), uc = unit_phase(a + b);
+    tb->pair[i] = make_int4(1 + ua.x + ub.x - uc.x, ua.y + ub.y - uc.y, ua.z + ub.z - uc.z, ua.w + ub.w - uc.w);
+  }
+  if (tid == 0) {
+    uint32_t P = 1, Q = 0;
+    for (int e = 0; e < 64; ++e) { tb->pell[64 + e] = make_int2((int)P, (int)Q); uint32_t nP = P + 2u * Q, nQ = P + Q; P = nP; Q = nQ; }
+    P = 1; Q = 0;
+    for (int e = 0; e <= 64; ++e) { tb->pell[64 - e] = make_int2((int)P, (int)Q); uint32_t nP = 2u * Q - P, nQ = P - Q; P = nP; Q = nQ; }
   }
   const int n_bars = prm.resident ? 1 : prm.n_stages;
   if (tid == 0) {
@@ -335,22 +363,18 @@ __global__ void __launch_bounds__(kSlicedThreads, 1) sample_sliced_kernel(const 
     for (int ci = 0; ci < n_comp; ++ci) {
       const uint32_t* __restrict__ comp = comp_tab + ci * kCompWords;
       const int F = (int)comp[C_F], n_c = (int)comp[C_NC];
-      for (int i = 0; i < F; ++i) xcol[i * kSlicedThreads] = active ? prm.xt[(size_t)(xt_row0 + i) * prm.slab_cap + slab] : 0u;
-      for (int i = F; i < prm.rows; ++i) xcol[i * kSlicedThreads] = 0u;
-      xcol[one_row * kSlicedThreads] = 0xFFFFFFFFu;
-      float prev[32];
-#pragma unroll
-      for (int s = 0; s < 32; ++s) prev[s] = 0.0f;
+      for (int i = 0; i < F; ++i) xcol[i * T] = active ? prm.xt[(size_t)(xt_row0 + i) * prm.slab_cap + slab] : 0u;
+      for (int i = F; i < prm.rows; ++i) xcol[i * T] = 0u;
+      xcol[one_row * T] = 0xFFFFFFFFu;
 
       for (int k = 0; k <= n_c; ++k) {
         const uint32_t* __restrict__ lvl = level_tab + (comp[C_FIRST_LEVEL] + k) * kLevelWords;
         const bool approx = (lvl[L_FLAGS] & 1u) != 0u;
-        if (k > 0) xcol[(F + k - 1) * kSlicedThreads] = 0xFFFFFFFFu;  // trying bit 1 for every shot
-        SlabAcc<HAS_EXACT> S;
-#pragma unroll
-        for (int s = 0; s < 32; ++s)
-#pragma unroll
-          for (int c = 0; c < (HAS_EXACT ? 4 : 2); ++c) S.v[s][c] = 0u;
+        if (k > 0) xcol[(F + k - 1) * T] = 0xFFFFFFFFu;  // trying bit 1 for every shot
+        for (int s = 0; s < 32; ++s) {
+          if constexpr (HAS_EXACT) reinterpret_cast<uint4*>(scol)[s * T] = make_uint4(0u, 0u, 0u, 0u);
+          else reinterpret_cast<uint2*>(scol)[s * T] = make_uint2(0u, 0u);
+        }
         const int first_chunk = (int)lvl[L_FIRST_CHUNK], nck = (int)lvl[L_N_CHUNKS];
         for (int c = 0; c < nck; ++c) {
           const uint32_t* row = chunk_tab + (first_chunk + c) * kChunkWords;
@@ -362,7 +386,7 @@ __global__ void __launch_bounds__(kSlicedThreads, 1) sample_sliced_kernel(const 
             mbar_wait(&bars[stage], (uint32_t)((q / prm.n_stages) & 1));
             off = (uint32_t)stage * (uint32_t)prm.stage_words;
           }
-          sliced_graphs<HAS_EXACT>(sdata, off, (int)row[K_GRAPHS], approx, xcol, pwcol, tb, S);
+          sliced_graphs<T, HAS_EXACT>(sdata, off, (int)row[K_GRAPHS], approx, xbytes, pwcol, scol, tb);
           if (!prm.resident) {
             __syncthreads();
             if (tid == 0 && q + prm.n_stages < total_q) issue(q + prm.n_stages);
@@ -378,15 +402,16 @@ __global__ void __launch_bounds__(kSlicedThreads, 1) sample_sliced_kernel(const 
           k1 = prm.subkeys[2 * (draw0 + k - 1) + 1];
         }
         uint32_t bits = 0;
-#pragma unroll
+#pragma unroll 2
         for (int s = 0; s < 32; ++s) {
           float re, im;
           if (approx) {
-            re = __uint_as_float(S.v[s][0]);
-            im = __uint_as_float(S.v[s][1]);
+            const float2 a2 = reinterpret_cast<const float2*>(scol)[s * (HAS_EXACT ? 2 : 1) * T];
+            re = a2.x; im = a2.y;
           } else {
             if constexpr (HAS_EXACT) {
-              ZW cz = ZW{S.v[s][0], S.v[s][1], S.v[s][2], S.v[s][3]};
+              const uint4 a4 = reinterpret_cast<const uint4*>(scol)[s * T];
+              ZW cz = ZW{a4.x, a4.y, a4.z, a4.w};
               int p = p_lo;
               zw_fixpoint(cz, p);
               zw_to_complex(cz, p, re, im);
@@ -397,16 +422,17 @@ __global__ void __launch_bounds__(kSlicedThreads, 1) sample_sliced_kernel(const 
           if (empty) { re = 0.0f; im = 0.0f; }
           const float p1 = complex_abs(re, im);
           if (k == 0) {
-            prev[s] = p1;
+            pcol[s * T] = p1;
           } else {
+            const float pv = pcol[s * T];
             const float u = uniform_f32(k0, k1, shot0 + (unsigned long long)s);
-            const bool bit = u < __fdiv_rn(p1, prev[s]);
-            prev[s] = bit ? p1 : __fsub_rn(prev[s], p1);
+            const bool bit = u < __fdiv_rn(p1, pv);
+            pcol[s * T] = bit ? p1 : __fsub_rn(pv, p1);
             bits |= (bit ? 1u : 0u) << s;
           }
         }
         if (k > 0) {
-          xcol[(F + k - 1) * kSlicedThreads] = bits;
+          xcol[(F + k - 1) * T] = bits;
           if (active) prm.ot[(size_t)(draw0 + k - 1) * prm.slab_cap + slab] = bits;
         }
       }

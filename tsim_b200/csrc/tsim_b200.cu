@@ -503,7 +503,8 @@ struct tsb_program {
   uint32_t* d_heavy = nullptr;  // for tsb_sample_device
   long long heavy_cap = 0;
   // MODE_SLICED
-  int is_sliced = 0, s_has_exact = 0, s_rows = 0, s_xt_off = 0, s_pw_off = 0, total_F = 0, max_nc = 0;
+  int is_sliced = 0, s_has_exact = 0, s_rows = 0, s_xt_off = 0, s_pw_off = 0, s_s_off = 0, s_prev_off = 0, s_threads = 0;
+  int total_F = 0, max_nc = 0;
   tsb_program* aux = nullptr;   // companion per-row program (norm check); not owned
   uint32_t* d_xt = nullptr;     // scratch for tsb_sample_device
   uint32_t* d_ot = nullptr;
@@ -579,6 +580,11 @@ static EvalFn eval_fn_for(int W) {
     default: return nullptr;
   }
 }
+typedef void (*SlicedFn)(const SParams);
+static SlicedFn sliced_fn(int T, int has_exact) {
+  if (has_exact) return T == 256 ? sample_sliced_kernel<256, true> : T == 128 ? sample_sliced_kernel<128, true> : sample_sliced_kernel<64, true>;
+  return T == 256 ? sample_sliced_kernel<256, false> : T == 128 ? sample_sliced_kernel<128, false> : sample_sliced_kernel<64, false>;
+}
 static SampleFn sample_fn(int mode, int W) { return mode == kModeFast ? sample_fn_for<kModeFast>(W) : sample_fn_for<kModeFaithful>(W); }
 static EvalFn eval_fn(int mode, int W) { return mode == kModeFast ? eval_fn_for<kModeFast>(W) : eval_fn_for<kModeFaithful>(W); }
 
@@ -626,9 +632,6 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
   if (mode == kModeSliced) {
     p->is_sliced = 1;
     p->s_rows = (int)blob[H_ZERO_ROW] + 1;
-    p->s_xt_off = (kBarWords + (int)(sizeof(SlicedTables) / 4) + 31) & ~31;
-    p->s_pw_off = p->s_xt_off + p->s_rows * kSlicedThreads;
-    fixed_words = p->s_pw_off + 2 * kMaxGeneralPairs * kSlicedThreads;
     const uint32_t* lv = blob + blob[H_OFF_LEVEL];
     for (uint32_t i = 0; i < blob[H_N_LEVELS]; ++i)
       if (!(lv[i * kLevelWords + L_FLAGS] & 1u) && lv[i * kLevelWords + L_G] > 0u) p->s_has_exact = 1;
@@ -636,6 +639,24 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
     for (int c = 0; c < n_comp; ++c) {
       p->total_F += (int)ct[c * kCompWords + C_F];
       p->max_nc = std::max(p->max_nc, (int)ct[c * kCompWords + C_NC]);
+    }
+    // threads per CTA: the largest of 256/128/64 whose private columns leave room for g (resident, or >= 2 stages)
+    int lim_smem = (int)prop.sharedMemPerBlockOptin;
+    if (const char* lim = getenv("TSIM_B200_SMEM_LIMIT")) {
+      int v = atoi(lim);
+      if (v > 0) lim_smem = std::min(lim_smem, v);
+    }
+    const long long dw = blob[H_DATA_WORDS], mc = ((long long)blob[H_MAX_CHUNK] + 31) & ~31ll;
+    for (int T : {256, 128, 64}) {
+      const int xt_off = (kBarWords + (int)(sizeof(SlicedTables) / 4) + 31) & ~31;
+      const int pw_off = xt_off + p->s_rows * T;
+      const int s_off = pw_off + 2 * kMaxGeneralPairs * T;
+      const int prev_off = s_off + 32 * T * (p->s_has_exact ? 4 : 2);
+      const int fixed = (prev_off + 32 * T + 31) & ~31;
+      const long long room = (long long)lim_smem / 4 - fixed;
+      p->s_threads = T; p->s_xt_off = xt_off; p->s_pw_off = pw_off; p->s_s_off = s_off; p->s_prev_off = prev_off;
+      fixed_words = fixed;
+      if (room >= dw || (mc > 0 && room >= 2 * mc)) break;
     }
   }
   fixed_words = (fixed_words + 31) & ~31;  // 128-byte align the data region
@@ -665,8 +686,7 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
   p->smem_data_off = fixed_words;
   const int smem_bytes = (int)((fixed_words + used) * 4);
   if (mode == kModeSliced) {
-    CUB(cudaFuncSetAttribute((const void*)sample_sliced_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    CUB(cudaFuncSetAttribute((const void*)sample_sliced_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CUB(cudaFuncSetAttribute((const void*)sliced_fn(p->s_threads, p->s_has_exact), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   } else {
     CUB(cudaFuncSetAttribute((const void*)sample_fn(mode, W), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   }
@@ -676,7 +696,7 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
   in.n_direct = (int)blob[H_N_DIRECT]; in.n_components = n_comp; in.n_draws = n_draws;
   in.words_f64 = (int)blob[H_WF64]; in.words_out64 = (int)blob[H_WOUT64];
   in.resident = resident; in.n_chunks = (int)blob[H_N_CHUNKS]; in.smem_bytes = smem_bytes;
-  in.threads = mode == kModeSliced ? kSlicedThreads : kThreads; in.grid = p->sm_count; in.data_bytes = data_words * 4;
+  in.threads = mode == kModeSliced ? p->s_threads : kThreads; in.grid = p->sm_count; in.data_bytes = data_words * 4;
 #undef CUB
   *out = p;
   return TSB_OK;
@@ -874,12 +894,13 @@ static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long 
     k.blob = p->d_blob; k.xt = d_xt; k.ot = d_ot; k.subkeys = d_subkeys; k.B = B; k.shot_offset = shot_offset;
     k.n_slabs = n_slabs; k.slab_cap = (int)slab_cap;
     const int grid = std::max(1, std::min(p->sm_count, (n_slabs + 31) / 32));
-    k.rounds = (n_slabs + grid * kSlicedThreads - 1) / (grid * kSlicedThreads);
+    const int T = p->s_threads;
+    k.rounds = (n_slabs + grid * T - 1) / (grid * T);
     k.per_cta = (n_slabs + grid * k.rounds - 1) / (grid * k.rounds);
     k.resident = in.resident; k.n_stages = p->n_stages; k.stage_words = p->stage_words;
-    k.smem_xt_off = p->s_xt_off; k.smem_pw_off = p->s_pw_off; k.smem_data_off = p->smem_data_off; k.rows = p->s_rows;
-    if (p->s_has_exact) sample_sliced_kernel<true><<<grid, kSlicedThreads, in.smem_bytes, st>>>(k);
-    else sample_sliced_kernel<false><<<grid, kSlicedThreads, in.smem_bytes, st>>>(k);
+    k.smem_xt_off = p->s_xt_off; k.smem_pw_off = p->s_pw_off; k.smem_s_off = p->s_s_off; k.smem_prev_off = p->s_prev_off;
+    k.smem_data_off = p->smem_data_off; k.rows = p->s_rows;
+    sliced_fn(T, p->s_has_exact)<<<grid, T, in.smem_bytes, st>>>(k);
     CU(cudaGetLastError());
   }
   assemble_out_kernel<<<tblocks, 256, 0, st>>>(p->d_blob, d_f, d_ot, B, n_slabs, (int)slab_cap, d_out);

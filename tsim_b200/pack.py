@@ -236,6 +236,8 @@ def pack_program(
                 f"fast mode is not provably exact for this program (log2 bound {bound_info['log2_bound']:.1f} >= 30.5)"
             )
         mode_id = MODE_SLICED if mode in ("sliced", MODE_SLICED) else MODE_FAST
+        if mode_id == MODE_SLICED:
+            max_chunk_words = min(max_chunk_words, 4096)  # sliced CTAs keep per-shot state in shared memory: small stages
     else:
         raise ValueError(f"unknown mode {mode!r}")
 

@@ -127,7 +127,7 @@ def test_cfg2_shape_matches_oracle_resident_and_streamed(mode, monkeypatch):
     key = oracle.split((0, 0))[1]
     want, want_dev = _oracle(prog, f, key)
     dp = _device_program(prog, mode)
-    assert dp.info["resident"] == 1
+    assert dp.info["resident"] == (0 if mode == "sliced" else 1)  # sliced CTAs spend their shared memory on per-shot state
     got, dev = dp.sample(f, key)
     assert np.array_equal(got, want) and _dev_equal(dev, want_dev)
     # packed formats
@@ -136,7 +136,7 @@ def test_cfg2_shape_matches_oracle_resident_and_streamed(mode, monkeypatch):
     # same program through the streamed path (shared memory capped -> chunk ring)
     monkeypatch.setenv("TSIM_B200_SMEM_LIMIT", str((140 if mode == "sliced" else 64) * 1024))
     dps = _device_program(prog, mode)
-    assert dps.info["resident"] == 0
+    assert dps.info["resident"] == 0 and (mode != "sliced" or dps.info["threads"] < dp.info["threads"])
     got2, dev2 = dps.sample(f, key)
     assert np.array_equal(got2, want) and _dev_equal(dev2, want_dev)
 

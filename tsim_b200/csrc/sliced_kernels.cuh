@@ -154,32 +154,35 @@ __device__ __forceinline__ void add_cnt5(uint32_t (&Bp)[5], uint32_t w) {
 template <int T>
 __device__ __forceinline__ uint32_t ld_row(uint32_t xbytes, uint32_t row) {
   uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(xbytes + row * (uint32_t)(4 * T)));
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(xbytes + row * (uint32_t)(4 * T)) : "memory");
   return v;
 }
 
 template <int T>
+__device__ __forceinline__ uint32_t xor4(uint32_t xbytes, uint32_t iw) {
+  const uint32_t a0 = ld_row<T>(xbytes, iw & 255u), a1 = ld_row<T>(xbytes, __byte_perm(iw, 0, 0x4441));
+  const uint32_t a2 = ld_row<T>(xbytes, __byte_perm(iw, 0, 0x4442)), a3 = ld_row<T>(xbytes, iw >> 24);
+  return (a0 ^ a1) ^ (a2 ^ a3);
+}
+
+template <int T>
 __device__ __forceinline__ uint32_t sliced_parity(const uint32_t* __restrict__ sdata, uint32_t o, int n, uint32_t xbytes) {
+  // masks of weight <= 12 (three index words) are the common case: straight-line, all loads in flight at once
+  if (n <= 3) {
+    const uint32_t i0 = sdata[o], i1 = sdata[o + 1], i2 = sdata[o + 2];  // over-reads stay inside the record
+    uint32_t acc = xor4<T>(xbytes, i0);
+    if (n > 1) acc ^= xor4<T>(xbytes, i1);
+    if (n > 2) acc ^= xor4<T>(xbytes, i2);
+    return n > 0 ? acc : 0u;
+  }
   uint32_t acc0 = 0, acc1 = 0;
   int w = 0;
   for (; w + 1 < n; w += 2) {
     const uint32_t i0 = sdata[o + w], i1 = sdata[o + w + 1];
-    const uint32_t a0 = ld_row<T>(xbytes, i0 & 255u), a1 = ld_row<T>(xbytes, __byte_perm(i0, 0, 0x4441));
-    const uint32_t a2 = ld_row<T>(xbytes, __byte_perm(i0, 0, 0x4442)), a3 = ld_row<T>(xbytes, i0 >> 24);
-    const uint32_t b0 = ld_row<T>(xbytes, i1 & 255u), b1 = ld_row<T>(xbytes, __byte_perm(i1, 0, 0x4441));
-    const uint32_t b2 = ld_row<T>(xbytes, __byte_perm(i1, 0, 0x4442)), b3 = ld_row<T>(xbytes, i1 >> 24);
-    acc0 ^= a0 ^ a1;
-    acc1 ^= b0 ^ b1;
-    acc0 ^= a2 ^ a3;
-    acc1 ^= b2 ^ b3;
+    acc0 ^= xor4<T>(xbytes, i0);
+    acc1 ^= xor4<T>(xbytes, i1);
   }
-  if (w < n) {
-    const uint32_t i0 = sdata[o + w];
-    const uint32_t a0 = ld_row<T>(xbytes, i0 & 255u), a1 = ld_row<T>(xbytes, __byte_perm(i0, 0, 0x4441));
-    const uint32_t a2 = ld_row<T>(xbytes, __byte_perm(i0, 0, 0x4442)), a3 = ld_row<T>(xbytes, i0 >> 24);
-    acc0 ^= a0 ^ a1;
-    acc1 ^= a2 ^ a3;
-  }
+  if (w < n) acc0 ^= xor4<T>(xbytes, sdata[o + w]);
   return acc0 ^ acc1;
 }
 
@@ -357,6 +360,9 @@ __global__ void __launch_bounds__(T, 1) sample_sliced_kernel(const SParams prm) 
   for (int round = 0; round < prm.rounds; ++round) {
     const int slab = (round * (int)gridDim.x + (int)blockIdx.x) * prm.per_cta + tid;
     const bool active = tid < prm.per_cta && slab < prm.n_slabs;
+    // a warp with no slab at all only keeps the stage ring's barriers company
+    const int wslab = (round * (int)gridDim.x + (int)blockIdx.x) * prm.per_cta + (tid & ~31);
+    const bool warp_active = (tid & ~31) < prm.per_cta && wslab < prm.n_slabs;
     const unsigned long long shot0 = (unsigned long long)prm.shot_offset + (unsigned long long)slab * 32ull;
 
     int xt_row0 = 0, draw0 = 0;
@@ -386,7 +392,7 @@ __global__ void __launch_bounds__(T, 1) sample_sliced_kernel(const SParams prm) 
             mbar_wait(&bars[stage], (uint32_t)((q / prm.n_stages) & 1));
             off = (uint32_t)stage * (uint32_t)prm.stage_words;
           }
-          sliced_graphs<T, HAS_EXACT>(sdata, off, (int)row[K_GRAPHS], approx, xbytes, pwcol, scol, tb);
+          if (warp_active) sliced_graphs<T, HAS_EXACT>(sdata, off, (int)row[K_GRAPHS], approx, xbytes, pwcol, scol, tb);
           if (!prm.resident) {
             __syncthreads();
             if (tid == 0 && q + prm.n_stages < total_q) issue(q + prm.n_stages);
@@ -403,7 +409,7 @@ __global__ void __launch_bounds__(T, 1) sample_sliced_kernel(const SParams prm) 
         }
         uint32_t bits = 0;
 #pragma unroll 2
-        for (int s = 0; s < 32; ++s) {
+        for (int s = 0; s < (warp_active ? 32 : 0); ++s) {
           float re, im;
           if (approx) {
             const float2 a2 = reinterpret_cast<const float2*>(scol)[s * (HAS_EXACT ? 2 : 1) * T];

@@ -506,6 +506,9 @@ struct tsb_program {
   int is_sliced = 0, s_has_exact = 0, s_rows = 0, s_xt_off = 0, s_pw_off = 0, s_s_off = 0, s_prev_off = 0, s_threads = 0;
   int total_F = 0, max_nc = 0;
   tsb_program* aux = nullptr;   // companion per-row program (norm check); not owned
+  cudaStream_t side = nullptr;  // the norm check of shot 0 runs here, overlapped with the rest of the batch
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  uint64_t* d_row0 = nullptr;   // copies of f row 0 and output row 0 for the check
   uint32_t* d_xt = nullptr;     // scratch for tsb_sample_device
   uint32_t* d_ot = nullptr;
   long long scratch_slabs = 0;
@@ -640,6 +643,10 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
       p->total_F += (int)ct[c * kCompWords + C_F];
       p->max_nc = std::max(p->max_nc, (int)ct[c * kCompWords + C_NC]);
     }
+    CUB(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    CUB(cudaMalloc(&p->d_row0, 8 * (size_t)(blob[H_WF64] + blob[H_WOUT64])));
     // threads per CTA: the largest of 256/128/64 whose private columns leave room for g (resident, or >= 2 stages)
     int lim_smem = (int)prop.sharedMemPerBlockOptin;
     if (const char* lim = getenv("TSIM_B200_SMEM_LIMIT")) {
@@ -731,6 +738,10 @@ int tsb_program_destroy(tsb_program* p) {
   if (p->d_heavy) cudaFree(p->d_heavy);
   if (p->d_xt) cudaFree(p->d_xt);
   if (p->d_ot) cudaFree(p->d_ot);
+  if (p->d_row0) cudaFree(p->d_row0);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
+  if (p->side) cudaStreamDestroy(p->side);
   if (p->ev_a) cudaEventDestroy(p->ev_a);
   if (p->ev_b) cudaEventDestroy(p->ev_b);
   if (p->stream) cudaStreamDestroy(p->stream);
@@ -879,7 +890,8 @@ static NormFn norm_fn_for(int W) {
 
 // K0t -> K1s -> K2a -> K1c on one stream
 static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long long shot_offset, const uint32_t* d_subkeys,
-                         uint64_t* d_out, float* d_norm_dev, cudaStream_t st, uint32_t* d_xt, uint32_t* d_ot, long long slab_cap) {
+                         uint64_t* d_out, float* d_norm_dev, cudaStream_t st, uint32_t* d_xt, uint32_t* d_ot, long long slab_cap,
+                         bool join = false) {
   if (B <= 0) return TSB_OK;
   const tsb_info& in = p->info;
   const int n_slabs = (int)((B + 31) / 32);
@@ -906,10 +918,17 @@ static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long 
   assemble_out_kernel<<<tblocks, 256, 0, st>>>(p->d_blob, d_f, d_ot, B, n_slabs, (int)slab_cap, d_out);
   CU(cudaGetLastError());
   if (shot_offset == 0 && in.n_components > 0 && p->aux) {
+    // fork: the check works on copies of row 0, on a side stream, while st carries on with the next slice / step
     const tsb_program* a = p->aux;
+    CU(cudaMemcpyAsync(p->d_row0, d_f, 8 * (size_t)in.words_f64, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(p->d_row0 + in.words_f64, d_out, 8 * (size_t)in.words_out64, cudaMemcpyDeviceToDevice, st));
+    CU(cudaEventRecord(p->ev_fork, st));
+    CU(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
     NormFn fn = a->info.mode == kModeFast ? norm_fn_for<kModeFast>(a->info.words) : norm_fn_for<kModeFaithful>(a->info.words);
-    fn<<<in.n_components, 128, (2 * p->max_nc + 1) * sizeof(float), st>>>(a->d_blob, d_f, d_out, d_norm_dev);
+    fn<<<in.n_components, 128, (2 * p->max_nc + 1) * sizeof(float), p->side>>>(a->d_blob, p->d_row0, p->d_row0 + in.words_f64, d_norm_dev);
     CU(cudaGetLastError());
+    CU(cudaEventRecord(p->ev_join, p->side));
+    if (join) CU(cudaStreamWaitEvent(st, p->ev_join, 0));
   }
   return TSB_OK;
 }
@@ -949,8 +968,9 @@ int tsb_sample_device(tsb_program* p, const uint64_t* d_f, int64_t B, int64_t sh
       CU(cudaMalloc(&p->d_ot, 4 * (size_t)slabs * std::max(1, p->info.n_draws)));
       p->scratch_slabs = slabs;
     }
+    // the stream only waits for the (overlapped) norm check when the caller wants the deviations in its own buffer
     int rc = launch_sliced(p, d_f, B, shot_offset, p->d_subkeys, d_out, d_norm_dev ? d_norm_dev : p->d_norm_dev, st, p->d_xt,
-                           p->d_ot, p->scratch_slabs);
+                           p->d_ot, p->scratch_slabs, d_norm_dev != nullptr);
     if (rc) return rc;
     CU(cudaEventRecord(p->ev_b, st));
     p->last_launches = B > 0 ? 5 : 0;
@@ -1117,6 +1137,7 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
       s.timed = false;
     }
   }
+  if (p->side) CU(cudaStreamSynchronize(p->side));
   if (norm_dev && in.n_components > 0)
     CU(cudaMemcpy(norm_dev, p->d_norm_dev, sizeof(float) * in.n_components, cudaMemcpyDeviceToHost));
   return TSB_OK;
@@ -1367,6 +1388,7 @@ int tsb_sample_noisy_host(tsb_program* p, tsb_noise* n, int64_t B, int64_t shot_
       s.timed = false;
     }
   }
+  if (p->side) CU(cudaStreamSynchronize(p->side));
   if (norm_dev && in.n_components > 0)
     CU(cudaMemcpy(norm_dev, p->d_norm_dev, sizeof(float) * in.n_components, cudaMemcpyDeviceToHost));
   return TSB_OK;

@@ -236,7 +236,7 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
         if len(terms) > 0xFFFF:
             raise _Unsupported("too many terms")
         power2 = int(pre.power2[g])
-        body = [w for t in terms for w in t]
+        body = [w for t in terms for w in t] + [0, 0]  # slack: the kernel may read two words past the last index word
         words = np.zeros(SLICED_HEADER_WORDS + len(body), dtype=np.uint32)
         words[0] = len(terms) | (len(general_ctl) << 16)
         words[1] = (b_base + B_OFFSET) | (nb << 8)

@@ -91,8 +91,20 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
             for _t in range(n_terms):
                 cw = int(data[o])
                 typ, n1, n2 = cw & 3, (cw >> 2) & 63, (cw >> 8) & 63
+                generic = cw >> 31
+                if generic:
+                    has_extra = typ == 3
+                    ex = int(data[o + 1]) if has_extra else 0
+                    o1 = o + 1 + (1 if has_extra else 0)
+                    o2 = o1 + n1
+                    length = 1 + (1 if has_extra else 0) + n1 + (n2 if typ != 0 else 0)
+                    length += (-length) % 4
+                else:
+                    o1, o2 = o + 1, o + 4
+                    ex = int(data[o + 7]) if typ != 0 else 0
+                    length = 4 if typ == 0 else 8
                 if typ == 0:
-                    p = parity(o + 1, n1)
+                    p = parity(o1, n1)
                     add_a((cw >> 14) & 7, p)
                     bm, zm = (cw >> 17) & 3, (cw >> 19) & 3
                     if bm == 1:
@@ -103,16 +115,12 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
                         Z |= p
                     elif zm == 2:
                         Z |= ~p & full
-                    o += 1 + n1
                 elif typ == 1:
-                    A[2] ^= parity(o + 1, n1) & parity(o + 1 + n1, n2)
-                    o += 1 + n1 + n2
+                    A[2] ^= parity(o1, n1) & parity(o2, n2)
                 elif typ == 2:
-                    gen[(cw >> 14) & 15] = (parity(o + 1, n1), parity(o + 1 + n1, n2))
-                    o += 1 + n1 + n2
+                    gen[(cw >> 14) & 15] = (parity(o1, n1), parity(o2, n2))
                 else:
-                    ex = int(data[o + 1])
-                    pa, pb = parity(o + 2, n1), parity(o + 2 + n1, n2)
+                    pa, pb = parity(o1, n1), parity(o2, n2)
                     for v, wd in enumerate((pa, pb, pa & pb)):
                         add_a((ex >> (6 * v)) & 7, wd)
                         db = ((ex >> (6 * v + 3)) & 7) - 3
@@ -124,7 +132,7 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
                             wa = pa if combo & 1 else ~pa & full
                             wb = pb if combo & 2 else ~pb & full
                             Z |= wa & wb
-                    o += 2 + n1 + n2
+                o += length
             k1, k2 = h[8:12], h[12:16]
             for s in range(N):
                 if (Z >> s) & 1:

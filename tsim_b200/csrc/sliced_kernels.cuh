@@ -167,14 +167,6 @@ __device__ __forceinline__ uint32_t xor4(uint32_t xbytes, uint32_t iw) {
 
 template <int T>
 __device__ __forceinline__ uint32_t sliced_parity(const uint32_t* __restrict__ sdata, uint32_t o, int n, uint32_t xbytes) {
-  // masks of weight <= 12 (three index words) are the common case: straight-line, all loads in flight at once
-  if (n <= 3) {
-    const uint32_t i0 = sdata[o], i1 = sdata[o + 1], i2 = sdata[o + 2];  // over-reads stay inside the record
-    uint32_t acc = xor4<T>(xbytes, i0);
-    if (n > 1) acc ^= xor4<T>(xbytes, i1);
-    if (n > 2) acc ^= xor4<T>(xbytes, i2);
-    return n > 0 ? acc : 0u;
-  }
   uint32_t acc0 = 0, acc1 = 0;
   int w = 0;
   for (; w + 1 < n; w += 2) {
@@ -197,34 +189,50 @@ __device__ __forceinline__ void sliced_graphs(const uint32_t* __restrict__ sdata
     const uint32_t b64 = h0.y & 0xFFu;
     uint32_t A0 = 0, A1 = 0, A2 = 0, Z = 0;
     uint32_t Bp[5] = {0, 0, 0, 0, 0};
-    // ---- phase 1: bit-sliced accumulation over the term stream
+    // ---- phase 1: bit-sliced accumulation over the term stream (software-pipelined: the next term's record is
+    //      fetched while the current term's rows are in flight)
     uint32_t o = off + kSlicedHeaderWords;
+    uint4 cur0 = *reinterpret_cast<const uint4*>(sdata + o), cur1 = *reinterpret_cast<const uint4*>(sdata + o + 4);
     for (int t = 0; t < n_terms; ++t) {
-      const uint32_t cw = sdata[o];
+      const uint32_t cw = cur0.x;
       const uint32_t type = cw & 3u;
       const int n1 = (int)((cw >> 2) & 63u), n2 = (int)((cw >> 8) & 63u);
+      const bool generic = (cw >> 31) != 0u;
+      uint32_t len;
+      if (!generic) len = type == 0u ? 4u : 8u;
+      else len = (uint32_t)round4(1 + (type == 3u ? 1 : 0) + n1 + (type != 0u ? n2 : 0));
+      const uint4 nx0 = *reinterpret_cast<const uint4*>(sdata + o + len);
+      const uint4 nx1 = *reinterpret_cast<const uint4*>(sdata + o + len + 4);
+      uint32_t p1, p2 = 0, ex = 0;
+      if (!generic) {
+        p1 = xor4<T>(xbytes, cur0.y);
+        if (n1 > 1) p1 ^= xor4<T>(xbytes, cur0.z);
+        if (n1 > 2) p1 ^= xor4<T>(xbytes, cur0.w);
+        if (type != 0u) {
+          p2 = xor4<T>(xbytes, cur1.x);
+          if (n2 > 1) p2 ^= xor4<T>(xbytes, cur1.y);
+          if (n2 > 2) p2 ^= xor4<T>(xbytes, cur1.z);
+          ex = cur1.w;
+        }
+      } else {
+        const uint32_t o1 = o + 1 + (type == 3u ? 1u : 0u);
+        if (type == 3u) ex = sdata[o + 1];
+        p1 = sliced_parity<T>(sdata, o1, n1, xbytes);
+        if (type != 0u) p2 = sliced_parity<T>(sdata, o1 + n1, n2, xbytes);
+      }
       if (type == 0u) {
-        const uint32_t p = sliced_parity<T>(sdata, o + 1, n1, xbytes);
-        add_a3(A0, A1, A2, (cw >> 14) & 7u, p);
+        add_a3(A0, A1, A2, (cw >> 14) & 7u, p1);
         const uint32_t bm = (cw >> 17) & 3u, zm = (cw >> 19) & 3u;
-        if (bm) add_cnt5(Bp, bm == 1u ? p : ~p);
-        if (zm) Z |= (zm == 1u ? p : ~p);
-        o += 1 + n1;
+        if (bm) add_cnt5(Bp, bm == 1u ? p1 : ~p1);
+        if (zm) Z |= (zm == 1u ? p1 : ~p1);
       } else if (type == 1u) {
-        const uint32_t p1 = sliced_parity<T>(sdata, o + 1, n1, xbytes);
-        const uint32_t p2 = sliced_parity<T>(sdata, o + 1 + n1, n2, xbytes);
         A2 ^= p1 & p2;
-        o += 1 + n1 + n2;
       } else if (type == 2u) {
         const uint32_t slot = (cw >> 14) & 15u;
-        pwcol[(2 * slot) * T] = sliced_parity<T>(sdata, o + 1, n1, xbytes);
-        pwcol[(2 * slot + 1) * T] = sliced_parity<T>(sdata, o + 1 + n1, n2, xbytes);
-        o += 1 + n1 + n2;
+        pwcol[(2 * slot) * T] = p1;
+        pwcol[(2 * slot + 1) * T] = p2;
       } else {
-        const uint32_t ex = sdata[o + 1];
-        const uint32_t pa = sliced_parity<T>(sdata, o + 2, n1, xbytes);
-        const uint32_t pb = sliced_parity<T>(sdata, o + 2 + n1, n2, xbytes);
-        const uint32_t wd[3] = {pa, pb, pa & pb};
+        const uint32_t wd[3] = {p1, p2, p1 & p2};
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
           add_a3(A0, A1, A2, (ex >> (6 * v)) & 7u, wd[v]);
@@ -233,12 +241,14 @@ __device__ __forceinline__ void sliced_graphs(const uint32_t* __restrict__ sdata
           for (int r = 0; r < (db < 0 ? -db : db); ++r) add_cnt5(Bp, w);
         }
         const uint32_t ztt = (ex >> 18) & 15u;
-        if (ztt & 1u) Z |= ~pa & ~pb;
-        if (ztt & 2u) Z |= pa & ~pb;
-        if (ztt & 4u) Z |= ~pa & pb;
-        if (ztt & 8u) Z |= pa & pb;
-        o += 2 + n1 + n2;
+        if (ztt & 1u) Z |= ~p1 & ~p2;
+        if (ztt & 2u) Z |= p1 & ~p2;
+        if (ztt & 4u) Z |= ~p1 & p2;
+        if (ztt & 8u) Z |= p1 & p2;
       }
+      o += len;
+      cur0 = nx0;
+      cur1 = nx1;
     }
     // ---- phase 2: per-shot decode and accumulation
     const uint4 k1 = *reinterpret_cast<const uint4*>(sdata + off + 8);
@@ -248,7 +258,7 @@ __device__ __forceinline__ void sliced_graphs(const uint32_t* __restrict__ sdata
     const float sc = pow2_f32((int)h0.z), pw = pow2_f32((int)h0.w);
     const uint32_t fx = 1u << (h1.x & 31u);
     // cnt: five count planes -> one word per plane; a: three planes
-#pragma unroll 2
+#pragma unroll 4
     for (int s = 0; s < 32; ++s) {
       if ((Z >> s) & 1u) continue;
       const uint32_t a = ((A0 >> s) & 1u) | (((A1 >> s) & 1u) << 1) | (((A2 >> s) & 1u) << 2);

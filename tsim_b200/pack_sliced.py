@@ -17,7 +17,11 @@ Graph record (uint32 words):
     [18..19] reserved
     then the term stream, one control word per term followed by its index words:
         cw bits 0-1 type (0 LIN, 1 PI, 2 PAIR_GENERAL, 3 PAIR_MONOID), bits 2-7 n1, bits 8-13 n2 (index words of
-        the first / second parity; an index word holds four row indices, padded with the all-zero row)
+        the first / second parity; an index word holds four row indices, padded with the all-zero row), bit 31 generic.
+        Every term record is 16-byte aligned.  Compact form (all parities <= 3 index words, the common case):
+            LIN  [cw, a0, a1, a2]                      others  [cw, a0, a1, a2, b0, b1, b2, extra]
+        so a term is one or two 128-bit shared-memory reads at fixed positions (unused index words are never read).
+        Generic form (bit 31): [cw, extra?, a..., b...] padded to a multiple of four words.
         LIN          bits 14-16 da, 17-18 bmode (1: count p, 2: count ~p), 19-20 zmode (1: Z |= p, 2: Z |= ~p)
         PI           A2 ^= p1 & p2
         PAIR_GENERAL bits 14-17 slot: parity words are kept for the per-shot ring product
@@ -87,6 +91,21 @@ def pair_factor(alpha: int, beta: int):
     return tuple(int(i == 0) + ua[i] + ub[i] - uc[i] for i in range(4))
 
 
+GENERIC = 1 << 31
+
+
+def _term_record(cw: int, i1: list[int], i2: list[int] | None, extra: int | None) -> list[int]:
+    """Compact (4 or 8 words) or generic (padded to 4) term record."""
+    two = i2 is not None
+    if len(i1) <= 3 and (not two or len(i2) <= 3):
+        rec = [cw] + i1 + [0] * (3 - len(i1))
+        if two:
+            rec += i2 + [0] * (3 - len(i2)) + [extra or 0]
+        return rec
+    rec = [cw | GENERIC] + ([extra] if extra is not None else []) + i1 + (i2 or [])
+    return rec + [0] * ((-len(rec)) % 4)
+
+
 def _index_words(rows: list[int], zero_row: int) -> list[int]:
     rows = list(rows)
     while len(rows) % 4:
@@ -126,7 +145,7 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
             iw = _index_words(rows, zero_row)
             if len(iw) > 63:
                 raise _Unsupported("mask too heavy")
-            terms.append([T_LIN | (len(iw) << 2) | ((da & 7) << 14) | (bmode << 17) | (zmode << 19)] + iw)
+            terms.append(_term_record(T_LIN | (len(iw) << 2) | ((da & 7) << 14) | (bmode << 17) | (zmode << 19), iw, None, None))
 
         for j in range(min(int(n.counts[g]), A)):
             ph = int(n.phases[g, j]) & 7
@@ -174,7 +193,7 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
             i1, i2 = _index_words(r1, zero_row), _index_words(r2, zero_row)
             if len(i1) > 63 or len(i2) > 63:
                 raise _Unsupported("mask too heavy")
-            terms.append([T_PI | (len(i1) << 2) | (len(i2) << 8)] + i1 + i2)
+            terms.append(_term_record(T_PI | (len(i1) << 2) | (len(i2) << 8), i1, i2, None))
         general_ctl = []
         for j in range(min(int(q.counts[g]), D)):
             al, be = int(q.alpha[g, j]) & 7, int(q.beta[g, j]) & 7
@@ -190,7 +209,7 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
                     raise _Unsupported("too many general phase pairs in one graph")
                 slot = len(general_ctl)
                 general_ctl.append(al | (be << 3))
-                terms.append([T_PAIR_GENERAL | (len(i1) << 2) | (len(i2) << 8) | (slot << 14)] + i1 + i2)
+                terms.append(_term_record(T_PAIR_GENERAL | (len(i1) << 2) | (len(i2) << 8) | (slot << 14), i1, i2, None))
                 continue
             # value(pa, pb) as a polynomial: base + pa d10 + pb d01 + pa pb d11 in the exponents (a mod 8, b)
             ref = nz[0]
@@ -215,7 +234,7 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
                     b_base += db  # each negative unit is counted as (~p) - 1
                 units += abs(db)
             extra |= ztt << 18
-            terms.append([T_PAIR_MONOID | (len(i1) << 2) | (len(i2) << 8), extra] + i1 + i2)
+            terms.append(_term_record(T_PAIR_MONOID | (len(i1) << 2) | (len(i2) << 8), i1, i2, extra))
 
         if units > 31:
             raise _Unsupported("b counter needs more than 5 planes")
@@ -236,7 +255,7 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
         if len(terms) > 0xFFFF:
             raise _Unsupported("too many terms")
         power2 = int(pre.power2[g])
-        body = [w for t in terms for w in t] + [0, 0]  # slack: the kernel may read two words past the last index word
+        body = [w for t in terms for w in t] + [0] * 8  # slack: the kernel prefetches the next term's eight words
         words = np.zeros(SLICED_HEADER_WORDS + len(body), dtype=np.uint32)
         words[0] = len(terms) | (len(general_ctl) << 16)
         words[1] = (b_base + B_OFFSET) | (nb << 8)

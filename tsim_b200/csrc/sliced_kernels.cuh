@@ -149,38 +149,66 @@ __device__ __forceinline__ void add_cnt5(uint32_t (&Bp)[5], uint32_t w) {
   }
 }
 
-// XOR of the rows named by n index words starting at smem word offset o.  xbytes = byte address (shared window) of
-// this thread's column; row r sits at xbytes + r * 4T.
+// XOR of the rows named by index words; row r of this thread's column sits at xcol[r * T].
 template <int T>
-__device__ __forceinline__ uint32_t ld_row(uint32_t xbytes, uint32_t row) {
-  uint32_t v;
-  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(xbytes + row * (uint32_t)(4 * T)) : "memory");
-  return v;
+__device__ __forceinline__ uint32_t ld_row(const uint32_t* __restrict__ xcol, uint32_t row) {
+  return xcol[row * (uint32_t)T];
 }
 
 template <int T>
-__device__ __forceinline__ uint32_t xor4(uint32_t xbytes, uint32_t iw) {
-  const uint32_t a0 = ld_row<T>(xbytes, iw & 255u), a1 = ld_row<T>(xbytes, __byte_perm(iw, 0, 0x4441));
-  const uint32_t a2 = ld_row<T>(xbytes, __byte_perm(iw, 0, 0x4442)), a3 = ld_row<T>(xbytes, iw >> 24);
+__device__ __forceinline__ uint32_t xor4(const uint32_t* __restrict__ xcol, uint32_t iw) {
+  const uint32_t a0 = ld_row<T>(xcol, iw & 255u), a1 = ld_row<T>(xcol, __byte_perm(iw, 0, 0x4441));
+  const uint32_t a2 = ld_row<T>(xcol, __byte_perm(iw, 0, 0x4442)), a3 = ld_row<T>(xcol, iw >> 24);
   return (a0 ^ a1) ^ (a2 ^ a3);
 }
 
 template <int T>
-__device__ __forceinline__ uint32_t sliced_parity(const uint32_t* __restrict__ sdata, uint32_t o, int n, uint32_t xbytes) {
+__device__ __forceinline__ void rows4(const uint32_t* __restrict__ xcol, uint32_t iw, uint32_t (&r)[4]) {
+  r[0] = ld_row<T>(xcol, iw & 255u);
+  r[1] = ld_row<T>(xcol, __byte_perm(iw, 0, 0x4441));
+  r[2] = ld_row<T>(xcol, __byte_perm(iw, 0, 0x4442));
+  r[3] = ld_row<T>(xcol, iw >> 24);
+}
+
+template <int T>
+__device__ __forceinline__ uint32_t xor12(const uint32_t* __restrict__ xcol, uint32_t i0, uint32_t i1, uint32_t i2) {
+  uint32_t a[4], b[4], c[4];
+  rows4<T>(xcol, i0, a);
+  rows4<T>(xcol, i1, b);
+  rows4<T>(xcol, i2, c);
+  return (a[0] ^ a[1] ^ a[2]) ^ (a[3] ^ b[0] ^ b[1]) ^ (b[2] ^ b[3] ^ c[0]) ^ (c[1] ^ c[2] ^ c[3]);
+}
+
+template <int T>
+__device__ __forceinline__ void xor24(const uint32_t* __restrict__ xcol, uint32_t i0, uint32_t i1, uint32_t i2, uint32_t j0, uint32_t j1,
+                                      uint32_t j2, uint32_t& p1, uint32_t& p2) {
+  uint32_t a[4], b[4], c[4], d[4], e[4], f[4];
+  rows4<T>(xcol, i0, a);
+  rows4<T>(xcol, i1, b);
+  rows4<T>(xcol, i2, c);
+  rows4<T>(xcol, j0, d);
+  rows4<T>(xcol, j1, e);
+  rows4<T>(xcol, j2, f);
+  p1 = (a[0] ^ a[1] ^ a[2]) ^ (a[3] ^ b[0] ^ b[1]) ^ (b[2] ^ b[3] ^ c[0]) ^ (c[1] ^ c[2] ^ c[3]);
+  p2 = (d[0] ^ d[1] ^ d[2]) ^ (d[3] ^ e[0] ^ e[1]) ^ (e[2] ^ e[3] ^ f[0]) ^ (f[1] ^ f[2] ^ f[3]);
+}
+
+template <int T>
+__device__ __forceinline__ uint32_t sliced_parity(const uint32_t* __restrict__ sdata, uint32_t o, int n, const uint32_t* __restrict__ xcol) {
   uint32_t acc0 = 0, acc1 = 0;
   int w = 0;
   for (; w + 1 < n; w += 2) {
     const uint32_t i0 = sdata[o + w], i1 = sdata[o + w + 1];
-    acc0 ^= xor4<T>(xbytes, i0);
-    acc1 ^= xor4<T>(xbytes, i1);
+    acc0 ^= xor4<T>(xcol, i0);
+    acc1 ^= xor4<T>(xcol, i1);
   }
-  if (w < n) acc0 ^= xor4<T>(xbytes, sdata[o + w]);
+  if (w < n) acc0 ^= xor4<T>(xcol, sdata[o + w]);
   return acc0 ^ acc1;
 }
 
 template <int T, bool HAS_EXACT>
 __device__ __forceinline__ void sliced_graphs(const uint32_t* __restrict__ sdata, uint32_t off, int n_graphs, bool approx,
-                                              uint32_t xbytes, uint32_t* __restrict__ pwcol, uint32_t* __restrict__ scol,
+                                              const uint32_t* __restrict__ xcol, uint32_t* __restrict__ pwcol, uint32_t* __restrict__ scol,
                                               const SlicedTables* __restrict__ tb) {
   for (int g = 0; g < n_graphs; ++g) {
     const uint4 h0 = *reinterpret_cast<const uint4*>(sdata + off);
@@ -205,20 +233,19 @@ __device__ __forceinline__ void sliced_graphs(const uint32_t* __restrict__ sdata
       const uint4 nx1 = *reinterpret_cast<const uint4*>(sdata + o + len + 4);
       uint32_t p1, p2 = 0, ex = 0;
       if (!generic) {
-        p1 = xor4<T>(xbytes, cur0.y);
-        if (n1 > 1) p1 ^= xor4<T>(xbytes, cur0.z);
-        if (n1 > 2) p1 ^= xor4<T>(xbytes, cur0.w);
-        if (type != 0u) {
-          p2 = xor4<T>(xbytes, cur1.x);
-          if (n2 > 1) p2 ^= xor4<T>(xbytes, cur1.y);
-          if (n2 > 2) p2 ^= xor4<T>(xbytes, cur1.z);
+        // compact record: twelve rows per parity, loaded unconditionally (padding names the zero row) so that all
+        // loads of the term are in flight before the first XOR needs one
+        if (type == 0u) {
+          p1 = xor12<T>(xcol, cur0.y, cur0.z, cur0.w);
+        } else {
+          xor24<T>(xcol, cur0.y, cur0.z, cur0.w, cur1.x, cur1.y, cur1.z, p1, p2);
           ex = cur1.w;
         }
       } else {
         const uint32_t o1 = o + 1 + (type == 3u ? 1u : 0u);
         if (type == 3u) ex = sdata[o + 1];
-        p1 = sliced_parity<T>(sdata, o1, n1, xbytes);
-        if (type != 0u) p2 = sliced_parity<T>(sdata, o1 + n1, n2, xbytes);
+        p1 = sliced_parity<T>(sdata, o1, n1, xcol);
+        if (type != 0u) p2 = sliced_parity<T>(sdata, o1 + n1, n2, xcol);
       }
       if (type == 0u) {
         add_a3(A0, A1, A2, (cw >> 14) & 7u, p1);
@@ -311,7 +338,7 @@ __global__ void __launch_bounds__(T, 1) sample_sliced_kernel(const SParams prm) 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   SlicedTables* tb = reinterpret_cast<SlicedTables*>(smem + 64);
   uint32_t* xcol = smem + prm.smem_xt_off + tid;  // this thread's column: row r at xcol[r * T]
-  const uint32_t xbytes = smem_u32(xcol);
+  const const uint32_t* __restrict__ xcol = smem_u32(xcol);
   uint32_t* pwcol = smem + prm.smem_pw_off + tid;
   // S: element (s, tid) at scol + s * stride * T words, stride = 4 (exact) or 2 (approx) words; vector accesses
   uint32_t* scol = smem + prm.smem_s_off + tid * (HAS_EXACT ? 4 : 2);
@@ -402,7 +429,7 @@ __global__ void __launch_bounds__(T, 1) sample_sliced_kernel(const SParams prm) 
             mbar_wait(&bars[stage], (uint32_t)((q / prm.n_stages) & 1));
             off = (uint32_t)stage * (uint32_t)prm.stage_words;
           }
-          if (warp_active) sliced_graphs<T, HAS_EXACT>(sdata, off, (int)row[K_GRAPHS], approx, xbytes, pwcol, scol, tb);
+          if (warp_active) sliced_graphs<T, HAS_EXACT>(sdata, off, (int)row[K_GRAPHS], approx, xcol, pwcol, scol, tb);
           if (!prm.resident) {
             __syncthreads();
             if (tid == 0 && q + prm.n_stages < total_q) issue(q + prm.n_stages);

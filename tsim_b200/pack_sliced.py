@@ -94,13 +94,15 @@ def pair_factor(alpha: int, beta: int):
 GENERIC = 1 << 31
 
 
-def _term_record(cw: int, i1: list[int], i2: list[int] | None, extra: int | None) -> list[int]:
-    """Compact (4 or 8 words) or generic (padded to 4) term record."""
+def _term_record(cw: int, i1: list[int], i2: list[int] | None, extra: int | None, zero_row: int) -> list[int]:
+    """Compact (4 or 8 words) or generic (padded to 4) term record.  Unused index words of the compact form name
+    the all-zero row four times: the kernel loads all twelve rows of a parity unconditionally."""
     two = i2 is not None
+    zw = zero_row * 0x01010101
     if len(i1) <= 3 and (not two or len(i2) <= 3):
-        rec = [cw] + i1 + [0] * (3 - len(i1))
+        rec = [cw] + i1 + [zw] * (3 - len(i1))
         if two:
-            rec += i2 + [0] * (3 - len(i2)) + [extra or 0]
+            rec += i2 + [zw] * (3 - len(i2)) + [extra or 0]
         return rec
     rec = [cw | GENERIC] + ([extra] if extra is not None else []) + i1 + (i2 or [])
     return rec + [0] * ((-len(rec)) % 4)
@@ -145,7 +147,7 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
             iw = _index_words(rows, zero_row)
             if len(iw) > 63:
                 raise _Unsupported("mask too heavy")
-            terms.append(_term_record(T_LIN | (len(iw) << 2) | ((da & 7) << 14) | (bmode << 17) | (zmode << 19), iw, None, None))
+            terms.append(_term_record(T_LIN | (len(iw) << 2) | ((da & 7) << 14) | (bmode << 17) | (zmode << 19), iw, None, None, zero_row))
 
         for j in range(min(int(n.counts[g]), A)):
             ph = int(n.phases[g, j]) & 7
@@ -193,7 +195,7 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
             i1, i2 = _index_words(r1, zero_row), _index_words(r2, zero_row)
             if len(i1) > 63 or len(i2) > 63:
                 raise _Unsupported("mask too heavy")
-            terms.append(_term_record(T_PI | (len(i1) << 2) | (len(i2) << 8), i1, i2, None))
+            terms.append(_term_record(T_PI | (len(i1) << 2) | (len(i2) << 8), i1, i2, None, zero_row))
         general_ctl = []
         for j in range(min(int(q.counts[g]), D)):
             al, be = int(q.alpha[g, j]) & 7, int(q.beta[g, j]) & 7
@@ -209,7 +211,7 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
                     raise _Unsupported("too many general phase pairs in one graph")
                 slot = len(general_ctl)
                 general_ctl.append(al | (be << 3))
-                terms.append(_term_record(T_PAIR_GENERAL | (len(i1) << 2) | (len(i2) << 8) | (slot << 14), i1, i2, None))
+                terms.append(_term_record(T_PAIR_GENERAL | (len(i1) << 2) | (len(i2) << 8) | (slot << 14), i1, i2, None, zero_row))
                 continue
             # value(pa, pb) as a polynomial: base + pa d10 + pb d01 + pa pb d11 in the exponents (a mod 8, b)
             ref = nz[0]
@@ -234,7 +236,7 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
                     b_base += db  # each negative unit is counted as (~p) - 1
                 units += abs(db)
             extra |= ztt << 18
-            terms.append(_term_record(T_PAIR_MONOID | (len(i1) << 2) | (len(i2) << 8), i1, i2, extra))
+            terms.append(_term_record(T_PAIR_MONOID | (len(i1) << 2) | (len(i2) << 8), i1, i2, extra, zero_row))
 
         if units > 31:
             raise _Unsupported("b counter needs more than 5 planes")

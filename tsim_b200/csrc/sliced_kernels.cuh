@@ -338,7 +338,6 @@ __global__ void __launch_bounds__(T, 1) sample_sliced_kernel(const SParams prm) 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   SlicedTables* tb = reinterpret_cast<SlicedTables*>(smem + 64);
   uint32_t* xcol = smem + prm.smem_xt_off + tid;  // this thread's column: row r at xcol[r * T]
-  const const uint32_t* __restrict__ xcol = smem_u32(xcol);
   uint32_t* pwcol = smem + prm.smem_pw_off + tid;
   // S: element (s, tid) at scol + s * stride * T words, stride = 4 (exact) or 2 (approx) words; vector accesses
   uint32_t* scol = smem + prm.smem_s_off + tid * (HAS_EXACT ? 4 : 2);

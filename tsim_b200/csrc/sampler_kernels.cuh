@@ -313,7 +313,8 @@ __device__ __forceinline__ void eval_chunk_fast(const Src& src, uint32_t off, in
     for (int j = 0; j < nL; ++j, o += SL) {
       uint32_t r[SL];
       load_rec<SL>(src, o, r);
-      a += (uint32_t)(__popc(masked_xor<W>(x, r)) & 1) * r[W];
+      // a += parity * delta as one IMAD (the compiler's own choice is compare + select + add)
+      asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a) : "r"((uint32_t)__popc(masked_xor<W>(x, r)) & 1u), "r"(r[W]));
     }
     o = off + kFastHeaderWords + round4(nL * SL);
     // pi terms: a += 4 * (parity(psi) & parity(phi)); the constants ride on the always-one parameter bit

@@ -462,7 +462,18 @@ static int fail(int code, const std::string& msg) {
   } while (0)
 
 constexpr int kSlots = 3;            // pipeline depth of tsb_sample_host
-constexpr long long kSlice = 1 << 17;  // shots per pipeline slice
+constexpr long long kSliceDefault = 1 << 17;  // shots per pipeline slice
+static long long slice_shots() {
+  static long long v = [] {
+    if (const char* e = getenv("TSIM_B200_SLICE")) {
+      long long x = atoll(e);
+      if (x >= 1024) return x;
+    }
+    return kSliceDefault;
+  }();
+  return v;
+}
+#define kSlice slice_shots()
 
 struct Slot {
   cudaStream_t stream = nullptr;

@@ -339,3 +339,60 @@ def test_postselection_matches_unmasked_rows(no_norm_check):
     assert discarded.any() and (~discarded).any()
     comp_cols = np.setdiff1d(np.arange(7), direct_cols)
     assert not got[discarded][:, comp_cols].any()
+
+
+# ---------------------------------------------------------------------------------------------
+# int32 wrap-around: the reference's arithmetic wraps silently (exact_scalar.py:31-39); MODE_FAITHFUL must wrap the
+# same way, and the packer must refuse to reorder such programs
+# ---------------------------------------------------------------------------------------------
+
+
+def test_faithful_mode_reproduces_int32_wraparound():
+    from tsim_b200 import pack as PK
+
+    rng = np.random.default_rng(77)
+    F, n_c = 6, 2
+    levels = []
+    for k in range(n_c + 1):
+        lv = random_level(rng, G=3, P=F + k, A=44, H=2, C=2, D=3, approx=False, density=0.4, power2_range=(-3, 3))
+        lv.node_phases.counts[:] = 44
+        lv.node_phases.phases[:] = rng.choice([1, 3, 5, 7], size=lv.node_phases.phases.shape)  # no vanishing factors
+        lv.prefactor.floatfactor[:] = rng.integers(-9, 10, size=(3, 4))
+        levels.append(lv)
+    comp = CompiledComponent((0, 1), np.arange(F, dtype=np.int32), tuple(levels))
+    prog = make_program([comp], num_f=F)
+    ok, info = PK.reorder_is_exact(prog)
+    assert not ok
+    dp = _device_program(prog, "auto")
+    assert dp.info["mode"] == 0
+    with pytest.raises(ValueError):
+        PK.pack_program(prog, mode="sliced")
+    f = rng.integers(0, 2, size=(600, F)).astype(np.uint8)
+    want, want_dev = _oracle(prog, f, (6, 6))
+    got, dev = dp.sample(f, (6, 6))
+    assert np.array_equal(got, want) and _dev_equal(dev, want_dev)
+    # the wrap really happens: amplitudes differ from an int64 evaluation of the same node products
+    x = np.hstack([f[:50], np.ones((50, 0), np.uint8)])
+    amp = E.evaluate(levels[0], x)
+    assert np.array_equal(dp.evaluate(0, 0, x).view(np.uint32), amp.view(np.uint32))
+
+
+@pytest.mark.parametrize("mode", ["fast", "sliced"])
+def test_reordered_modes_agree_with_faithful_near_the_bound(mode):
+    from tsim_b200 import pack as PK
+
+    rng = np.random.default_rng(5)
+    F, n_c = 8, 2
+    levels = []
+    for k in range(n_c + 1):
+        lv = random_level(rng, G=6, P=F + k, A=18, H=3, C=3, D=2, approx=False, density=0.35, power2_range=(-6, 0))
+        lv.prefactor.floatfactor[:] = rng.integers(-3, 4, size=(6, 4))
+        levels.append(lv)
+    comp = CompiledComponent((0, 1), np.arange(F, dtype=np.int32), tuple(levels))
+    prog = make_program([comp], num_f=F)
+    ok, info = PK.reorder_is_exact(prog)
+    assert ok and info["log2_bound"] > 22
+    f = rng.integers(0, 2, size=(2000, F)).astype(np.uint8)
+    want, want_dev = _oracle(prog, f, (2, 9))
+    got, dev = _device_program(prog, mode).sample(f, (2, 9))
+    assert np.array_equal(got, want) and _dev_equal(dev, want_dev)

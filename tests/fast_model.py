@@ -10,7 +10,7 @@ import numpy as np
 
 from oracle.exact_scalar import pow2_f32, to_complex_parts
 from tsim_b200 import pack as PK
-from tsim_b200.pack_fast import FAST_HEADER_WORDS, lin_stride, pair_stride, pi_stride, round4
+from tsim_b200.pack_fast import FAST_HEADER_WORDS, lin_stride, mpair_stride, pair_stride, pi_stride, round4
 
 M32 = 0xFFFFFFFF
 W8 = np.exp(1j * np.pi / 4)
@@ -124,6 +124,12 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
                 o += SP
             a = (a + (e << 31)) & M32
             o = off + FAST_HEADER_WORDS + round4(nL * SL) + round4(nPi * SP)
+            SM = mpair_stride(W)
+            for j in range(h[7]):
+                r = data[o : o + SM]
+                pa, pb = _par(xw, r[:W]), _par(xw, r[W : 2 * W])
+                a = (a + pa * int(r[2 * W]) + pb * int(r[2 * W + 1]) + (pa & pb) * int(r[2 * W + 2])) & M32
+                o += SM
             Pp = (1, 0, 0, 0)
             for j in range(nD):
                 r = data[o : o + SD]
@@ -143,13 +149,16 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
                     S = [(S[i] + v[i] * sc) & M32 for i in range(4)]
                 else:
                     vc = np.array([_s32(t) for t in v], dtype=np.int32)
-                    tre, tim = to_complex_parts(vc[None, :], np.array([_s32(h[2])], np.int32))
+                    tre, tim = to_complex_parts(vc[None, :], np.array([0], np.int32))
+                    sc = np.array([h[2]], np.uint32).view(np.float32)[0]
+                    with np.errstate(all="ignore"):
+                        tre, tim = (tre * sc).astype(np.float32), (tim * sc).astype(np.float32)
                     are = np.array([h[5]], np.uint32).view(np.float32)[0]
                     aim = np.array([h[6]], np.uint32).view(np.float32)[0]
                     with np.errstate(all="ignore"):
                         ure = np.float32(np.float32(tre[0] * are) - np.float32(tim[0] * aim))
                         uim = np.float32(np.float32(tre[0] * aim) + np.float32(tim[0] * are))
-                        pw = pow2_f32(np.array([_s32(h[3])]))[0]
+                        pw = np.array([h[3]], np.uint32).view(np.float32)[0]
                         re = np.float32(re + np.float32(ure * pw))
                         im = np.float32(im + np.float32(uim * pw))
             off = o

@@ -263,9 +263,10 @@ __host__ __device__ constexpr int round4(int n) { return (n + 3) & ~3; }
 __host__ __device__ constexpr int fast_lin_stride(int W) { return W == 1 ? 2 : round4(W + 1); }
 __host__ __device__ constexpr int fast_pi_stride(int W) { return W == 1 ? 2 : round4(2 * W); }
 __host__ __device__ constexpr int fast_pair_stride(int W) { return round4(2 * W + 1); }
+__host__ __device__ constexpr int fast_mpair_stride(int W) { return round4(2 * W + 3); }
 constexpr int kFastHeaderWords = 16;
-// graph header: [0] nL | nPi << 12 | nD << 24   [1] acc0   [2] p_T (= n >> 2)   [3] power2
-//               [4] shift (= p_T + power2 - p_lo)   [5] approx.re  [6] approx.im  [7] -
+// graph header: [0] nL | nPi << 12 | nD << 24   [1] acc0   [2] float32 bits of 2^p_T (p_T = n >> 2)   [3] float32 bits of 2^power2
+//               [4] shift (= p_T + power2 - p_lo)   [5] approx.re  [6] approx.im  [7] number of monoid pairs
 //               [8..11] K1 = (1+w)^(n&3) * floatfactor   [12..15] K2 = K1 * sqrt2
 // acc fields:   bits 0..15 count of vanishing node factors, bits 16..28 b + 64, bits 29..31 a
 
@@ -326,7 +327,18 @@ __device__ __forceinline__ void eval_chunk_fast(const Src& src, uint32_t off, in
     }
     a += e << 31;
     o = off + kFastHeaderWords + round4(nL * SL) + round4(nPi * SP);
-    // pair terms: plain (wrapping) product of table factors
+    // monoid-type pairs: a += pa * d1 + pb * d2 + (pa & pb) * d12
+    {
+      constexpr int SM = fast_mpair_stride(W);
+      const int nM = (int)src.ld(off + 7);
+      for (int j = 0; j < nM; ++j, o += SM) {
+        uint32_t r[SM];
+        load_rec<SM>(src, o, r);
+        const uint32_t pa = (uint32_t)__popc(masked_xor<W>(x, r)) & 1u, pb = (uint32_t)__popc(masked_xor<W>(x, r + W)) & 1u;
+        a += pa * r[2 * W] + pb * r[2 * W + 1] + (pa & pb) * r[2 * W + 2];
+      }
+    }
+    // general pair terms: plain (wrapping) product of table factors
     ZW Pp = zw_make(1, 0, 0, 0);
     for (int j = 0; j < nD; ++j, o += SD) {
       uint32_t r[SD];
@@ -347,12 +359,17 @@ __device__ __forceinline__ void eval_chunk_fast(const Src& src, uint32_t off, in
         const uint32_t sc = 1u << h1.x;  // shift < 31 is guaranteed by pack.py's bound
         acc.c.c0 += v.c0 * sc; acc.c.c1 += v.c1 * sc; acc.c.c2 += v.c2 * sc; acc.c.c3 += v.c3 * sc;
       } else {
-        float tre, tim;
-        zw_to_complex(v, (int)h0.z, tre, tim);
+        // zw_to_complex with the scale 2^p_T read from the record
+        const float s2 = TSB_SQRT1_2;
+        const float f0 = __int2float_rn((int32_t)v.c0), f1 = __int2float_rn((int32_t)v.c1);
+        const float f2 = __int2float_rn((int32_t)v.c2), f3 = __int2float_rn((int32_t)v.c3);
+        const float t1 = __fmul_rn(f1, s2), t3 = __fmul_rn(f3, s2), sc = __uint_as_float(h0.z);
+        const float tre = __fmul_rn(__fadd_rn(__fadd_rn(f0, t1), t3), sc);
+        const float tim = __fmul_rn(__fsub_rn(__fadd_rn(t1, f2), t3), sc);
         const float are = __uint_as_float(h1.y), aim = __uint_as_float(h1.z);
         float ure = __fsub_rn(__fmul_rn(tre, are), __fmul_rn(tim, aim));
         float uim = __fadd_rn(__fmul_rn(tre, aim), __fmul_rn(tim, are));
-        float pw = pow2_f32((int)h0.w);
+        float pw = __uint_as_float(h0.w);
         acc.re = __fadd_rn(acc.re, __fmul_rn(ure, pw));
         acc.im = __fadd_rn(acc.im, __fmul_rn(uim, pw));
       }

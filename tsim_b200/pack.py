@@ -33,7 +33,7 @@ import numpy as np
 from .program import CompiledProgram, CompiledScalarGraphs
 
 MAGIC = 0x32425354  # "TSB2"
-VERSION = 3
+VERSION = 4
 MODE_FAITHFUL = 0
 MODE_FAST = 1
 MODE_SLICED = 2

@@ -14,8 +14,9 @@ so a graph's product of those families is described by three small integers that
 (flipping a parity maps k -> k ^ 4, which keeps n unless the factor vanishes), so the power of two
 ``n >> 2`` and the residue ``(1+w)^(n & 3)`` are folded into the graph's constants at pack time
 (``(1+w)^4 = 2 w^2 (1+sqrt2)^2``).  The device turns ``(a, b)`` back into four coefficients with a
-Pell-number table and a signed permutation; phase pairs (``terms.py:174-187``) contain other primes
-and stay a plain ring product.  The reordering is only used when ``pack.reorder_is_exact`` holds.
+Pell-number table and a signed permutation.  A phase pair (``terms.py:174-187``) whose four possible factors
+all lie in the monoid (at least one of alpha, beta even) becomes three virtual terms (pa, pb, pa and pb); the
+odd-odd pairs contain other primes and stay a plain ring product.  The reordering is only used when ``pack.reorder_is_exact`` holds.
 """
 
 from __future__ import annotations
@@ -24,11 +25,34 @@ import numpy as np
 
 from .program import CompiledScalarGraphs
 
+
+def monoid_exponents(c):
+    from .pack_sliced import monoid_exponents as f
+
+    return f(c)
+
+
+def pair_factor(alpha, beta):
+    from .pack_sliced import pair_factor as f
+
+    return f(alpha, beta)
+
 FAST_HEADER_WORDS = 16
 B_OFFSET = 64
 
 # (a, b, n) with 1 + w^k = w^a (1+sqrt2)^b (1+w)^n ; k = 4 vanishes
 MONOID = {0: (6, -2, 4), 1: (0, 0, 1), 2: (0, -1, 2), 3: (1, -1, 1), 5: (6, -1, 1), 6: (6, -1, 2), 7: (7, 0, 1)}
+
+
+def _pow2_bits(p: int) -> np.uint32:
+    """float32 bit pattern of 2**p: denormals kept, overflow -> +inf, underflow -> 0 (same as the device's pow2_f32)."""
+    if p > 127:
+        return np.uint32(0x7F800000)
+    if p >= -126:
+        return np.uint32((p + 127) << 23)
+    if p >= -149:
+        return np.uint32(1 << (p + 149))
+    return np.uint32(0)
 
 
 def round4(n: int) -> int:
@@ -45,6 +69,10 @@ def pi_stride(W: int) -> int:
 
 def pair_stride(W: int) -> int:
     return round4(2 * W + 1)
+
+
+def mpair_stride(W: int) -> int:
+    return round4(2 * W + 3)
 
 
 def _zw_mul(x, y):
@@ -135,9 +163,32 @@ def fast_level_records(lv: CompiledScalarGraphs, W: int, n_params: int):
                 continue
             pis.append((_mask_words(pm, W, pc), _mask_words(fm, W, fc)))
         pairs = []
+        mpairs = []  # phase pairs whose four possible factors all lie in the monoid: three virtual linear terms
         for j in range(min(int(q.counts[g]), D)):
-            ctl = (int(q.alpha[g, j]) & 7) | ((int(q.beta[g, j]) & 7) << 3)
-            pairs.append((_mask_words(q.alpha_params[g, j], W), _mask_words(q.beta_params[g, j], W), ctl))
+            al, be = int(q.alpha[g, j]) & 7, int(q.beta[g, j]) & 7
+            ma, mb = _mask_words(q.alpha_params[g, j], W), _mask_words(q.beta_params[g, j], W)
+            combos = [monoid_exponents(pair_factor(al ^ (4 * pa), be ^ (4 * pb))) for pb in (0, 1) for pa in (0, 1)]
+            nz = [c for c in combos if c not in (None, "zero")]
+            if not (all(c is not None for c in combos) and nz and len({c[2] for c in nz}) == 1):
+                pairs.append((ma, mb, al | (be << 3)))
+                continue
+            e = [c if c != "zero" else nz[0] for c in combos]  # exponents of a vanishing factor are irrelevant
+            zc = [1 if c == "zero" else 0 for c in combos]
+            a0 += e[0][0]
+            b0 += e[0][1]
+            z0 += zc[0]
+            n_tot += nz[0][2]
+            d = []
+            for hi, lo in (((1,), (0,)), ((2,), (0,)), ((3, 0), (1, 2))):
+                da = (sum(e[i][0] for i in hi) - sum(e[i][0] for i in lo)) & 7
+                db = sum(e[i][1] for i in hi) - sum(e[i][1] for i in lo)
+                dz = sum(zc[i] for i in hi) - sum(zc[i] for i in lo)
+                d.append((((da & 7) << 29) + (db << 16) + dz) & 0xFFFFFFFF)
+            bs = [c[1] - e[0][1] for c in e]
+            b_lo += min(bs)
+            b_hi += max(bs)
+            z_hi += max(z - zc[0] for z in zc)
+            mpairs.append((ma, mb, d))
 
         p_t = n_tot >> 2
         r = n_tot & 3
@@ -145,7 +196,7 @@ def fast_level_records(lv: CompiledScalarGraphs, W: int, n_params: int):
         b0 += 2 * p_t
         if not (0 <= b0 + B_OFFSET + b_lo and b0 + B_OFFSET + b_hi <= 127 and z0 + z_hi <= 0xFFFF):
             raise ValueError("graph exceeds the packed accumulator's field ranges")
-        if len(lin) > 0xFFF or len(pis) > 0xFFF or len(pairs) > 0xFF:
+        if len(lin) > 0xFFF or len(pis) > 0xFFF or len(pairs) > 0xFF or len(mpairs) > 0xFFFF:
             raise ValueError("too many terms in one graph for the fast record header")
         k1 = _zw_mul(ONE_PLUS_W_POW[r], tuple(int(v) for v in pre.floatfactor[g]))
         k2 = _zw_mul(k1, SQRT2)
@@ -153,11 +204,16 @@ def fast_level_records(lv: CompiledScalarGraphs, W: int, n_params: int):
             raise ValueError("graph constants overflow int32")
         power2 = int(pre.power2[g])
 
-        words = np.zeros(FAST_HEADER_WORDS + round4(len(lin) * SL) + round4(len(pis) * SP) + len(pairs) * SD, dtype=np.uint32)
+        SM = mpair_stride(W)
+        words = np.zeros(
+            FAST_HEADER_WORDS + round4(len(lin) * SL) + round4(len(pis) * SP) + len(mpairs) * SM + len(pairs) * SD, dtype=np.uint32
+        )
+        words[7] = len(mpairs)
         words[0] = len(lin) | (len(pis) << 12) | (len(pairs) << 24)
         words[1] = _pack_acc(a0, b0 + B_OFFSET, z0)
-        words[2] = np.int32(p_t).view(np.uint32)
-        words[3] = np.int32(power2).view(np.uint32)
+        # exact float32 powers of two, precomputed (the approximate branch scales by 2^p_T and 2^power2 per graph)
+        words[2] = _pow2_bits(p_t)
+        words[3] = _pow2_bits(power2)
         aff = np.complex64(pre.approximate_floatfactors[g])
         words[5] = np.float32(aff.real).view(np.uint32)
         words[6] = np.float32(aff.imag).view(np.uint32)
@@ -174,6 +230,11 @@ def fast_level_records(lv: CompiledScalarGraphs, W: int, n_params: int):
             words[o + W : o + 2 * W] = m2
             o += SP
         o = FAST_HEADER_WORDS + round4(len(lin) * SL) + round4(len(pis) * SP)
+        for m1, m2, d in mpairs:
+            words[o : o + W] = m1
+            words[o + W : o + 2 * W] = m2
+            words[o + 2 * W : o + 2 * W + 3] = d
+            o += SM
         for m1, m2, ctl in pairs:
             words[o : o + W] = m1
             words[o + W : o + 2 * W] = m2

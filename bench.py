@@ -110,10 +110,26 @@ def make_workload(shots: int, seed: int = 12345):
 
 
 def cpu_reference_run(prog, f_sample, key, steps: int, warmup: int):
-    """Oracle on all host cores; returns (shots/s, cores, description)."""
+    """CPU restatement of the reference path on all host cores; returns (shots/s, cores, seconds per step, what ran).
+
+    Preferred: the C restatement (oracle/c/oracle.c, validated bit for bit against the NumPy oracle) on a thread pool;
+    fallback when gcc is missing: the NumPy oracle on a process pool."""
+    cores = os.cpu_count() or 1
+    try:
+        from oracle import cport
+
+        cport.load()
+        for _ in range(max(1, warmup)):
+            cport.sample_program(prog, f_sample[: max(cores * 64, 512)], key, threads=cores)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cport.sample_program(prog, f_sample, key, threads=cores)
+        dt = time.perf_counter() - t0
+        return steps * f_sample.shape[0] / dt, cores, dt / steps, "C restatement of the reference path (oracle/c/oracle.c), thread pool"
+    except Exception as exc:  # pragma: no cover - depends on the box
+        log(f"[bench] C oracle unavailable ({exc}); timing the NumPy oracle")
     from oracle.parallel import OraclePool
 
-    cores = os.cpu_count() or 1
     pool = OraclePool(prog, key, cores)
     try:
         for _ in range(warmup):
@@ -124,7 +140,7 @@ def cpu_reference_run(prog, f_sample, key, steps: int, warmup: int):
         dt = time.perf_counter() - t0
     finally:
         pool.close()
-    return steps * f_sample.shape[0] / dt, cores, dt / steps
+    return steps * f_sample.shape[0] / dt, cores, dt / steps, "NumPy restatement of the reference path (oracle/), process pool"
 
 
 def run_reference(args):
@@ -136,11 +152,11 @@ def run_reference(args):
     f = cs.sample(sample)
     key = (0, 42)
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    # bounded: the oracle does about 1.5e3 shots/s/core, keep the whole run within minutes
+    # bounded: the C restatement does about 1e4 shots/s/core; 2^20 shots per step on 16 cores is about 8 s
     steps = min(steps, 5)
     warmup = min(warmup, 1)
-    value, cores, sec = cpu_reference_run(prog, f, key, steps, warmup)
-    desc = f"{sample} shots per step of the {WORKLOAD} workload (same program, same noise model), {steps} steps"
+    value, cores, sec, what = cpu_reference_run(prog, f, key, steps, warmup)
+    desc = f"{sample} shots per step of the {WORKLOAD} workload (same program, same noise model), {steps} steps; {what}"
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -155,7 +171,7 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "int32+f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "shots_per_step": sample, "note": "NumPy restatement of the reference path (jax not installable here), multiprocessing over shot slices"},
+        "config": {"workload": WORKLOAD, "shots_per_step": sample, "note": "CPU restatement of the reference path (jax not installable here), all host cores: " + what},
         "cpu_baseline": {"value": value, "unit": "shots/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -371,13 +387,13 @@ def run_gpu(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         fs = cs.sample(args.cpu_shots)
-        v, cores, sec = cpu_reference_run(prog, fs, (0, 42), 1, 1)
+        v, cores, sec, what = cpu_reference_run(prog, fs, (0, 42), 1, 1)
         cpu = {
             "value": v,
             "unit": "shots/s",
             "cores": cores,
             "kind": "port",
-            "sample": f"{args.cpu_shots} shots of the same workload, 1 warm-up + 1 timed pass ({sec:.1f} s)",
+            "sample": f"{args.cpu_shots} shots of the same workload, 1 warm-up + 1 timed pass ({sec:.1f} s); {what}",
         }
 
     line = {
@@ -427,7 +443,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--shots", type=int, default=1_000_000)
-    ap.add_argument("--cpu-shots", type=int, default=16384)
+    ap.add_argument("--cpu-shots", type=int, default=1 << 20)
     ap.add_argument("--mode", default="auto", choices=["auto", "fast", "faithful", "sliced"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")

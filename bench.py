@@ -443,7 +443,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--shots", type=int, default=1_000_000)
-    ap.add_argument("--cpu-shots", type=int, default=1 << 20)
+    ap.add_argument("--cpu-shots", type=int, default=1 << 22)
     ap.add_argument("--mode", default="auto", choices=["auto", "fast", "faithful", "sliced"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")

@@ -226,6 +226,23 @@ class DeviceChannelSampler:
         )
         return out
 
+    def sample_device(self, d_f: int, num_samples: int, *, shot_offset: int = 0, call: int | None = None,
+                      skip_shot0: bool = False, stream: int = 0) -> None:
+        """Write packed rows for in-batch shots ``[shot_offset, shot_offset + num_samples)`` into the device buffer
+        at address ``d_f`` (e.g. ``torch.Tensor.data_ptr()``); asynchronous on ``stream``."""
+        import ctypes as C
+
+        from . import _lib
+
+        if call is None:
+            call = self.next_call()
+        _lib.check(
+            self._lib.tsb_noise_sample_device(
+                self._h, int(num_samples), int(shot_offset), self.seed, int(call), int(skip_shot0), C.c_void_p(d_f),
+                C.c_void_p(stream) if stream else None,
+            )
+        )
+
     def sample(self, num_samples: int = 1, **kw) -> np.ndarray:
         """Dense ``uint8[num_samples, num_f]`` (the reference's format)."""
         packed = self.sample_packed(num_samples, **kw)

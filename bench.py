@@ -104,7 +104,7 @@ def make_workload(shots: int, seed: int = 12345):
     from tsim_b200.noise import ChannelSampler
     from tsim_b200.synthetic import noise_probs, synthetic_program
 
-    prog = synthetic_program(WORKLOAD)
+    prog = synthetic_program(os.environ.get("TSIM_B200_BENCH_WORKLOAD", WORKLOAD))
     cs = ChannelSampler.from_bit_probs(noise_probs(prog.infer_num_f(), 1e-3), seed=seed)
     return prog, cs
 
@@ -410,12 +410,12 @@ def run_gpu(args):
         "dtype": "int32+f32",
         "data": "synthetic",
         "config": {
-            "workload": WORKLOAD,
+            "workload": args.workload,
             "shots_per_gpu_per_step": shots,
             "batch_size": shots,
             "num_f": info["num_f"],
             "num_outputs": n_out,
-            "stabiliser_terms": 148,
+            "stabiliser_terms": int(sum(lv.num_graphs for c in prog.components for lv in c.compiled_scalar_graphs)),
             "kernel_mode": ("faithful", "fast", "sliced")[info["mode"]],
             "g_resident_in_smem": bool(info["resident"]),
             "l2": f"inputs/outputs rotate over {n_buf} buffer pairs ({n_buf * per_step_bytes / 1e6:.0f} MB > 126 MB L2)",
@@ -447,7 +447,9 @@ def main():
     ap.add_argument("--mode", default="auto", choices=["auto", "fast", "faithful", "sliced"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--workload", default=WORKLOAD, help="synthetic configuration (default: the headline cfg2_distill35)")
     args = ap.parse_args()
+    os.environ["TSIM_B200_BENCH_WORKLOAD"] = args.workload
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -22,7 +22,7 @@
 
 namespace tsb {
 
-constexpr int kThreads = 768;
+constexpr int kThreads = 1024;
 
 struct KParams {
   const uint32_t* __restrict__ blob;  // whole blob in HBM

@@ -31,7 +31,8 @@ constexpr int kBarWords = 64;
 constexpr int kMaxStages = 32;
 
 template <int W, int MODE>
-__global__ void __launch_bounds__(kThreads, 1) sample_kernel(const KParams prm) {
+__global__ void __launch_bounds__(threads_for_words(W), 1) sample_kernel(const KParams prm) {
+  constexpr int kThreads = threads_for_words(W);
   extern __shared__ __align__(128) uint32_t smem[];
   const uint32_t* __restrict__ blob = prm.blob;
   const int tid = threadIdx.x;
@@ -462,7 +463,7 @@ static int fail(int code, const std::string& msg) {
   } while (0)
 
 constexpr int kSlots = 3;            // pipeline depth of tsb_sample_host
-constexpr long long kSliceDefault = 98304;  // shots per pipeline slice (192 tiles; best of the sweep in tools/sweep_slice.py)
+constexpr long long kSliceDefault = 98304;  // shots per pipeline slice (128 tiles of 768; best of the sweep in tools/sweep_slice.py)
 static long long slice_shots() {
   static long long v = [] {
     if (const char* e = getenv("TSIM_B200_SLICE")) {
@@ -642,6 +643,7 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
 
   // shared-memory plan
   const int wf32 = 2 * (int)blob[H_WF64], wout32 = 2 * (int)blob[H_WOUT64];
+  const int kThreads = threads_for_words(W);
   int fixed_words = kBarWords + (int)(sizeof(Tables) / 4) + (wf32 + wout32) * kThreads;
   if (mode == kModeSliced) {
     p->is_sliced = 1;
@@ -772,6 +774,7 @@ static int launch_sample_rows(tsb_program* p, const uint64_t* d_f, long long B, 
   KParams k;
   k.blob = p->d_blob; k.f = d_f; k.out = d_out; k.norm_dev = d_norm_dev; k.subkeys = d_subkeys;
   k.B = B; k.shot_offset = shot_offset;
+  const int kThreads = p->info.threads;
   k.n_tiles = (int)((B + kThreads - 1) / kThreads);
   k.resident = p->info.resident; k.n_stages = p->n_stages; k.stage_words = p->stage_words; k.smem_data_off = p->smem_data_off;
   k.rows = rows; k.n_rows = n_rows;

@@ -24,7 +24,7 @@ namespace tsb {
 
 // threads per CTA of the per-row sampling kernel: more resident warps hide the POPC / LDS latencies (measured on cfg2:
 // 512 -> 3.82 ms, 768 -> 3.27 ms, 1024 -> 3.27 ms); wide parameter vectors need the registers of the 512-thread shape
-__host__ __device__ constexpr int threads_for_words(int W) { return W <= 2 ? 768 : 512; }
+__host__ __device__ constexpr int threads_for_words(int W) { return W <= 4 ? 768 : 512; }
 
 struct KParams {
   const uint32_t* __restrict__ blob;  // whole blob in HBM

@@ -463,7 +463,7 @@ static int fail(int code, const std::string& msg) {
   } while (0)
 
 constexpr int kSlots = 3;            // pipeline depth of tsb_sample_host
-constexpr long long kSliceDefault = 98304;  // shots per pipeline slice (128 tiles of 768; best of the sweep in tools/sweep_slice.py)
+constexpr long long kSliceDefault = 262144;  // shots per pipeline slice (best of the sweep in tools/sweep_slice.py)
 static long long slice_shots() {
   static long long v = [] {
     if (const char* e = getenv("TSIM_B200_SLICE")) {

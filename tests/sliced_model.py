@@ -2,26 +2,15 @@
 
 Words are Python integers with one bit per shot, so the model follows the kernel's plane arithmetic literally
 (XOR of rows per parity, 3-plane adder for ``a``, ripple counter for ``b``, OR-plane for vanishing factors) and
-then decodes per shot exactly like the kernel's second phase.  CPU test infrastructure only.
+then, per shot, gathers the plane bits into an index and adds the decode-table entry exactly like the kernel's
+second phase.  CPU test infrastructure only.
 """
 
 import numpy as np
 
-from fast_model import M32, PAIR, PELL, _mul, _s32
-from oracle.exact_scalar import pow2_f32, to_complex_parts
+from fast_model import M32, _s32
 from tsim_b200 import pack as PK
 from tsim_b200.pack_sliced import SLICED_HEADER_WORDS
-
-
-def _rot(v, a):
-    c0, c1, c2, c3 = v
-    if a & 1:
-        c0, c1, c2, c3 = c3, c0, c1, -c2
-    if a & 2:
-        c0, c1, c2, c3 = -c2, c3, c0, -c1
-    if a & 4:
-        c0, c1, c2, c3 = -c0, -c1, -c2, -c3
-    return tuple(x & M32 for x in (c0, c1, c2, c3))
 
 
 def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarray):
@@ -56,11 +45,13 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
         return acc
 
     for c in range(int(lvl[7]), int(lvl[7]) + int(lvl[8])):
-        off, _, ng, _ = (int(v) for v in chunks[c])
+        coff, _, ng, _ = (int(v) for v in chunks[c])
         for _g in range(ng):
+            off = coff + int(data[coff + _g])  # directory: chunk-relative record offsets
             h = [int(v) for v in data[off : off + SLICED_HEADER_WORDS]]
             n_terms, n_gen = h[0] & 0xFFFF, h[0] >> 16
-            b_base64, nb = h[1] & 0xFF, (h[1] >> 8) & 0xFF
+            n_idx, nb = h[1] & 0xFF, (h[1] >> 8) & 0xFF
+            tbl = coff + h[2]
             A = [0, 0, 0]
             Bp = [0] * 5
             Z = 0
@@ -133,34 +124,22 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
                             wb = pb if combo & 2 else ~pb & full
                             Z |= wa & wb
                 o += length
-            k1, k2 = h[8:12], h[12:16]
             for s in range(N):
                 if (Z >> s) & 1:
                     continue
-                a = ((A[0] >> s) & 1) | (((A[1] >> s) & 1) << 1) | (((A[2] >> s) & 1) << 2)
-                cnt = sum(((Bp[k] >> s) & 1) << k for k in range(5))
-                Pb, Qb = PELL[(b_base64 + cnt) & 127]
-                v = tuple((k1[i] * Pb + k2[i] * Qb) & M32 for i in range(4))
-                v = _rot(v, a)
+                planes = A + Bp[:nb]
                 for slot in range(n_gen):
-                    ctl = (h[16 + slot // 4] >> (8 * (slot % 4))) & 63
-                    pa, pb = gen[slot]
-                    v = _mul(v, PAIR[(ctl ^ (((pa >> s) & 1) << 2) ^ (((pb >> s) & 1) << 5)) & 63])
+                    planes = planes + list(gen[slot])
+                assert len(planes) == n_idx
+                idx = sum(((pl >> s) & 1) << k for k, pl in enumerate(planes))
                 if not approx:
-                    sc = 1 << h[4]
-                    S[s] = [(S[s][i] + v[i] * sc) & M32 for i in range(4)]
+                    e = [int(v) for v in data[tbl + 4 * idx : tbl + 4 * idx + 4]]
+                    S[s] = [(S[s][i] + e[i]) & M32 for i in range(4)]
                 else:
-                    vc = np.array([_s32(t) for t in v], dtype=np.int32)
-                    tre, tim = to_complex_parts(vc[None, :], np.array([_s32(h[2])], np.int32))
-                    are = np.array([h[5]], np.uint32).view(np.float32)[0]
-                    aim = np.array([h[6]], np.uint32).view(np.float32)[0]
+                    e = data[tbl + 2 * idx : tbl + 2 * idx + 2].view(np.float32)
                     with np.errstate(all="ignore"):
-                        ure = np.float32(np.float32(tre[0] * are) - np.float32(tim[0] * aim))
-                        uim = np.float32(np.float32(tre[0] * aim) + np.float32(tim[0] * are))
-                        pw = pow2_f32(np.array([_s32(h[3])]))[0]
-                        RE[s] = np.float32(RE[s] + np.float32(ure * pw))
-                        IM[s] = np.float32(IM[s] + np.float32(uim * pw))
-            off += h[7]
+                        RE[s] = np.float32(RE[s] + e[0])
+                        IM[s] = np.float32(IM[s] + e[1])
     out = []
     for s in range(N):
         if approx:

@@ -14,6 +14,8 @@ DEPS = [
     os.path.join(HERE, "csrc", "sampler_kernels.cuh"),
     os.path.join(HERE, "csrc", "zomega.cuh"),
     os.path.join(HERE, "csrc", "blob.h"),
+    os.path.join(HERE, "csrc", "sliced_kernels.cuh"),
+    os.path.join(HERE, "csrc", "noise_kernels.cuh"),
     os.path.join(os.path.dirname(HERE), "include", "tsim_b200.h"),
 ]
 

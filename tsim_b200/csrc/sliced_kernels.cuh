@@ -20,9 +20,8 @@
 
 namespace tsb {
 
-constexpr int kSlicedMaxThreads = 256;
-constexpr int kSlicedHeaderWords = 20;
-constexpr int kMaxGeneralPairs = 8;
+constexpr int kSlicedHeaderWords = 8;
+constexpr int kPlaneRows = 12;  // "vanished" plane + up to 11 index planes (pack_sliced.MAX_INDEX_BITS)
 
 struct SParams {
   const uint32_t* __restrict__ blob;     // sliced blob
@@ -33,22 +32,16 @@ struct SParams {
   long long shot_offset;
   int n_slabs;
   int slab_cap;
-  int per_cta;  // slabs per CTA per round
+  int n_groups;  // groups of 32 slabs
+  int ng;        // groups per CTA per round
   int rounds;
-  int resident;
   int n_stages;
   int stage_words;
-  int smem_xt_off;    // word offsets inside dynamic shared memory
-  int smem_pw_off;
-  int smem_s_off;
+  int smem_xt_off;  // word offsets inside dynamic shared memory
+  int smem_pl_off;
   int smem_prev_off;
   int smem_data_off;
-  int rows;           // zero_row + 1
-};
-
-struct SlicedTables {
-  int4 pair[64];
-  int2 pell[128];
+  int rows;  // zero_row + 1
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -120,10 +113,12 @@ __global__ void __launch_bounds__(256) assemble_out_kernel(const uint32_t* __res
 // ---------------------------------------------------------------------------------------------
 // K1s
 // ---------------------------------------------------------------------------------------------
-// Per-thread state lives in private shared-memory columns (index [row][tid], so a warp access is one conflict-free
-// wavefront): the transposed parameters xt, the parity words of general pairs pw, the per-shot level accumulators S and
-// the chain-rule state prev.  Keeping S / prev out of registers lets the per-shot loops stay rolled: the hot loop
-// body must fit the 32 KB instruction cache (a 32x unrolled body ran at 26 % issue, stalled on instruction fetch).
+// A *group* of SPLIT warps owns 32 slabs (lane = slab, 1024 shots).  The group's transposed parameter matrix sits in
+// shared memory ([row][lane], one conflict-free wavefront per access).  The graphs of a chunk are handed out in waves
+// of SPLIT: warp w of the group runs phase 1 (bit-sliced term stream -> planes) for graph wave + w and parks the
+// planes in shared memory; after a group barrier every warp runs phase 2 for ITS 32 / SPLIT shots of each slab over
+// the wave's graphs in order (the approximate branch is a sequential float sum over graphs): gather the plane bits
+// into the index, add the decode-table entry.  Level accumulators stay in registers.
 __device__ __forceinline__ void add_a3(uint32_t& A0, uint32_t& A1, uint32_t& A2, uint32_t da, uint32_t p) {
   if (da & 1u) {
     const uint32_t c0 = A0 & p;
@@ -149,199 +144,197 @@ __device__ __forceinline__ void add_cnt5(uint32_t (&Bp)[5], uint32_t w) {
   }
 }
 
-// XOR of the rows named by index words; row r of this thread's column sits at xcol[r * T].
-template <int T>
-__device__ __forceinline__ uint32_t ld_row(const uint32_t* __restrict__ xcol, uint32_t row) {
-  return xcol[row * (uint32_t)T];
-}
+// row r of this lane's column sits at xcol[r * 32]
+__device__ __forceinline__ uint32_t ld_row(const uint32_t* __restrict__ xcol, uint32_t row) { return xcol[row * 32u]; }
 
-template <int T>
 __device__ __forceinline__ uint32_t xor4(const uint32_t* __restrict__ xcol, uint32_t iw) {
-  const uint32_t a0 = ld_row<T>(xcol, iw & 255u), a1 = ld_row<T>(xcol, __byte_perm(iw, 0, 0x4441));
-  const uint32_t a2 = ld_row<T>(xcol, __byte_perm(iw, 0, 0x4442)), a3 = ld_row<T>(xcol, iw >> 24);
+  const uint32_t a0 = ld_row(xcol, iw & 255u), a1 = ld_row(xcol, __byte_perm(iw, 0, 0x4441));
+  const uint32_t a2 = ld_row(xcol, __byte_perm(iw, 0, 0x4442)), a3 = ld_row(xcol, iw >> 24);
   return (a0 ^ a1) ^ (a2 ^ a3);
 }
 
-template <int T>
 __device__ __forceinline__ void rows4(const uint32_t* __restrict__ xcol, uint32_t iw, uint32_t (&r)[4]) {
-  r[0] = ld_row<T>(xcol, iw & 255u);
-  r[1] = ld_row<T>(xcol, __byte_perm(iw, 0, 0x4441));
-  r[2] = ld_row<T>(xcol, __byte_perm(iw, 0, 0x4442));
-  r[3] = ld_row<T>(xcol, iw >> 24);
+  r[0] = ld_row(xcol, iw & 255u);
+  r[1] = ld_row(xcol, __byte_perm(iw, 0, 0x4441));
+  r[2] = ld_row(xcol, __byte_perm(iw, 0, 0x4442));
+  r[3] = ld_row(xcol, iw >> 24);
 }
 
-template <int T>
 __device__ __forceinline__ uint32_t xor12(const uint32_t* __restrict__ xcol, uint32_t i0, uint32_t i1, uint32_t i2) {
   uint32_t a[4], b[4], c[4];
-  rows4<T>(xcol, i0, a);
-  rows4<T>(xcol, i1, b);
-  rows4<T>(xcol, i2, c);
+  rows4(xcol, i0, a);
+  rows4(xcol, i1, b);
+  rows4(xcol, i2, c);
   return (a[0] ^ a[1] ^ a[2]) ^ (a[3] ^ b[0] ^ b[1]) ^ (b[2] ^ b[3] ^ c[0]) ^ (c[1] ^ c[2] ^ c[3]);
 }
 
-template <int T>
 __device__ __forceinline__ void xor24(const uint32_t* __restrict__ xcol, uint32_t i0, uint32_t i1, uint32_t i2, uint32_t j0, uint32_t j1,
                                       uint32_t j2, uint32_t& p1, uint32_t& p2) {
   uint32_t a[4], b[4], c[4], d[4], e[4], f[4];
-  rows4<T>(xcol, i0, a);
-  rows4<T>(xcol, i1, b);
-  rows4<T>(xcol, i2, c);
-  rows4<T>(xcol, j0, d);
-  rows4<T>(xcol, j1, e);
-  rows4<T>(xcol, j2, f);
+  rows4(xcol, i0, a);
+  rows4(xcol, i1, b);
+  rows4(xcol, i2, c);
+  rows4(xcol, j0, d);
+  rows4(xcol, j1, e);
+  rows4(xcol, j2, f);
   p1 = (a[0] ^ a[1] ^ a[2]) ^ (a[3] ^ b[0] ^ b[1]) ^ (b[2] ^ b[3] ^ c[0]) ^ (c[1] ^ c[2] ^ c[3]);
   p2 = (d[0] ^ d[1] ^ d[2]) ^ (d[3] ^ e[0] ^ e[1]) ^ (e[2] ^ e[3] ^ f[0]) ^ (f[1] ^ f[2] ^ f[3]);
 }
 
-template <int T>
-__device__ __forceinline__ uint32_t sliced_parity(const uint32_t* __restrict__ sdata, uint32_t o, int n, const uint32_t* __restrict__ xcol) {
+__device__ __forceinline__ uint32_t sliced_parity(const uint32_t* __restrict__ cbase, uint32_t o, int n, const uint32_t* __restrict__ xcol) {
   uint32_t acc0 = 0, acc1 = 0;
   int w = 0;
   for (; w + 1 < n; w += 2) {
-    const uint32_t i0 = sdata[o + w], i1 = sdata[o + w + 1];
-    acc0 ^= xor4<T>(xcol, i0);
-    acc1 ^= xor4<T>(xcol, i1);
+    const uint32_t i0 = cbase[o + w], i1 = cbase[o + w + 1];
+    acc0 ^= xor4(xcol, i0);
+    acc1 ^= xor4(xcol, i1);
   }
-  if (w < n) acc0 ^= xor4<T>(xcol, sdata[o + w]);
+  if (w < n) acc0 ^= xor4(xcol, cbase[o + w]);
   return acc0 ^ acc1;
 }
 
-template <int T, bool HAS_EXACT>
-__device__ __forceinline__ void sliced_graphs(const uint32_t* __restrict__ sdata, uint32_t off, int n_graphs, bool approx,
-                                              const uint32_t* __restrict__ xcol, uint32_t* __restrict__ pwcol, uint32_t* __restrict__ scol,
-                                              const SlicedTables* __restrict__ tb) {
-  for (int g = 0; g < n_graphs; ++g) {
-    const uint4 h0 = *reinterpret_cast<const uint4*>(sdata + off);
-    const uint4 h1 = *reinterpret_cast<const uint4*>(sdata + off + 4);
-    const int n_terms = (int)(h0.x & 0xFFFFu), n_gen = (int)(h0.x >> 16);
-    const uint32_t b64 = h0.y & 0xFFu;
-    uint32_t A0 = 0, A1 = 0, A2 = 0, Z = 0;
-    uint32_t Bp[5] = {0, 0, 0, 0, 0};
-    // ---- phase 1: bit-sliced accumulation over the term stream (software-pipelined: the next term's record is
-    //      fetched while the current term's rows are in flight)
-    uint32_t o = off + kSlicedHeaderWords;
-    uint4 cur0 = *reinterpret_cast<const uint4*>(sdata + o), cur1 = *reinterpret_cast<const uint4*>(sdata + o + 4);
-    for (int t = 0; t < n_terms; ++t) {
-      const uint32_t cw = cur0.x;
-      const uint32_t type = cw & 3u;
-      const int n1 = (int)((cw >> 2) & 63u), n2 = (int)((cw >> 8) & 63u);
-      const bool generic = (cw >> 31) != 0u;
-      uint32_t len;
-      if (!generic) len = type == 0u ? 4u : 8u;
-      else len = (uint32_t)round4(1 + (type == 3u ? 1 : 0) + n1 + (type != 0u ? n2 : 0));
-      const uint4 nx0 = *reinterpret_cast<const uint4*>(sdata + o + len);
-      const uint4 nx1 = *reinterpret_cast<const uint4*>(sdata + o + len + 4);
-      uint32_t p1, p2 = 0, ex = 0;
-      if (!generic) {
-        // compact record: twelve rows per parity, loaded unconditionally (padding names the zero row) so that all
-        // loads of the term are in flight before the first XOR needs one
-        if (type == 0u) {
-          p1 = xor12<T>(xcol, cur0.y, cur0.z, cur0.w);
-        } else {
-          xor24<T>(xcol, cur0.y, cur0.z, cur0.w, cur1.x, cur1.y, cur1.z, p1, p2);
-          ex = cur1.w;
-        }
-      } else {
-        const uint32_t o1 = o + 1 + (type == 3u ? 1u : 0u);
-        if (type == 3u) ex = sdata[o + 1];
-        p1 = sliced_parity<T>(sdata, o1, n1, xcol);
-        if (type != 0u) p2 = sliced_parity<T>(sdata, o1 + n1, n2, xcol);
-      }
+// phase 1: the term stream of one graph for the 32 slabs of the group -> plane rows plw[r * 32]:
+// r = 0 "some factor vanished", 1..3 a, 4..4+nb-1 the b counter, then (pa, pb) of every general pair
+__device__ __forceinline__ void sliced_phase1(const uint32_t* __restrict__ cbase, uint32_t rec, const uint32_t* __restrict__ xcol,
+                                              uint32_t* __restrict__ plw) {
+  const uint4 h0 = *reinterpret_cast<const uint4*>(cbase + rec);
+  const int n_terms = (int)(h0.x & 0xFFFFu);
+  const uint32_t nb = (h0.y >> 8) & 0xFFu;
+  uint32_t A0 = 0, A1 = 0, A2 = 0, Z = 0;
+  uint32_t Bp[5] = {0, 0, 0, 0, 0};
+  // software-pipelined: the next term's record is fetched while the current term's rows are in flight
+  uint32_t o = rec + kSlicedHeaderWords;
+  uint4 cur0 = *reinterpret_cast<const uint4*>(cbase + o), cur1 = *reinterpret_cast<const uint4*>(cbase + o + 4);
+  for (int t = 0; t < n_terms; ++t) {
+    const uint32_t cw = cur0.x;
+    const uint32_t type = cw & 3u;
+    const int n1 = (int)((cw >> 2) & 63u), n2 = (int)((cw >> 8) & 63u);
+    const bool generic = (cw >> 31) != 0u;
+    uint32_t len;
+    if (!generic) len = type == 0u ? 4u : 8u;
+    else len = (uint32_t)round4(1 + (type == 3u ? 1 : 0) + n1 + (type != 0u ? n2 : 0));
+    const uint4 nx0 = *reinterpret_cast<const uint4*>(cbase + o + len);
+    const uint4 nx1 = *reinterpret_cast<const uint4*>(cbase + o + len + 4);
+    uint32_t p1, p2 = 0, ex = 0;
+    if (!generic) {
+      // compact record: twelve rows per parity, loaded unconditionally (padding names the zero row) so that all
+      // loads of the term are in flight before the first XOR needs one
       if (type == 0u) {
-        add_a3(A0, A1, A2, (cw >> 14) & 7u, p1);
-        const uint32_t bm = (cw >> 17) & 3u, zm = (cw >> 19) & 3u;
-        if (bm) add_cnt5(Bp, bm == 1u ? p1 : ~p1);
-        if (zm) Z |= (zm == 1u ? p1 : ~p1);
-      } else if (type == 1u) {
-        A2 ^= p1 & p2;
-      } else if (type == 2u) {
-        const uint32_t slot = (cw >> 14) & 15u;
-        pwcol[(2 * slot) * T] = p1;
-        pwcol[(2 * slot + 1) * T] = p2;
+        p1 = xor12(xcol, cur0.y, cur0.z, cur0.w);
       } else {
-        const uint32_t wd[3] = {p1, p2, p1 & p2};
+        xor24(xcol, cur0.y, cur0.z, cur0.w, cur1.x, cur1.y, cur1.z, p1, p2);
+        ex = cur1.w;
+      }
+    } else {
+      const uint32_t o1 = o + 1 + (type == 3u ? 1u : 0u);
+      if (type == 3u) ex = cbase[o + 1];
+      p1 = sliced_parity(cbase, o1, n1, xcol);
+      if (type != 0u) p2 = sliced_parity(cbase, o1 + n1, n2, xcol);
+    }
+    if (type == 0u) {
+      add_a3(A0, A1, A2, (cw >> 14) & 7u, p1);
+      const uint32_t bm = (cw >> 17) & 3u, zm = (cw >> 19) & 3u;
+      if (bm) add_cnt5(Bp, bm == 1u ? p1 : ~p1);
+      if (zm) Z |= (zm == 1u ? p1 : ~p1);
+    } else if (type == 1u) {
+      A2 ^= p1 & p2;
+    } else if (type == 2u) {
+      const uint32_t r0 = 4u + nb + 2u * ((cw >> 14) & 15u);
+      plw[r0 * 32u] = p1;
+      plw[(r0 + 1u) * 32u] = p2;
+    } else {
+      const uint32_t wd[3] = {p1, p2, p1 & p2};
 #pragma unroll
-        for (int v = 0; v < 3; ++v) {
-          add_a3(A0, A1, A2, (ex >> (6 * v)) & 7u, wd[v]);
-          const int db = (int)((ex >> (6 * v + 3)) & 7u) - 3;
-          const uint32_t w = db > 0 ? wd[v] : ~wd[v];
-          for (int r = 0; r < (db < 0 ? -db : db); ++r) add_cnt5(Bp, w);
-        }
-        const uint32_t ztt = (ex >> 18) & 15u;
-        if (ztt & 1u) Z |= ~p1 & ~p2;
-        if (ztt & 2u) Z |= p1 & ~p2;
-        if (ztt & 4u) Z |= ~p1 & p2;
-        if (ztt & 8u) Z |= p1 & p2;
+      for (int v = 0; v < 3; ++v) {
+        add_a3(A0, A1, A2, (ex >> (6 * v)) & 7u, wd[v]);
+        const int db = (int)((ex >> (6 * v + 3)) & 7u) - 3;
+        const uint32_t w = db > 0 ? wd[v] : ~wd[v];
+        for (int r = 0; r < (db < 0 ? -db : db); ++r) add_cnt5(Bp, w);
       }
-      o += len;
-      cur0 = nx0;
-      cur1 = nx1;
+      const uint32_t ztt = (ex >> 18) & 15u;
+      if (ztt & 1u) Z |= ~p1 & ~p2;
+      if (ztt & 2u) Z |= p1 & ~p2;
+      if (ztt & 4u) Z |= ~p1 & p2;
+      if (ztt & 8u) Z |= p1 & p2;
     }
-    // ---- phase 2: per-shot decode and accumulation
-    const uint4 k1 = *reinterpret_cast<const uint4*>(sdata + off + 8);
-    const uint4 k2 = *reinterpret_cast<const uint4*>(sdata + off + 12);
-    const uint2 ctlw = *reinterpret_cast<const uint2*>(sdata + off + 16);
-    const float are = __uint_as_float(h1.y), aim = __uint_as_float(h1.z);
-    const float sc = pow2_f32((int)h0.z), pw = pow2_f32((int)h0.w);
-    const uint32_t fx = 1u << (h1.x & 31u);
-    // cnt: five count planes -> one word per plane; a: three planes
-#pragma unroll 4
-    for (int s = 0; s < 32; ++s) {
-      if ((Z >> s) & 1u) continue;
-      const uint32_t a = ((A0 >> s) & 1u) | (((A1 >> s) & 1u) << 1) | (((A2 >> s) & 1u) << 2);
-      const uint32_t cnt = ((Bp[0] >> s) & 1u) | (((Bp[1] >> s) & 1u) << 1) | (((Bp[2] >> s) & 1u) << 2) |
-                           (((Bp[3] >> s) & 1u) << 3) | (((Bp[4] >> s) & 1u) << 4);
-      const int2 pq = tb->pell[(b64 + cnt) & 127u];
-      const uint32_t P = (uint32_t)pq.x, Q = (uint32_t)pq.y;
-      ZW v = ZW{k1.x * P + k2.x * Q, k1.y * P + k2.y * Q, k1.z * P + k2.z * Q, k1.w * P + k2.w * Q};
-      v = zw_rotate(v, a);
-      for (int slot = 0; slot < n_gen; ++slot) {
-        const uint32_t ctl = ((slot < 4 ? ctlw.x : ctlw.y) >> (8 * (slot & 3))) & 63u;
-        const uint32_t pa = (pwcol[(2 * slot) * T] >> s) & 1u;
-        const uint32_t pb = (pwcol[(2 * slot + 1) * T] >> s) & 1u;
-        v = zw_mul(v, zw_from(tb->pair[(ctl ^ (pa << 2) ^ (pb << 5)) & 63u]));
-      }
-      if (!approx) {
-        if constexpr (HAS_EXACT) {
-          uint4* sp = reinterpret_cast<uint4*>(scol) + s * T;
-          uint4 acc = *sp;
-          acc.x += v.c0 * fx; acc.y += v.c1 * fx; acc.z += v.c2 * fx; acc.w += v.c3 * fx;
-          *sp = acc;
-        }
+    o += len;
+    cur0 = nx0;
+    cur1 = nx1;
+  }
+  plw[0] = Z;
+  plw[32] = A0;
+  plw[64] = A1;
+  plw[96] = A2;
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+    if ((uint32_t)i < nb) plw[(4 + i) * 32] = Bp[i];
+}
+
+template <bool HAS_EXACT>
+struct SlicedAcc { typedef float2 type; };
+template <>
+struct SlicedAcc<true> { typedef uint4 type; };
+
+// phase 2: shots sh0 .. sh0 + SH - 1 of every slab: index = plane bits, contribution = decode-table entry
+template <int SH, bool HAS_EXACT>
+__device__ __forceinline__ void sliced_phase2(const uint32_t* __restrict__ cbase, uint32_t rec, const uint32_t* __restrict__ plj, int sh0,
+                                              bool approx, typename SlicedAcc<HAS_EXACT>::type (&acc)[SH]) {
+  const uint4 h0 = *reinterpret_cast<const uint4*>(cbase + rec);
+  const int n_idx = (int)(h0.y & 0xFFu);
+  const uint32_t* __restrict__ tbl = cbase + h0.z;
+  constexpr uint32_t kField = SH == 32 ? 0xFFFFFFFFu : ((1u << SH) - 1u);
+  const uint32_t zb = plj[0] >> sh0;
+  uint32_t idx[SH];
+#pragma unroll
+  for (int s = 0; s < SH; ++s) idx[s] = 0u;
+  for (int k = 0; k < n_idx; ++k) {
+    const uint32_t pk = ((plj[(1 + k) * 32] >> sh0) & kField) << k;
+    const uint32_t m = 1u << k;
+#pragma unroll
+    for (int s = 0; s < SH; ++s) idx[s] |= (pk >> s) & m;
+  }
+#pragma unroll
+  for (int s = 0; s < SH; ++s) {
+    if ((zb >> s) & 1u) continue;
+    if (approx) {
+      const float2 e = *reinterpret_cast<const float2*>(tbl + 2u * idx[s]);
+      if constexpr (HAS_EXACT) {
+        acc[s].x = __float_as_uint(__fadd_rn(__uint_as_float(acc[s].x), e.x));
+        acc[s].y = __float_as_uint(__fadd_rn(__uint_as_float(acc[s].y), e.y));
       } else {
-        const float s2 = TSB_SQRT1_2;
-        const float f0 = __int2float_rn((int32_t)v.c0), f1 = __int2float_rn((int32_t)v.c1);
-        const float f2 = __int2float_rn((int32_t)v.c2), f3 = __int2float_rn((int32_t)v.c3);
-        const float t1 = __fmul_rn(f1, s2), t3 = __fmul_rn(f3, s2);
-        const float tre = __fmul_rn(__fadd_rn(__fadd_rn(f0, t1), t3), sc);
-        const float tim = __fmul_rn(__fsub_rn(__fadd_rn(t1, f2), t3), sc);
-        const float ure = __fsub_rn(__fmul_rn(tre, are), __fmul_rn(tim, aim));
-        const float uim = __fadd_rn(__fmul_rn(tre, aim), __fmul_rn(tim, are));
-        float2* sp = reinterpret_cast<float2*>(scol) + s * (HAS_EXACT ? 2 : 1) * T;
-        float2 acc = *sp;
-        acc.x = __fadd_rn(acc.x, __fmul_rn(ure, pw));
-        acc.y = __fadd_rn(acc.y, __fmul_rn(uim, pw));
-        *sp = acc;
+        acc[s].x = __fadd_rn(acc[s].x, e.x);
+        acc[s].y = __fadd_rn(acc[s].y, e.y);
+      }
+    } else {
+      if constexpr (HAS_EXACT) {
+        const uint4 e = *reinterpret_cast<const uint4*>(tbl + 4u * idx[s]);
+        acc[s].x += e.x; acc[s].y += e.y; acc[s].z += e.z; acc[s].w += e.w;
       }
     }
-    off += h1.w;
   }
 }
 
-// dynamic shared memory (32-bit words): [0,64) mbarriers | SlicedTables | xt [rows][T] | pw [16][T] |
-// S [32][T] x (uint4 if HAS_EXACT else float2) | prev [32][T] | data region / stage ring
-template <int T, bool HAS_EXACT>
-__global__ void __launch_bounds__(T, 1) sample_sliced_kernel(const SParams prm) {
+__host__ __device__ constexpr int sliced_max_groups(int split) { return split == 4 ? 7 : 3; }
+__host__ __device__ constexpr int sliced_max_threads(int split) { return sliced_max_groups(split) * split * 32; }
+
+__device__ __forceinline__ void group_sync(int grp, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(nthreads) : "memory");
+}
+
+// dynamic shared memory (32-bit words): [0,64) mbarriers | xt [ng][rows][32] | planes [ng][SPLIT][kPlaneRows][32] |
+// prev [ng][32 shots][32] | stage ring
+template <int SPLIT, bool HAS_EXACT>
+__global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_kernel(const SParams prm) {
+  constexpr int SH = 32 / SPLIT;
+  typedef typename SlicedAcc<HAS_EXACT>::type Acc;
   extern __shared__ __align__(128) uint32_t smem[];
   const uint32_t* __restrict__ blob = prm.blob;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int grp = wid / SPLIT, w = wid % SPLIT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  SlicedTables* tb = reinterpret_cast<SlicedTables*>(smem + 64);
-  uint32_t* xcol = smem + prm.smem_xt_off + tid;  // this thread's column: row r at xcol[r * T]
-  uint32_t* pwcol = smem + prm.smem_pw_off + tid;
-  // S: element (s, tid) at scol + s * stride * T words, stride = 4 (exact) or 2 (approx) words; vector accesses
-  uint32_t* scol = smem + prm.smem_s_off + tid * (HAS_EXACT ? 4 : 2);
-  float* pcol = reinterpret_cast<float*>(smem + prm.smem_prev_off) + tid;
+  uint32_t* xcol = smem + prm.smem_xt_off + grp * prm.rows * 32 + lane;
+  uint32_t* plg = smem + prm.smem_pl_off + grp * (SPLIT * kPlaneRows * 32) + lane;
+  float* pcol = reinterpret_cast<float*>(smem + prm.smem_prev_off) + grp * (32 * 32) + lane;
   uint32_t* sdata = smem + prm.smem_data_off;
 
   const int n_comp = (int)blob[H_N_COMP], n_chunks = (int)blob[H_N_CHUNKS];
@@ -351,20 +344,8 @@ __global__ void __launch_bounds__(T, 1) sample_sliced_kernel(const SParams prm) 
   const uint32_t* __restrict__ gdata = blob + blob[H_OFF_DATA];
   const int one_row = (int)blob[H_ONE_ROW];
 
-  for (int i = tid; i < 64; i += T) {
-    int a = i & 7, b = i >> 3;
-    int4 ua = unit_phase(a), ub = unit_phase(b), uc = unit_phase(a + b);
-    tb->pair[i] = make_int4(1 + ua.x + ub.x - uc.x, ua.y + ub.y - uc.y, ua.z + ub.z - uc.z, ua.w + ub.w - uc.w);
-  }
   if (tid == 0) {
-    uint32_t P = 1, Q = 0;
-    for (int e = 0; e < 64; ++e) { tb->pell[64 + e] = make_int2((int)P, (int)Q); uint32_t nP = P + 2u * Q, nQ = P + Q; P = nP; Q = nQ; }
-    P = 1; Q = 0;
-    for (int e = 0; e <= 64; ++e) { tb->pell[64 - e] = make_int2((int)P, (int)Q); uint32_t nP = 2u * Q - P, nQ = P - Q; P = nP; Q = nQ; }
-  }
-  const int n_bars = prm.resident ? 1 : prm.n_stages;
-  if (tid == 0) {
-    for (int i = 0; i < n_bars; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < prm.n_stages; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -379,103 +360,109 @@ __global__ void __launch_bounds__(T, 1) sample_sliced_kernel(const SParams prm) 
     mbar_expect_tx(&bars[stage], bytes);
     tma_bulk_g2s(sdata + (size_t)stage * prm.stage_words, gdata + row[K_OFF], bytes, &bars[stage]);
   };
-  if (tid == 0 && n_chunks > 0) {
-    if (prm.resident) {
-      mbar_expect_tx(&bars[0], blob[H_DATA_WORDS] * 4u);
-      for (int ch = 0; ch < n_chunks; ++ch) {
-        const uint32_t* row = chunk_tab + ch * kChunkWords;
-        tma_bulk_g2s(sdata + row[K_OFF], gdata + row[K_OFF], row[K_WORDS] * 4u, &bars[0]);
-      }
-    } else {
-      for (long long q = 0; q < prm.n_stages && q < total_q; ++q) issue(q);
-    }
-  }
-  if (prm.resident && n_chunks > 0) mbar_wait(&bars[0], 0);
+  if (tid == 0)
+    for (long long q = 0; q < prm.n_stages && q < total_q; ++q) issue(q);
 
   long long q = 0;
   for (int round = 0; round < prm.rounds; ++round) {
-    const int slab = (round * (int)gridDim.x + (int)blockIdx.x) * prm.per_cta + tid;
-    const bool active = tid < prm.per_cta && slab < prm.n_slabs;
-    // a warp with no slab at all only keeps the stage ring's barriers company
-    const int wslab = (round * (int)gridDim.x + (int)blockIdx.x) * prm.per_cta + (tid & ~31);
-    const bool warp_active = (tid & ~31) < prm.per_cta && wslab < prm.n_slabs;
-    const unsigned long long shot0 = (unsigned long long)prm.shot_offset + (unsigned long long)slab * 32ull;
+    const int ggrp = (round * prm.ng + grp) * (int)gridDim.x + (int)blockIdx.x;
+    const bool gactive = ggrp < prm.n_groups;  // uniform over the group's warps
+    const int slab = ggrp * 32 + lane;
+    const bool active = gactive && slab < prm.n_slabs;
+    const unsigned long long shot0 =
+        (unsigned long long)prm.shot_offset + (unsigned long long)slab * 32ull + (unsigned long long)(w * SH);
 
     int xt_row0 = 0, draw0 = 0;
     for (int ci = 0; ci < n_comp; ++ci) {
       const uint32_t* __restrict__ comp = comp_tab + ci * kCompWords;
       const int F = (int)comp[C_F], n_c = (int)comp[C_NC];
-      for (int i = 0; i < F; ++i) xcol[i * T] = active ? prm.xt[(size_t)(xt_row0 + i) * prm.slab_cap + slab] : 0u;
-      for (int i = F; i < prm.rows; ++i) xcol[i * T] = 0u;
-      xcol[one_row * T] = 0xFFFFFFFFu;
+      if (gactive) {
+        group_sync(grp, SPLIT * 32);  // the previous component's readers are done with the columns
+        for (int i = w; i < prm.rows; i += SPLIT) {
+          uint32_t v = 0u;
+          if (i < F) v = active ? prm.xt[(size_t)(xt_row0 + i) * prm.slab_cap + slab] : 0u;
+          else if (i == one_row) v = 0xFFFFFFFFu;
+          xcol[i * 32] = v;
+        }
+      }
 
       for (int k = 0; k <= n_c; ++k) {
         const uint32_t* __restrict__ lvl = level_tab + (comp[C_FIRST_LEVEL] + k) * kLevelWords;
         const bool approx = (lvl[L_FLAGS] & 1u) != 0u;
-        if (k > 0) xcol[(F + k - 1) * T] = 0xFFFFFFFFu;  // trying bit 1 for every shot
-        for (int s = 0; s < 32; ++s) {
-          if constexpr (HAS_EXACT) reinterpret_cast<uint4*>(scol)[s * T] = make_uint4(0u, 0u, 0u, 0u);
-          else reinterpret_cast<uint2*>(scol)[s * T] = make_uint2(0u, 0u);
+        if (gactive) {
+          if (k > 0 && w == 0) xcol[(F + k - 1) * 32] = 0xFFFFFFFFu;  // trying bit 1 for every shot
+          group_sync(grp, SPLIT * 32);
+        }
+        Acc acc[SH];
+#pragma unroll
+        for (int s = 0; s < SH; ++s) {
+          if constexpr (HAS_EXACT) acc[s] = make_uint4(0u, 0u, 0u, 0u);
+          else acc[s] = make_float2(0.0f, 0.0f);
         }
         const int first_chunk = (int)lvl[L_FIRST_CHUNK], nck = (int)lvl[L_N_CHUNKS];
         for (int c = 0; c < nck; ++c) {
           const uint32_t* row = chunk_tab + (first_chunk + c) * kChunkWords;
-          uint32_t off;
-          if (prm.resident) {
-            off = row[K_OFF];
-          } else {
-            const int stage = (int)(q % prm.n_stages);
-            mbar_wait(&bars[stage], (uint32_t)((q / prm.n_stages) & 1));
-            off = (uint32_t)stage * (uint32_t)prm.stage_words;
-          }
-          if (warp_active) sliced_graphs<T, HAS_EXACT>(sdata, off, (int)row[K_GRAPHS], approx, xcol, pwcol, scol, tb);
-          if (!prm.resident) {
-            __syncthreads();
-            if (tid == 0 && q + prm.n_stages < total_q) issue(q + prm.n_stages);
-            ++q;
-          }
-        }
-        // finish the level for the 32 shots: |amp|, draw, chain rule
-        const int p_lo = (int)lvl[L_P_LO];
-        const bool empty = lvl[L_G] == 0u;
-        uint32_t k0 = 0, k1 = 0;
-        if (k > 0) {
-          k0 = prm.subkeys[2 * (draw0 + k - 1)];
-          k1 = prm.subkeys[2 * (draw0 + k - 1) + 1];
-        }
-        uint32_t bits = 0;
-#pragma unroll 2
-        for (int s = 0; s < (warp_active ? 32 : 0); ++s) {
-          float re, im;
-          if (approx) {
-            const float2 a2 = reinterpret_cast<const float2*>(scol)[s * (HAS_EXACT ? 2 : 1) * T];
-            re = a2.x; im = a2.y;
-          } else {
-            if constexpr (HAS_EXACT) {
-              const uint4 a4 = reinterpret_cast<const uint4*>(scol)[s * T];
-              ZW cz = ZW{a4.x, a4.y, a4.z, a4.w};
-              int p = p_lo;
-              zw_fixpoint(cz, p);
-              zw_to_complex(cz, p, re, im);
-            } else {
-              re = 0.0f; im = 0.0f;
+          const int stage = (int)(q % prm.n_stages);
+          mbar_wait(&bars[stage], (uint32_t)((q / prm.n_stages) & 1));
+          const uint32_t* __restrict__ cbase = sdata + (size_t)stage * prm.stage_words;
+          const int n_g = (int)row[K_GRAPHS];
+          if (gactive) {
+            for (int w0 = 0; w0 < n_g; w0 += SPLIT) {
+              if (w0 + w < n_g) sliced_phase1(cbase, cbase[w0 + w], xcol, plg + w * (kPlaneRows * 32));
+              group_sync(grp, SPLIT * 32);
+              const int nj = min(SPLIT, n_g - w0);
+              for (int j = 0; j < nj; ++j)
+                sliced_phase2<SH, HAS_EXACT>(cbase, cbase[w0 + j], plg + j * (kPlaneRows * 32), w * SH, approx, acc);
+              group_sync(grp, SPLIT * 32);
             }
           }
-          if (empty) { re = 0.0f; im = 0.0f; }
-          const float p1 = complex_abs(re, im);
-          if (k == 0) {
-            pcol[s * T] = p1;
-          } else {
-            const float pv = pcol[s * T];
-            const float u = uniform_f32(k0, k1, shot0 + (unsigned long long)s);
-            const bool bit = u < __fdiv_rn(p1, pv);
-            pcol[s * T] = bit ? p1 : __fsub_rn(pv, p1);
-            bits |= (bit ? 1u : 0u) << s;
-          }
+          __syncthreads();  // every group is done with this stage
+          if (tid == 0 && q + prm.n_stages < total_q) issue(q + prm.n_stages);
+          ++q;
         }
-        if (k > 0) {
-          xcol[(F + k - 1) * T] = bits;
-          if (active) prm.ot[(size_t)(draw0 + k - 1) * prm.slab_cap + slab] = bits;
+        // finish the level for this warp's shots: |amp|, draw, chain rule
+        if (gactive) {
+          const int p_lo = (int)lvl[L_P_LO];
+          const bool empty = lvl[L_G] == 0u;
+          uint32_t k0 = 0, k1 = 0;
+          if (k > 0) {
+            k0 = prm.subkeys[2 * (draw0 + k - 1)];
+            k1 = prm.subkeys[2 * (draw0 + k - 1) + 1];
+          }
+          uint32_t bits = 0;
+#pragma unroll
+          for (int s = 0; s < SH; ++s) {
+            float re = 0.0f, im = 0.0f;
+            if (approx) {
+              if constexpr (HAS_EXACT) { re = __uint_as_float(acc[s].x); im = __uint_as_float(acc[s].y); }
+              else { re = acc[s].x; im = acc[s].y; }
+            } else {
+              if constexpr (HAS_EXACT) {
+                ZW cz = ZW{acc[s].x, acc[s].y, acc[s].z, acc[s].w};
+                int p = p_lo;
+                zw_fixpoint(cz, p);
+                zw_to_complex(cz, p, re, im);
+              }
+            }
+            if (empty) { re = 0.0f; im = 0.0f; }
+            const float p1 = complex_abs(re, im);
+            float* pp = pcol + (w * SH + s) * 32;
+            if (k == 0) {
+              *pp = p1;
+            } else {
+              const float pv = *pp;
+              const float u = uniform_f32(k0, k1, shot0 + (unsigned long long)s);
+              const bool bit = u < __fdiv_rn(p1, pv);
+              *pp = bit ? p1 : __fsub_rn(pv, p1);
+              bits |= (bit ? 1u : 0u) << s;
+            }
+          }
+          if (k > 0) {
+            constexpr uint32_t kField = SH == 32 ? 0xFFFFFFFFu : ((1u << SH) - 1u);
+            atomicAnd(&xcol[(F + k - 1) * 32], (bits << (w * SH)) | ~(kField << (w * SH)));
+            group_sync(grp, SPLIT * 32);
+            if (w == 0 && active) prm.ot[(size_t)(draw0 + k - 1) * prm.slab_cap + slab] = xcol[(F + k - 1) * 32];
+          }
         }
       }
       xt_row0 += F;

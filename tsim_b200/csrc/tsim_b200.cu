@@ -515,7 +515,7 @@ struct tsb_program {
   uint32_t* d_heavy = nullptr;  // for tsb_sample_device
   long long heavy_cap = 0;
   // MODE_SLICED
-  int is_sliced = 0, s_has_exact = 0, s_rows = 0, s_xt_off = 0, s_pw_off = 0, s_s_off = 0, s_prev_off = 0, s_threads = 0;
+  int is_sliced = 0, s_has_exact = 0, s_rows = 0, s_smem_limit = 0, s_stage_words = 0;
   int total_F = 0, max_nc = 0;
   tsb_program* aux = nullptr;   // companion per-row program (norm check); not owned
   cudaStream_t side = nullptr;  // the norm check of shot 0 runs here, overlapped with the rest of the batch
@@ -596,10 +596,25 @@ static EvalFn eval_fn_for(int W) {
   }
 }
 typedef void (*SlicedFn)(const SParams);
-static SlicedFn sliced_fn(int T, int has_exact) {
-  if (has_exact) return T == 256 ? sample_sliced_kernel<256, true> : T == 128 ? sample_sliced_kernel<128, true> : sample_sliced_kernel<64, true>;
-  return T == 256 ? sample_sliced_kernel<256, false> : T == 128 ? sample_sliced_kernel<128, false> : sample_sliced_kernel<64, false>;
+// exact-branch accumulators are four words per shot: only the 8-way split keeps them in registers
+static SlicedFn sliced_fn(int split, int has_exact) {
+  if (has_exact) return sample_sliced_kernel<8, true>;
+  return split == 4 ? sample_sliced_kernel<4, false> : sample_sliced_kernel<8, false>;
 }
+
+// Shared-memory plan of one sliced launch: `ng` groups of `split` warps (sliced_kernels.cuh).
+struct SlicedPlan {
+  int split = 0, ng = 0, rounds = 0, grid = 0, n_stages = 0;
+  int xt_off = 0, pl_off = 0, prev_off = 0, data_off = 0, smem_bytes = 0;
+};
+static int sliced_group_words(int rows, int split) { return rows * 32 + split * kPlaneRows * 32 + 32 * 32; }
+// largest number of groups (<= cap) that leaves room for `want_stages` stages; 0 if not even one group fits
+static int sliced_fit_groups(int rows, int split, int cap, int stage_words, int want_stages, int smem_limit) {
+  for (int ng = cap; ng >= 1; --ng)
+    if (((long long)kBarWords + (long long)ng * sliced_group_words(rows, split) + (long long)want_stages * stage_words) * 4 <= smem_limit) return ng;
+  return 0;
+}
+static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl);
 static SampleFn sample_fn(int mode, int W) { return mode == kModeFast ? sample_fn_for<kModeFast>(W) : sample_fn_for<kModeFaithful>(W); }
 static EvalFn eval_fn(int mode, int W) { return mode == kModeFast ? eval_fn_for<kModeFast>(W) : eval_fn_for<kModeFaithful>(W); }
 
@@ -660,24 +675,22 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
     CUB(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
     CUB(cudaMalloc(&p->d_row0, 8 * (size_t)(blob[H_WF64] + blob[H_WOUT64])));
-    // threads per CTA: the largest of 256/128/64 whose private columns leave room for g (resident, or >= 2 stages)
     int lim_smem = (int)prop.sharedMemPerBlockOptin;
     if (const char* lim = getenv("TSIM_B200_SMEM_LIMIT")) {
       int v = atoi(lim);
       if (v > 0) lim_smem = std::min(lim_smem, v);
     }
-    const long long dw = blob[H_DATA_WORDS], mc = ((long long)blob[H_MAX_CHUNK] + 31) & ~31ll;
-    for (int T : {256, 128, 64}) {
-      const int xt_off = (kBarWords + (int)(sizeof(SlicedTables) / 4) + 31) & ~31;
-      const int pw_off = xt_off + p->s_rows * T;
-      const int s_off = pw_off + 2 * kMaxGeneralPairs * T;
-      const int prev_off = s_off + 32 * T * (p->s_has_exact ? 4 : 2);
-      const int fixed = (prev_off + 32 * T + 31) & ~31;
-      const long long room = (long long)lim_smem / 4 - fixed;
-      p->s_threads = T; p->s_xt_off = xt_off; p->s_pw_off = pw_off; p->s_s_off = s_off; p->s_prev_off = prev_off;
-      fixed_words = fixed;
-      if (room >= dw || (mc > 0 && room >= 2 * mc)) break;
+    p->s_smem_limit = lim_smem;
+    p->s_stage_words = std::max(32, ((int)blob[H_MAX_CHUNK] + 31) & ~31);
+    const int split_min = p->s_has_exact ? 8 : 4;
+    if (!sliced_fit_groups(p->s_rows, split_min, 1, p->s_stage_words, 1, lim_smem) ||
+        !sliced_fit_groups(p->s_rows, 8, 1, p->s_stage_words, 1, lim_smem)) {
+      fail(TSB_ERR_UNSUPPORTED, "a single chunk of the program does not fit in shared memory next to one slab group");
+      return bail(TSB_ERR_UNSUPPORTED);
     }
+    for (int split : {4, 8})
+      CUB(cudaFuncSetAttribute((const void*)sliced_fn(split, p->s_has_exact), cudaFuncAttributeMaxDynamicSharedMemorySize, lim_smem));
+    fixed_words = kBarWords;
   }
   fixed_words = (fixed_words + 31) & ~31;  // 128-byte align the data region
   int max_smem = (int)prop.sharedMemPerBlockOptin;
@@ -688,11 +701,11 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
   const long long budget_words = (long long)max_smem / 4 - fixed_words;
   const long long data_words = blob[H_DATA_WORDS];
   const int max_chunk = (int)blob[H_MAX_CHUNK];
-  if (budget_words < std::max(max_chunk, 4)) {
+  if (mode != kModeSliced && budget_words < std::max(max_chunk, 4)) {
     fail(TSB_ERR_UNSUPPORTED, "a single chunk of the program does not fit in shared memory");
     return bail(TSB_ERR_UNSUPPORTED);
   }
-  int resident = data_words <= budget_words ? 1 : 0;
+  int resident = (mode != kModeSliced && data_words <= budget_words) ? 1 : 0;
   long long used;
   if (resident) {
     p->n_stages = 1;
@@ -705,18 +718,21 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
   }
   p->smem_data_off = fixed_words;
   const int smem_bytes = (int)((fixed_words + used) * 4);
-  if (mode == kModeSliced) {
-    CUB(cudaFuncSetAttribute((const void*)sliced_fn(p->s_threads, p->s_has_exact), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  } else {
+  if (mode != kModeSliced)
     CUB(cudaFuncSetAttribute((const void*)sample_fn(mode, W), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  }
 
   tsb_info& in = p->info;
   in.mode = mode; in.words = W; in.num_f = (int)blob[H_NUM_F]; in.num_outputs = (int)blob[H_N_OUT];
   in.n_direct = (int)blob[H_N_DIRECT]; in.n_components = n_comp; in.n_draws = n_draws;
   in.words_f64 = (int)blob[H_WF64]; in.words_out64 = (int)blob[H_WOUT64];
   in.resident = resident; in.n_chunks = (int)blob[H_N_CHUNKS]; in.smem_bytes = smem_bytes;
-  in.threads = mode == kModeSliced ? p->s_threads : kThreads; in.grid = p->sm_count; in.data_bytes = data_words * 4;
+  in.threads = kThreads; in.grid = p->sm_count; in.data_bytes = data_words * 4;
+  if (mode == kModeSliced) {  // report the plan of a chip-filling batch
+    SlicedPlan pl;
+    sliced_plan(p, p->sm_count * 7 * 32, pl);
+    in.threads = pl.ng * pl.split * 32; in.smem_bytes = pl.smem_bytes; in.resident = 0;
+    p->n_stages = pl.n_stages; p->stage_words = p->s_stage_words;
+  }
 #undef CUB
   *out = p;
   return TSB_OK;
@@ -902,6 +918,36 @@ static NormFn norm_fn_for(int W) {
   }
 }
 
+// Groups per CTA, split and ring depth for a batch of n_slabs slabs.  Few groups per SM -> 8 warps per group (so that a
+// thin slice still keeps 16+ warps on an SM), otherwise 4.
+static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl) {
+  const int n_groups = std::max(1, (n_slabs + 31) / 32);
+  pl.grid = std::max(1, std::min(p->sm_count, n_groups));
+  const int gpc = (n_groups + pl.grid - 1) / pl.grid;  // groups per CTA
+  int split = (p->s_has_exact || gpc < 4) ? 8 : 4;
+  if (const char* e = getenv("TSIM_B200_SLICED_SPLIT")) {  // tuning knob
+    const int v = atoi(e);
+    if ((v == 4 && !p->s_has_exact) || v == 8) split = v;
+  }
+  const int n_chunks = (int)p->host_blob[H_N_CHUNKS];
+  const int want = std::min(2, std::max(1, n_chunks));
+  int cap = std::min(sliced_max_groups(split), gpc);
+  int ng = sliced_fit_groups(p->s_rows, split, cap, p->s_stage_words, want, p->s_smem_limit);
+  if (!ng) ng = sliced_fit_groups(p->s_rows, split, cap, p->s_stage_words, 1, p->s_smem_limit);
+  if (!ng) return false;
+  pl.split = split;
+  pl.rounds = (gpc + ng - 1) / ng;
+  pl.ng = (gpc + pl.rounds - 1) / pl.rounds;
+  pl.xt_off = kBarWords;
+  pl.pl_off = pl.xt_off + pl.ng * p->s_rows * 32;
+  pl.prev_off = pl.pl_off + pl.ng * split * kPlaneRows * 32;
+  pl.data_off = pl.prev_off + pl.ng * 32 * 32;
+  const long long room = (long long)p->s_smem_limit / 4 - pl.data_off;
+  pl.n_stages = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kMaxStages, std::max(1, n_chunks)), room / p->s_stage_words));
+  pl.smem_bytes = (pl.data_off + pl.n_stages * p->s_stage_words) * 4;
+  return true;
+}
+
 // K0t -> K1s -> K2a -> K1c on one stream
 static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long long shot_offset, const uint32_t* d_subkeys,
                          uint64_t* d_out, float* d_norm_dev, cudaStream_t st, uint32_t* d_xt, uint32_t* d_ot, long long slab_cap,
@@ -916,17 +962,16 @@ static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long 
     CU(cudaGetLastError());
   }
   if (in.n_draws > 0) {
+    SlicedPlan pl;
+    if (!sliced_plan(p, n_slabs, pl)) return fail(TSB_ERR_UNSUPPORTED, "internal: no sliced launch plan fits in shared memory");
     SParams k;
     k.blob = p->d_blob; k.xt = d_xt; k.ot = d_ot; k.subkeys = d_subkeys; k.B = B; k.shot_offset = shot_offset;
     k.n_slabs = n_slabs; k.slab_cap = (int)slab_cap;
-    const int grid = std::max(1, std::min(p->sm_count, (n_slabs + 31) / 32));
-    const int T = p->s_threads;
-    k.rounds = (n_slabs + grid * T - 1) / (grid * T);
-    k.per_cta = (n_slabs + grid * k.rounds - 1) / (grid * k.rounds);
-    k.resident = in.resident; k.n_stages = p->n_stages; k.stage_words = p->stage_words;
-    k.smem_xt_off = p->s_xt_off; k.smem_pw_off = p->s_pw_off; k.smem_s_off = p->s_s_off; k.smem_prev_off = p->s_prev_off;
-    k.smem_data_off = p->smem_data_off; k.rows = p->s_rows;
-    sliced_fn(T, p->s_has_exact)<<<grid, T, in.smem_bytes, st>>>(k);
+    k.n_groups = (n_slabs + 31) / 32; k.ng = pl.ng; k.rounds = pl.rounds;
+    k.n_stages = pl.n_stages; k.stage_words = p->s_stage_words;
+    k.smem_xt_off = pl.xt_off; k.smem_pl_off = pl.pl_off; k.smem_prev_off = pl.prev_off; k.smem_data_off = pl.data_off;
+    k.rows = p->s_rows;
+    sliced_fn(pl.split, p->s_has_exact)<<<pl.grid, pl.ng * pl.split * 32, pl.smem_bytes, st>>>(k);
     CU(cudaGetLastError());
   }
   assemble_out_kernel<<<tblocks, 256, 0, st>>>(p->d_blob, d_f, d_ot, B, n_slabs, (int)slab_cap, d_out);

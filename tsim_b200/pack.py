@@ -33,7 +33,7 @@ import numpy as np
 from .program import CompiledProgram, CompiledScalarGraphs
 
 MAGIC = 0x32425354  # "TSB2"
-VERSION = 4
+VERSION = 5
 MODE_FAITHFUL = 0
 MODE_FAST = 1
 MODE_SLICED = 2
@@ -236,8 +236,6 @@ def pack_program(
                 f"fast mode is not provably exact for this program (log2 bound {bound_info['log2_bound']:.1f} >= 30.5)"
             )
         mode_id = MODE_SLICED if mode in ("sliced", MODE_SLICED) else MODE_FAST
-        if mode_id == MODE_SLICED:
-            max_chunk_words = min(max_chunk_words, 4096)  # sliced CTAs keep per-shot state in shared memory: small stages
     else:
         raise ValueError(f"unknown mode {mode!r}")
 
@@ -306,9 +304,10 @@ def pack_program(
                 graph_lists = [recs[g] for g in range(lv.num_graphs)]
                 p_lo = 0
             elif mode_id == MODE_SLICED:
-                from .pack_sliced import sliced_level_records
+                from .pack_sliced import sliced_level_chunks, sliced_level_records
 
-                graph_lists, (A, H, C, D), p_lo = sliced_level_records(lv, max_p, max_p + 1)
+                graphs, (A, H, C, D), p_lo = sliced_level_records(lv, max_p, max_p + 1)
+                graph_lists = []
             else:
                 from .pack_fast import fast_level_records  # local import: keeps this module lean
 
@@ -335,6 +334,12 @@ def pack_program(
                 cur_words += len(rec)
                 cur_graphs += 1
             flush()
+            if mode_id == MODE_SLICED:
+                # chunk = directory | records | decode tables (pack_sliced.py); offsets inside are chunk-relative
+                for arr, n_graphs in sliced_level_chunks(graphs):
+                    chunk_rows.append([data_off, len(arr), n_graphs, 0])
+                    data_parts.append(arr)
+                    data_off += len(arr)
             flags = 1 if lv.prefactor.has_approximate_floatfactors else 0
             level_rows.append(
                 [lv.num_graphs, lv.n_params, A, H, C, D, flags, first_chunk, len(chunk_rows) - first_chunk,

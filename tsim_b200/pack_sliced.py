@@ -7,14 +7,22 @@ monoid element ``w^a (1+sqrt2)^b`` (see ``pack_fast.py``) are accumulated as bit
 ``a``, a bit-sliced counter for ``b``, one plane for "some factor vanished"); only the final decode of
 a graph's value and the sum over graphs run per shot.
 
+The planes of a graph form an index ``a | cnt << 3 | pair parities << (3 + nb)`` into a per-graph *decode table*
+built here at pack time: entry = the graph's contribution to the level sum for that index -- ``(re, im)`` float32 of
+``to_complex(value) * approximate_floatfactor * 2^power2`` in the approximate branch (same op order as the per-row
+kernels, so the bits are identical), or the four int32 coefficients of ``value << shift`` in the exact branch.  The
+device therefore never decodes a monoid element; per shot and graph it gathers the index bits and adds one entry.
+
+Chunk (the unit of the TMA stage ring) = directory (record offset of every graph, padded to 4 words) | graph
+records | decode tables.  All offsets are in words relative to the chunk start.
+
 Graph record (uint32 words):
 
     [0]  n_terms | n_general_pairs << 16
-    [1]  (b_base + 64) | n_b_planes << 8
-    [2]  p_T   [3] power2   [4] shift (= p_T + power2 - p_lo)   [5] approx.re   [6] approx.im   [7] record words
-    [8..11] K1 = w^a_static (1+w)^(n&3) floatfactor     [12..15] K2 = K1 sqrt2
-    [16..17] ctl bytes of up to 8 general pairs (alpha | beta << 3)
-    [18..19] reserved
+    [1]  n_index_bits | n_b_planes << 8
+    [2]  offset of the decode table (filled in when the chunk is assembled)
+    [3]  record words
+    [4..7] reserved
     then the term stream, one control word per term followed by its index words:
         cw bits 0-1 type (0 LIN, 1 PI, 2 PAIR_GENERAL, 3 PAIR_MONOID), bits 2-7 n1, bits 8-13 n2 (index words of
         the first / second parity; an index word holds four row indices, padded with the all-zero row), bit 31 generic.
@@ -40,8 +48,10 @@ import numpy as np
 from .pack_fast import MONOID, ONE_PLUS_W_POW, SQRT2, _zw_mul
 from .program import CompiledScalarGraphs
 
-SLICED_HEADER_WORDS = 20
-MAX_GENERAL_PAIRS = 8
+SLICED_HEADER_WORDS = 8
+MAX_GENERAL_PAIRS = 3
+MAX_INDEX_BITS = 11
+MAX_CHUNK_WORDS = 12288  # 48 KB stages
 B_OFFSET = 64
 T_LIN, T_PI, T_PAIR_GENERAL, T_PAIR_MONOID = 0, 1, 2, 3
 
@@ -134,7 +144,7 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
             r.append(one_row)
         return r
 
-    recs, shifts_base = [], []
+    recs, shifts_base, decode = [], [], []
     for g in range(G):
         a_s = int(pre.phase_indices[g]) & 7
         b_base = 0
@@ -241,6 +251,9 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
         if units > 31:
             raise _Unsupported("b counter needs more than 5 planes")
         nb = max(1, units.bit_length())
+        n_idx = 3 + nb + 2 * len(general_ctl)
+        if n_idx > MAX_INDEX_BITS:
+            raise _Unsupported("decode table of a graph would exceed 2^%d entries" % MAX_INDEX_BITS)
         p_t = n_tot >> 2
         r = n_tot & 3
         a_s = (a_s + 2 * p_t) & 7
@@ -260,28 +273,157 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
         body = [w for t in terms for w in t] + [0] * 8  # slack: the kernel prefetches the next term's eight words
         words = np.zeros(SLICED_HEADER_WORDS + len(body), dtype=np.uint32)
         words[0] = len(terms) | (len(general_ctl) << 16)
-        words[1] = (b_base + B_OFFSET) | (nb << 8)
-        words[2] = np.int32(p_t).view(np.uint32)
-        words[3] = np.int32(power2).view(np.uint32)
-        aff = np.complex64(pre.approximate_floatfactors[g])
-        words[5] = np.float32(aff.real).view(np.uint32)
-        words[6] = np.float32(aff.imag).view(np.uint32)
-        words[8:12] = np.array(k1, dtype=np.int64).astype(np.int32).view(np.uint32)
-        words[12:16] = np.array(k2, dtype=np.int64).astype(np.int32).view(np.uint32)
-        for s, ctl in enumerate(general_ctl):
-            words[16 + s // 4] |= np.uint32(ctl << (8 * (s % 4)))
+        words[1] = n_idx | (nb << 8)
         words[SLICED_HEADER_WORDS:] = np.array(body, dtype=np.uint64).astype(np.uint32)
         pad = (-len(words)) % 4
         if pad:
             words = np.concatenate([words, np.zeros(pad, np.uint32)])
-        words[7] = len(words)
+        words[3] = len(words)
         recs.append(words)
         shifts_base.append(p_t + power2)
+        decode.append(
+            dict(nb=nb, n_idx=n_idx, b64=b_base + B_OFFSET, k1=k1, k2=k2, ctl=list(general_ctl), p_t=p_t, power2=power2,
+                 aff=np.complex64(pre.approximate_floatfactors[g]))
+        )
 
     p_lo = min(shifts_base) if shifts_base else 0
-    for words, sb in zip(recs, shifts_base):
+    tables = []
+    for d, sb in zip(decode, shifts_base):
         sh = sb - p_lo
         if not approx and sh > 30:
             raise _Unsupported("fixed-point shift exceeds 30 bits")
-        words[4] = min(sh, 31)
-    return recs, (A, H, C, D), p_lo
+        tables.append(decode_table(d, approx, min(sh, 31)))
+    return list(zip(recs, tables)), (A, H, C, D), p_lo
+
+
+# ------------------------------------------------------------------------------------------------
+# decode tables
+# ------------------------------------------------------------------------------------------------
+
+
+def _pell_table() -> np.ndarray:
+    """uint32 [128, 2]: (1+sqrt2)^(e-64) = P + Q sqrt2 with the device's wrapping recurrences."""
+    t = np.zeros((128, 2), dtype=np.uint64)
+    P, Q = 1, 0
+    for e in range(64):
+        t[64 + e] = (P, Q)
+        P, Q = (P + 2 * Q) & 0xFFFFFFFF, (P + Q) & 0xFFFFFFFF
+    P, Q = 1, 0
+    for e in range(65):
+        t[64 - e] = (P, Q)
+        P, Q = (2 * Q - P) & 0xFFFFFFFF, (P - Q) & 0xFFFFFFFF
+    return t.astype(np.uint32)
+
+
+PELL = _pell_table()
+PAIR_TABLE = np.array(
+    [[v & 0xFFFFFFFF for v in pair_factor(i & 7, i >> 3)] for i in range(64)], dtype=np.uint64
+).astype(np.uint32)  # index alpha | beta << 3
+_SQRT1_2 = np.array([0x3F3504F3], dtype=np.uint32).view(np.float32)[0]
+
+
+def _mul_u32(x, y):
+    """Wrapping Z[w] product of uint32 [..., 4] arrays (exact_scalar.py:31-39)."""
+    a1, b1, c1, d1 = (x[..., i] for i in range(4))
+    a2, b2, c2, d2 = (y[..., i] for i in range(4))
+    with np.errstate(over="ignore"):
+        return np.stack(
+            [
+                a1 * a2 + b1 * d2 - c1 * c2 + d1 * b2,
+                a1 * b2 + b1 * a2 + c1 * d2 + d1 * c2,
+                a1 * c2 + b1 * b2 + c1 * a2 - d1 * d2,
+                a1 * d2 - b1 * c2 - c1 * b2 + d1 * a2,
+            ],
+            axis=-1,
+        ).astype(np.uint32)
+
+
+def _pow2_f32(p: int) -> np.float32:
+    from .pack_fast import _pow2_bits
+
+    return np.array([_pow2_bits(int(p))], dtype=np.uint32).view(np.float32)[0]
+
+
+def decode_values(d: dict) -> np.ndarray:
+    """uint32 [2^n_idx, 4]: the graph's value (wrapping int32 coefficients, power p_T) for every plane index."""
+    n_idx, nb = d["n_idx"], d["nb"]
+    idx = np.arange(1 << n_idx, dtype=np.int64)
+    a = idx & 7
+    cnt = (idx >> 3) & ((1 << nb) - 1)
+    pq = PELL[(d["b64"] + cnt) & 127]
+    k1 = np.array([v & 0xFFFFFFFF for v in d["k1"]], dtype=np.uint64).astype(np.uint32)
+    k2 = np.array([v & 0xFFFFFFFF for v in d["k2"]], dtype=np.uint64).astype(np.uint32)
+    with np.errstate(over="ignore"):
+        v = k1[None, :] * pq[:, 0:1] + k2[None, :] * pq[:, 1:2]
+        neg = lambda t: (np.uint32(0) - t).astype(np.uint32)
+        # multiply by w^a: w (c0,c1,c2,c3) = (c3, c0, c1, -c2); i (..) = (-c2, c3, c0, -c1)
+        r1 = np.stack([v[:, 3], v[:, 0], v[:, 1], neg(v[:, 2])], axis=1)
+        v = np.where((a & 1)[:, None] != 0, r1, v)
+        r2 = np.stack([neg(v[:, 2]), v[:, 3], v[:, 0], neg(v[:, 1])], axis=1)
+        v = np.where((a & 2)[:, None] != 0, r2, v)
+        v = np.where((a & 4)[:, None] != 0, neg(v), v).astype(np.uint32)
+    for slot, ctl in enumerate(d["ctl"]):
+        pa = (idx >> (3 + nb + 2 * slot)) & 1
+        pb = (idx >> (3 + nb + 2 * slot + 1)) & 1
+        v = _mul_u32(v, PAIR_TABLE[(ctl ^ (pa << 2) ^ (pb << 5)) & 63])
+    return v
+
+
+def decode_table(d: dict, approx: bool, shift: int) -> np.ndarray:
+    """uint32 [2^n_idx * (2 | 4)]: per-index contribution of the graph to the level sum (see the module docstring)."""
+    v = decode_values(d)
+    if not approx:
+        with np.errstate(over="ignore"):
+            return (v * np.uint32(1 << (shift & 31))).astype(np.uint32).reshape(-1)
+    f = v.view(np.int32).astype(np.float32)
+    s2 = _SQRT1_2
+    sc, pw = _pow2_f32(d["p_t"]), _pow2_f32(d["power2"])
+    are, aim = np.float32(d["aff"].real), np.float32(d["aff"].imag)
+    with np.errstate(all="ignore"):
+        t1, t3 = f[:, 1] * s2, f[:, 3] * s2
+        tre = ((f[:, 0] + t1) + t3) * sc
+        tim = ((t1 + f[:, 2]) - t3) * sc
+        ure = tre * are - tim * aim
+        uim = tre * aim + tim * are
+        out = np.stack([ure * pw, uim * pw], axis=1).astype(np.float32)
+    return np.ascontiguousarray(out).view(np.uint32).reshape(-1)
+
+
+def sliced_level_chunks(graphs, max_chunk_words: int = MAX_CHUNK_WORDS):
+    """Group (record, table) pairs of one level into chunks -> list of (uint32 chunk, n_graphs).
+
+    Graph counts per chunk are kept at multiples of 8 where the stage size allows (the kernel hands the graphs of a
+    chunk to its warps in waves of 4 or 8)."""
+
+    def size(gs):
+        return ((len(gs) + 3) & ~3) + sum(len(r) + ((len(t) + 3) & ~3) for r, t in gs)
+
+    chunks, i = [], 0
+    while i < len(graphs):
+        take = 0
+        while i + take < len(graphs) and size(graphs[i : i + take + 1]) <= max_chunk_words:
+            take += 1
+        if take == 0:
+            raise _Unsupported("a graph does not fit a stage")
+        if i + take < len(graphs):  # not the end of the level: keep whole waves together
+            for unit in (8, 4, 2):
+                if take >= unit:
+                    take -= take % unit
+                    break
+        gs = graphs[i : i + take]
+        n = len(gs)
+        total = size(gs)
+        chunk = np.zeros(total, dtype=np.uint32)
+        pos = (n + 3) & ~3
+        for j, (r, _t) in enumerate(gs):
+            chunk[j] = pos
+            chunk[pos : pos + len(r)] = r
+            pos += len(r)
+        for j, (_r, t) in enumerate(gs):
+            chunk[int(chunk[j]) + 2] = pos
+            chunk[pos : pos + len(t)] = t
+            pos += (len(t) + 3) & ~3
+        assert pos == total
+        chunks.append((chunk, n))
+        i += take
+    return chunks

@@ -66,3 +66,32 @@ def test_sliced_records_reproduce_oracle(P, seed, approx):
                 assert np.array_equal(g[1], ssum.coeffs[s]) and g[2] == int(ssum.power[s]), s
             else:
                 assert not np.any(g[1])
+
+
+@pytest.mark.parametrize("approx", [False, True])
+def test_graphs_with_many_general_pairs_are_split_into_gated_variants(approx):
+    rng = np.random.default_rng(7)
+    P = 12
+    lv = random_level(rng, G=3, P=P, A=3, H=2, C=2, D=6, approx=approx, density=0.3)
+    lv.phase_pairs.alpha[:] = 2 * rng.integers(0, 4, size=lv.phase_pairs.alpha.shape) + 1  # odd-odd: never monoid-type
+    lv.phase_pairs.beta[:] = 2 * rng.integers(0, 4, size=lv.phase_pairs.beta.shape) + 1
+    lv.phase_pairs.counts[:] = [6, 5, 4]
+    prog = _one_level_program(lv, P)
+    pp = PK.pack_program(prog, mode="sliced")
+    ch = pp.blob[int(pp.blob[PK.H_OFF_CHUNK]) :][: int(pp.blob[PK.H_N_CHUNKS]) * 4].reshape(-1, 4)
+    assert int(ch[:, 2].sum()) > 3 + 2  # level 0 was split (the constant level 1 adds its own graphs)
+    xs = rng.integers(0, 2, size=(64, P)).astype(np.uint8)
+    got = sliced_model.evaluate_level(pp, 0, 0, xs)
+    if approx:
+        re, im = E.evaluate_parts(lv, xs)
+        for s, g in enumerate(got):
+            assert np.float32(g[1]).tobytes() == re[s].tobytes() and np.float32(g[2]).tobytes() == im[s].tobytes()
+    else:
+        total = E.term_product(lv, xs)
+        with np.errstate(over="ignore"):
+            ssum = ExactScalar(total.coeffs, (total.power + lv.prefactor.power2[None, :]).astype(np.int32)).sum()
+        for s, g in enumerate(got):
+            if np.any(ssum.coeffs[s] != 0):
+                assert np.array_equal(g[1], ssum.coeffs[s]) and g[2] == int(ssum.power[s]), s
+            else:
+                assert not np.any(g[1])

@@ -2,7 +2,7 @@
 # One GPU-box pass for the sliced kernel: parity tests, then short benches.  Logs land in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/smi.txt 2>&1
-timeout -s KILL 900 python -m pytest tests -m gpu -x -q -k "sliced" > gpurun_out/t_sliced.log 2>&1
+timeout -s KILL 900 python -m pytest tests -m gpu -q > gpurun_out/t_sliced.log 2>&1
 echo "sliced tests rc=$?" | tee -a gpurun_out/t_sliced.log
 tail -15 gpurun_out/t_sliced.log
 for m in sliced fast; do

@@ -206,7 +206,7 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
             if len(i1) > 63 or len(i2) > 63:
                 raise _Unsupported("mask too heavy")
             terms.append(_term_record(T_PI | (len(i1) << 2) | (len(i2) << 8), i1, i2, None, zero_row))
-        general_ctl = []
+        general = []
         for j in range(min(int(q.counts[g]), D)):
             al, be = int(q.alpha[g, j]) & 7, int(q.beta[g, j]) & 7
             r1, r2 = rows_of(q.alpha_params[g, j]), rows_of(q.beta_params[g, j])
@@ -217,11 +217,7 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
             nz = [c for c in combos if c not in (None, "zero")]
             monoid_ok = all(c is not None for c in combos) and nz and len({c[2] for c in nz}) == 1
             if not monoid_ok:
-                if len(general_ctl) >= MAX_GENERAL_PAIRS:
-                    raise _Unsupported("too many general phase pairs in one graph")
-                slot = len(general_ctl)
-                general_ctl.append(al | (be << 3))
-                terms.append(_term_record(T_PAIR_GENERAL | (len(i1) << 2) | (len(i2) << 8) | (slot << 14), i1, i2, None, zero_row))
+                general.append((al, be, i1, i2))
                 continue
             # value(pa, pb) as a polynomial: base + pa d10 + pb d01 + pa pb d11 in the exponents (a mod 8, b)
             ref = nz[0]
@@ -251,9 +247,6 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
         if units > 31:
             raise _Unsupported("b counter needs more than 5 planes")
         nb = max(1, units.bit_length())
-        n_idx = 3 + nb + 2 * len(general_ctl)
-        if n_idx > MAX_INDEX_BITS:
-            raise _Unsupported("decode table of a graph would exceed 2^%d entries" % MAX_INDEX_BITS)
         p_t = n_tot >> 2
         r = n_tot & 3
         a_s = (a_s + 2 * p_t) & 7
@@ -263,28 +256,52 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
         ff = tuple(int(v) for v in pre.floatfactor[g])
         if always_zero:
             ff = (0, 0, 0, 0)
-        k1 = _zw_mul(_zw_mul(UNIT[a_s], ONE_PLUS_W_POW[r]), ff)
-        k2 = _zw_mul(k1, SQRT2)
-        if max(abs(v) for v in k1 + k2) >= 2**31:
-            raise _Unsupported("graph constants overflow int32")
-        if len(terms) > 0xFFFF:
-            raise _Unsupported("too many terms")
         power2 = int(pre.power2[g])
-        body = [w for t in terms for w in t] + [0] * 8  # slack: the kernel prefetches the next term's eight words
-        words = np.zeros(SLICED_HEADER_WORDS + len(body), dtype=np.uint32)
-        words[0] = len(terms) | (len(general_ctl) << 16)
-        words[1] = n_idx | (nb << 8)
-        words[SLICED_HEADER_WORDS:] = np.array(body, dtype=np.uint64).astype(np.uint32)
-        pad = (-len(words)) % 4
-        if pad:
-            words = np.concatenate([words, np.zeros(pad, np.uint32)])
-        words[3] = len(words)
-        recs.append(words)
-        shifts_base.append(p_t + power2)
-        decode.append(
-            dict(nb=nb, n_idx=n_idx, b64=b_base + B_OFFSET, k1=k1, k2=k2, ctl=list(general_ctl), p_t=p_t, power2=power2,
-                 aff=np.complex64(pre.approximate_floatfactors[g]))
-        )
+        # General pairs: the first few extend the decode-table index by (pa, pb); each further pair splits the graph
+        # into one variant per (pa, pb) combination -- the pair's factor for that combination is folded into the
+        # constants and a gate term makes the variant vanish for every other combination, so exactly one variant of
+        # a graph contributes for a given shot (the float sum of the approximate branch sees the same addends).
+        in_table = min(len(general), MAX_GENERAL_PAIRS, (MAX_INDEX_BITS - 3 - nb) // 2)
+        excess = general[in_table:]
+        if len(excess) > 3:
+            raise _Unsupported("too many general phase pairs in one graph")
+        n_idx = 3 + nb + 2 * in_table
+        general_ctl = []
+        for slot, (al, be, i1, i2) in enumerate(general[:in_table]):
+            general_ctl.append(al | (be << 3))
+            terms.append(_term_record(T_PAIR_GENERAL | (len(i1) << 2) | (len(i2) << 8) | (slot << 14), i1, i2, None, zero_row))
+        for combo in range(4 ** len(excess)):
+            ffv = ff
+            gates = []
+            for e, (al, be, i1, i2) in enumerate(excess):
+                pa, pb = (combo >> (2 * e)) & 1, (combo >> (2 * e + 1)) & 1
+                ffv = _zw_mul(ffv, pair_factor(al ^ (4 * pa), be ^ (4 * pb)))
+                extra = sum(3 << (6 * v + 3) for v in range(3)) | ((0xF ^ (1 << (pa + 2 * pb))) << 18)
+                gates.append(_term_record(T_PAIR_MONOID | (len(i1) << 2) | (len(i2) << 8), i1, i2, extra, zero_row))
+            if excess and not any(ffv):
+                continue  # this combination contributes nothing
+            k1 = _zw_mul(_zw_mul(UNIT[a_s], ONE_PLUS_W_POW[r]), ffv)
+            k2 = _zw_mul(k1, SQRT2)
+            if max(abs(v) for v in k1 + k2) >= 2**31:
+                raise _Unsupported("graph constants overflow int32")
+            all_terms = terms + gates
+            if len(all_terms) > 0xFFFF:
+                raise _Unsupported("too many terms")
+            body = [w for t in all_terms for w in t] + [0] * 8  # slack: the kernel prefetches the next term's eight words
+            words = np.zeros(SLICED_HEADER_WORDS + len(body), dtype=np.uint32)
+            words[0] = len(all_terms) | (len(general_ctl) << 16)
+            words[1] = n_idx | (nb << 8)
+            words[SLICED_HEADER_WORDS:] = np.array(body, dtype=np.uint64).astype(np.uint32)
+            pad = (-len(words)) % 4
+            if pad:
+                words = np.concatenate([words, np.zeros(pad, np.uint32)])
+            words[3] = len(words)
+            recs.append(words)
+            shifts_base.append(p_t + power2)
+            decode.append(
+                dict(nb=nb, n_idx=n_idx, b64=b_base + B_OFFSET, k1=k1, k2=k2, ctl=list(general_ctl), p_t=p_t, power2=power2,
+                     aff=np.complex64(pre.approximate_floatfactors[g]))
+            )
 
     p_lo = min(shifts_base) if shifts_base else 0
     tables = []

@@ -36,20 +36,15 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
     if int(lvl[0]) == 0:
         return [("approx", np.float32(0), np.float32(0))] * N
 
-    def parity(o, n):
-        acc = 0
-        for w in range(n):
-            iw = int(data[o + w])
-            for k in range(4):
-                acc ^= rows.get((iw >> (8 * k)) & 255, 0)
-        return acc
+    def par2(w):
+        return rows.get((w & 0xFFFF) // 128, 0) ^ rows.get((w >> 16) // 128, 0)
 
     for c in range(int(lvl[7]), int(lvl[7]) + int(lvl[8])):
         coff, _, ng, _ = (int(v) for v in chunks[c])
         for _g in range(ng):
             off = coff + int(data[coff + _g])  # directory: chunk-relative record offsets
             h = [int(v) for v in data[off : off + SLICED_HEADER_WORDS]]
-            n_terms, n_gen = h[0] & 0xFFFF, h[0] >> 16
+            n_words, n_gen = h[0] & 0xFFFF, h[0] >> 16
             n_idx, nb = h[1] & 0xFF, (h[1] >> 8) & 0xFF
             tbl = coff + h[2]
             A = [0, 0, 0]
@@ -79,25 +74,27 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
                     cy = t
 
             o = off + SLICED_HEADER_WORDS
-            for _t in range(n_terms):
-                cw = int(data[o])
-                typ, n1, n2 = cw & 3, (cw >> 2) & 63, (cw >> 8) & 63
-                generic = cw >> 31
-                if generic:
-                    has_extra = typ == 3
-                    ex = int(data[o + 1]) if has_extra else 0
-                    o1 = o + 1 + (1 if has_extra else 0)
-                    o2 = o1 + n1
-                    length = 1 + (1 if has_extra else 0) + n1 + (n2 if typ != 0 else 0)
-                    length += (-length) % 4
+            end = o + n_words
+            q = 0
+            while o < end:
+                hdr = int(data[o])
+                cls, op, prm = hdr & 3, (hdr >> 2) & 7, hdr >> 5
+                if cls < 3:
+                    nw = (3, 5, 7)[cls]
+                    ws = [int(v) for v in data[o + 1 : o + 1 + nw]]
+                    o += 1 + nw
                 else:
-                    o1, o2 = o + 1, o + 4
-                    ex = int(data[o + 7]) if typ != 0 else 0
-                    length = 4 if typ == 0 else 8
-                if typ == 0:
-                    p = parity(o1, n1)
-                    add_a((cw >> 14) & 7, p)
-                    bm, zm = (cw >> 17) & 3, (cw >> 19) & 3
+                    nw = int(data[o + 1])
+                    ws = [int(v) for v in data[o + 2 : o + 2 + nw]]
+                    o += 2 + nw
+                p = 0
+                for w in ws:
+                    p ^= par2(w)
+                if op == 0:
+                    q = p
+                elif op == 1:
+                    add_a(prm & 7, p)
+                    bm, zm = (prm >> 3) & 3, (prm >> 5) & 3
                     if bm == 1:
                         add_cnt(p)
                     elif bm == 2:
@@ -106,12 +103,13 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
                         Z |= p
                     elif zm == 2:
                         Z |= ~p & full
-                elif typ == 1:
-                    A[2] ^= parity(o1, n1) & parity(o2, n2)
-                elif typ == 2:
-                    gen[(cw >> 14) & 15] = (parity(o1, n1), parity(o2, n2))
+                elif op == 2:
+                    A[2] ^= q & p
+                elif op == 3:
+                    gen[prm & 15] = (q, p)
                 else:
-                    pa, pb = parity(o1, n1), parity(o2, n2)
+                    ex = prm
+                    pa, pb = q, p
                     for v, wd in enumerate((pa, pb, pa & pb)):
                         add_a((ex >> (6 * v)) & 7, wd)
                         db = ((ex >> (6 * v + 3)) & 7) - 3
@@ -123,7 +121,7 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
                             wa = pa if combo & 1 else ~pa & full
                             wb = pb if combo & 2 else ~pb & full
                             Z |= wa & wb
-                o += length
+            assert o == end
             for s in range(N):
                 if (Z >> s) & 1:
                     continue

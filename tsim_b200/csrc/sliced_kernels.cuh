@@ -144,122 +144,83 @@ __device__ __forceinline__ void add_cnt5(uint32_t (&Bp)[5], uint32_t w) {
   }
 }
 
-// row r of this lane's column sits at xcol[r * 32]
-__device__ __forceinline__ uint32_t ld_row(const uint32_t* __restrict__ xcol, uint32_t row) { return xcol[row * 32u]; }
-
-__device__ __forceinline__ uint32_t xor4(const uint32_t* __restrict__ xcol, uint32_t iw) {
-  const uint32_t a0 = ld_row(xcol, iw & 255u), a1 = ld_row(xcol, __byte_perm(iw, 0, 0x4441));
-  const uint32_t a2 = ld_row(xcol, __byte_perm(iw, 0, 0x4442)), a3 = ld_row(xcol, iw >> 24);
-  return (a0 ^ a1) ^ (a2 ^ a3);
+// Row offsets in the block stream are byte offsets (row * 128) into this lane's column of the group's matrix.
+__device__ __forceinline__ uint32_t ld_off(const char* __restrict__ xb, uint32_t off) {
+  return *reinterpret_cast<const uint32_t*>(xb + off);
+}
+__device__ __forceinline__ uint32_t par2(const char* __restrict__ xb, uint32_t w) {
+  return ld_off(xb, w & 0xFFFFu) ^ ld_off(xb, w >> 16);
 }
 
-__device__ __forceinline__ void rows4(const uint32_t* __restrict__ xcol, uint32_t iw, uint32_t (&r)[4]) {
-  r[0] = ld_row(xcol, iw & 255u);
-  r[1] = ld_row(xcol, __byte_perm(iw, 0, 0x4441));
-  r[2] = ld_row(xcol, __byte_perm(iw, 0, 0x4442));
-  r[3] = ld_row(xcol, iw >> 24);
-}
+enum SlicedOp { OP_FIRST = 0, OP_LIN = 1, OP_PI = 2, OP_PAIRGEN = 3, OP_PAIRMON = 4 };
 
-__device__ __forceinline__ uint32_t xor12(const uint32_t* __restrict__ xcol, uint32_t i0, uint32_t i1, uint32_t i2) {
-  uint32_t a[4], b[4], c[4];
-  rows4(xcol, i0, a);
-  rows4(xcol, i1, b);
-  rows4(xcol, i2, c);
-  return (a[0] ^ a[1] ^ a[2]) ^ (a[3] ^ b[0] ^ b[1]) ^ (b[2] ^ b[3] ^ c[0]) ^ (c[1] ^ c[2] ^ c[3]);
-}
-
-__device__ __forceinline__ void xor24(const uint32_t* __restrict__ xcol, uint32_t i0, uint32_t i1, uint32_t i2, uint32_t j0, uint32_t j1,
-                                      uint32_t j2, uint32_t& p1, uint32_t& p2) {
-  uint32_t a[4], b[4], c[4], d[4], e[4], f[4];
-  rows4(xcol, i0, a);
-  rows4(xcol, i1, b);
-  rows4(xcol, i2, c);
-  rows4(xcol, j0, d);
-  rows4(xcol, j1, e);
-  rows4(xcol, j2, f);
-  p1 = (a[0] ^ a[1] ^ a[2]) ^ (a[3] ^ b[0] ^ b[1]) ^ (b[2] ^ b[3] ^ c[0]) ^ (c[1] ^ c[2] ^ c[3]);
-  p2 = (d[0] ^ d[1] ^ d[2]) ^ (d[3] ^ e[0] ^ e[1]) ^ (e[2] ^ e[3] ^ f[0]) ^ (f[1] ^ f[2] ^ f[3]);
-}
-
-__device__ __forceinline__ uint32_t sliced_parity(const uint32_t* __restrict__ cbase, uint32_t o, int n, const uint32_t* __restrict__ xcol) {
-  uint32_t acc0 = 0, acc1 = 0;
-  int w = 0;
-  for (; w + 1 < n; w += 2) {
-    const uint32_t i0 = cbase[o + w], i1 = cbase[o + w + 1];
-    acc0 ^= xor4(xcol, i0);
-    acc1 ^= xor4(xcol, i1);
-  }
-  if (w < n) acc0 ^= xor4(xcol, cbase[o + w]);
-  return acc0 ^ acc1;
-}
-
-// phase 1: the term stream of one graph for the 32 slabs of the group -> plane rows plw[r * 32]:
-// r = 0 "some factor vanished", 1..3 a, 4..4+nb-1 the b counter, then (pa, pb) of every general pair
+// phase 1: the block stream of one graph for the 32 slabs of the group -> plane rows plw[r * 32]:
+// r = 0 "some factor vanished", 1..3 a, 4..4+nb-1 the b counter, then (pa, pb) of every in-table general pair.
+// Block format: pack_sliced.py::_block.
 __device__ __forceinline__ void sliced_phase1(const uint32_t* __restrict__ cbase, uint32_t rec, const uint32_t* __restrict__ xcol,
                                               uint32_t* __restrict__ plw) {
-  const uint4 h0 = *reinterpret_cast<const uint4*>(cbase + rec);
-  const int n_terms = (int)(h0.x & 0xFFFFu);
+  const char* __restrict__ xb = reinterpret_cast<const char*>(xcol);
+  const uint2 h0 = *reinterpret_cast<const uint2*>(cbase + rec);
   const uint32_t nb = (h0.y >> 8) & 0xFFu;
-  uint32_t A0 = 0, A1 = 0, A2 = 0, Z = 0;
+  uint32_t A0 = 0, A1 = 0, A2 = 0, Z = 0, q = 0;
   uint32_t Bp[5] = {0, 0, 0, 0, 0};
-  // software-pipelined: the next term's record is fetched while the current term's rows are in flight
-  uint32_t o = rec + kSlicedHeaderWords;
-  uint4 cur0 = *reinterpret_cast<const uint4*>(cbase + o), cur1 = *reinterpret_cast<const uint4*>(cbase + o + 4);
-  for (int t = 0; t < n_terms; ++t) {
-    const uint32_t cw = cur0.x;
-    const uint32_t type = cw & 3u;
-    const int n1 = (int)((cw >> 2) & 63u), n2 = (int)((cw >> 8) & 63u);
-    const bool generic = (cw >> 31) != 0u;
-    uint32_t len;
-    if (!generic) len = type == 0u ? 4u : 8u;
-    else len = (uint32_t)round4(1 + (type == 3u ? 1 : 0) + n1 + (type != 0u ? n2 : 0));
-    const uint4 nx0 = *reinterpret_cast<const uint4*>(cbase + o + len);
-    const uint4 nx1 = *reinterpret_cast<const uint4*>(cbase + o + len + 4);
-    uint32_t p1, p2 = 0, ex = 0;
-    if (!generic) {
-      // compact record: twelve rows per parity, loaded unconditionally (padding names the zero row) so that all
-      // loads of the term are in flight before the first XOR needs one
-      if (type == 0u) {
-        p1 = xor12(xcol, cur0.y, cur0.z, cur0.w);
-      } else {
-        xor24(xcol, cur0.y, cur0.z, cur0.w, cur1.x, cur1.y, cur1.z, p1, p2);
-        ex = cur1.w;
+  const uint32_t* __restrict__ b = cbase + rec + kSlicedHeaderWords;
+  const uint32_t* __restrict__ end = b + (h0.x & 0xFFFFu);
+  while (b < end) {
+    const uint2 h = *reinterpret_cast<const uint2*>(b);
+    const uint32_t hdr = h.x, cls = hdr & 3u;
+    uint32_t p;
+    if (cls == 0u) {
+      const uint2 w1 = *reinterpret_cast<const uint2*>(b + 2);
+      p = par2(xb, h.y) ^ par2(xb, w1.x) ^ par2(xb, w1.y);
+      b += 4;
+    } else if (cls == 1u) {
+      const uint2 w1 = *reinterpret_cast<const uint2*>(b + 2), w2 = *reinterpret_cast<const uint2*>(b + 4);
+      p = (par2(xb, h.y) ^ par2(xb, w1.x) ^ par2(xb, w1.y)) ^ (par2(xb, w2.x) ^ par2(xb, w2.y));
+      b += 6;
+    } else if (cls == 2u) {
+      const uint2 w1 = *reinterpret_cast<const uint2*>(b + 2), w2 = *reinterpret_cast<const uint2*>(b + 4);
+      const uint2 w3 = *reinterpret_cast<const uint2*>(b + 6);
+      p = (par2(xb, h.y) ^ par2(xb, w1.x) ^ par2(xb, w1.y)) ^ (par2(xb, w2.x) ^ par2(xb, w2.y)) ^ (par2(xb, w3.x) ^ par2(xb, w3.y));
+      b += 8;
+    } else {
+      const uint32_t n = h.y;
+      p = 0u;
+      for (uint32_t i = 0; i < n; i += 2) {
+        const uint2 w = *reinterpret_cast<const uint2*>(b + 2 + i);
+        p ^= par2(xb, w.x) ^ par2(xb, w.y);
       }
-    } else {
-      const uint32_t o1 = o + 1 + (type == 3u ? 1u : 0u);
-      if (type == 3u) ex = cbase[o + 1];
-      p1 = sliced_parity(cbase, o1, n1, xcol);
-      if (type != 0u) p2 = sliced_parity(cbase, o1 + n1, n2, xcol);
+      b += 2 + n;
     }
-    if (type == 0u) {
-      add_a3(A0, A1, A2, (cw >> 14) & 7u, p1);
-      const uint32_t bm = (cw >> 17) & 3u, zm = (cw >> 19) & 3u;
-      if (bm) add_cnt5(Bp, bm == 1u ? p1 : ~p1);
-      if (zm) Z |= (zm == 1u ? p1 : ~p1);
-    } else if (type == 1u) {
-      A2 ^= p1 & p2;
-    } else if (type == 2u) {
-      const uint32_t r0 = 4u + nb + 2u * ((cw >> 14) & 15u);
-      plw[r0 * 32u] = p1;
-      plw[(r0 + 1u) * 32u] = p2;
+    const uint32_t op = (hdr >> 2) & 7u, prm = hdr >> 5;
+    if (op == OP_FIRST) {
+      q = p;
+    } else if (op == OP_PI) {
+      A2 ^= q & p;
+    } else if (op == OP_LIN) {
+      add_a3(A0, A1, A2, prm & 7u, p);
+      const uint32_t bm = (prm >> 3) & 3u, zm = (prm >> 5) & 3u;
+      if (bm) add_cnt5(Bp, bm == 1u ? p : ~p);
+      if (zm) Z |= (zm == 1u ? p : ~p);
+    } else if (op == OP_PAIRGEN) {
+      const uint32_t r0 = 4u + nb + 2u * (prm & 15u);
+      plw[r0 * 32u] = q;
+      plw[(r0 + 1u) * 32u] = p;
     } else {
-      const uint32_t wd[3] = {p1, p2, p1 & p2};
+      const uint32_t wd[3] = {q, p, q & p};
 #pragma unroll
       for (int v = 0; v < 3; ++v) {
-        add_a3(A0, A1, A2, (ex >> (6 * v)) & 7u, wd[v]);
-        const int db = (int)((ex >> (6 * v + 3)) & 7u) - 3;
+        add_a3(A0, A1, A2, (prm >> (6 * v)) & 7u, wd[v]);
+        const int db = (int)((prm >> (6 * v + 3)) & 7u) - 3;
         const uint32_t w = db > 0 ? wd[v] : ~wd[v];
         for (int r = 0; r < (db < 0 ? -db : db); ++r) add_cnt5(Bp, w);
       }
-      const uint32_t ztt = (ex >> 18) & 15u;
-      if (ztt & 1u) Z |= ~p1 & ~p2;
-      if (ztt & 2u) Z |= p1 & ~p2;
-      if (ztt & 4u) Z |= ~p1 & p2;
-      if (ztt & 8u) Z |= p1 & p2;
+      const uint32_t ztt = (prm >> 18) & 15u;
+      if (ztt & 1u) Z |= ~q & ~p;
+      if (ztt & 2u) Z |= q & ~p;
+      if (ztt & 4u) Z |= ~q & p;
+      if (ztt & 8u) Z |= q & p;
     }
-    o += len;
-    cur0 = nx0;
-    cur1 = nx1;
   }
   plw[0] = Z;
   plw[32] = A0;
@@ -332,8 +293,13 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int grp = wid / SPLIT, w = wid % SPLIT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  uint32_t* xcol = smem + prm.smem_xt_off + grp * prm.rows * 32 + lane;
-  uint32_t* plg = smem + prm.smem_pl_off + grp * (SPLIT * kPlaneRows * 32) + lane;
+  // word offsets of this thread's columns; made opaque so that the compiler keeps them in registers instead of
+  // re-deriving them from threadIdx inside the block loop (it did, ten instructions per block)
+  uint32_t xoff = prm.smem_xt_off + grp * prm.rows * 32 + lane;
+  uint32_t ploff = prm.smem_pl_off + grp * (SPLIT * kPlaneRows * 32) + lane;
+  asm volatile("" : "+r"(xoff), "+r"(ploff));
+  uint32_t* xcol = smem + xoff;
+  uint32_t* plg = smem + ploff;
   float* pcol = reinterpret_cast<float*>(smem + prm.smem_prev_off) + grp * (32 * 32) + lane;
   uint32_t* sdata = smem + prm.smem_data_off;
 

@@ -712,7 +712,7 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
     p->stage_words = (int)data_words;
     used = data_words;
   } else {
-    p->stage_words = (max_chunk + 31) & ~31;
+    p->stage_words = std::max(32, (max_chunk + 31) & ~31);
     p->n_stages = (int)std::min<long long>(kMaxStages, budget_words / p->stage_words);
     used = (long long)p->n_stages * p->stage_words;
   }

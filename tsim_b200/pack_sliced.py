@@ -23,18 +23,14 @@ Graph record (uint32 words):
     [2]  offset of the decode table (filled in when the chunk is assembled)
     [3]  record words
     [4..7] reserved
-    then the term stream, one control word per term followed by its index words:
-        cw bits 0-1 type (0 LIN, 1 PI, 2 PAIR_GENERAL, 3 PAIR_MONOID), bits 2-7 n1, bits 8-13 n2 (index words of
-        the first / second parity; an index word holds four row indices, padded with the all-zero row), bit 31 generic.
-        Every term record is 16-byte aligned.  Compact form (all parities <= 3 index words, the common case):
-            LIN  [cw, a0, a1, a2]                      others  [cw, a0, a1, a2, b0, b1, b2, extra]
-        so a term is one or two 128-bit shared-memory reads at fixed positions (unused index words are never read).
-        Generic form (bit 31): [cw, extra?, a..., b...] padded to a multiple of four words.
-        LIN          bits 14-16 da, 17-18 bmode (1: count p, 2: count ~p), 19-20 zmode (1: Z |= p, 2: Z |= ~p)
-        PI           A2 ^= p1 & p2
-        PAIR_GENERAL bits 14-17 slot: parity words are kept for the per-shot ring product
-        PAIR_MONOID  one extra word after cw: for v in (pa, pb, pa&pb): da_v (3 bits), db_v + 3 (3 bits); bits 18-21
-                     truth table of vanishing combinations (bit pa + 2 pb)
+    then the block stream ([0] low half = its length in words).  A block computes one parity (see ``_block``) and applies
+    an op to it:
+        FIRST    keep the parity as q (first half of a two-parity term)
+        LIN      params da (3 bits) | bmode << 3 (1: count p, 2: count ~p) | zmode << 5 (1: Z |= p, 2: Z |= ~p)
+        PI       A2 ^= q & p
+        PAIRGEN  params slot: (q, p) become index planes of the decode table
+        PAIRMON  params: for v in (q, p, q & p): da_v (3 bits), db_v + 3 (3 bits); bits 18-21 truth table of the
+                 vanishing combinations (bit q + 2 p)
 
 Row indices: parameter i -> row i; row ``one_row`` is all ones (constants of the pi family), ``zero_row`` all zeros.
 """
@@ -53,7 +49,6 @@ MAX_GENERAL_PAIRS = 3
 MAX_INDEX_BITS = 11
 MAX_CHUNK_WORDS = 12288  # 48 KB stages
 B_OFFSET = 64
-T_LIN, T_PI, T_PAIR_GENERAL, T_PAIR_MONOID = 0, 1, 2, 3
 
 UNIT = [(1, 0, 0, 0), (0, 1, 0, 0), (0, 0, 1, 0), (0, 0, 0, -1), (-1, 0, 0, 0), (0, -1, 0, 0), (0, 0, -1, 0), (0, 0, 0, 1)]
 ONE_PLUS_SQRT2 = (1, 1, 0, 1)
@@ -101,28 +96,26 @@ def pair_factor(alpha: int, beta: int):
     return tuple(int(i == 0) + ua[i] + ub[i] - uc[i] for i in range(4))
 
 
-GENERIC = 1 << 31
+OP_FIRST, OP_LIN, OP_PI, OP_PAIRGEN, OP_PAIRMON = 0, 1, 2, 3, 4
+ROW_STRIDE_BYTES = 128  # a row of a group's transposed parameter matrix: 32 lanes x 4 bytes
+BLOCK_ROWS = (6, 10, 14)  # rows of the three straight-line block classes
 
 
-def _term_record(cw: int, i1: list[int], i2: list[int] | None, extra: int | None, zero_row: int) -> list[int]:
-    """Compact (4 or 8 words) or generic (padded to 4) term record.  Unused index words of the compact form name
-    the all-zero row four times: the kernel loads all twelve rows of a parity unconditionally."""
-    two = i2 is not None
-    zw = zero_row * 0x01010101
-    if len(i1) <= 3 and (not two or len(i2) <= 3):
-        rec = [cw] + i1 + [zw] * (3 - len(i1))
-        if two:
-            rec += i2 + [zw] * (3 - len(i2)) + [extra or 0]
-        return rec
-    rec = [cw | GENERIC] + ([extra] if extra is not None else []) + i1 + (i2 or [])
-    return rec + [0] * ((-len(rec)) % 4)
-
-
-def _index_words(rows: list[int], zero_row: int) -> list[int]:
-    rows = list(rows)
-    while len(rows) % 4:
-        rows.append(zero_row)
-    return [rows[i] | (rows[i + 1] << 8) | (rows[i + 2] << 16) | (rows[i + 3] << 24) for i in range(0, len(rows), 4)]
+def _block(op: int, params: int, rows: list[int], zero_row: int) -> list[int]:
+    """One parity block: header word ``cls | op << 2 | params << 5`` followed by 16-bit row offsets (row * 128 bytes),
+    two per word.  Classes 0-2 hold 6 / 10 / 14 rows (padded with the all-zero row: the kernel loads them with
+    straight-line code); class 3 is ``[hdr, n_words, offsets...]`` for heavier masks.  Blocks are 8-byte aligned."""
+    if params >> 27:
+        raise _Unsupported("block parameters do not fit")
+    offs = [r * ROW_STRIDE_BYTES for r in rows]
+    zo = zero_row * ROW_STRIDE_BYTES
+    for cls, cap in enumerate(BLOCK_ROWS):
+        if len(offs) <= cap:
+            offs = offs + [zo] * (cap - len(offs))
+            return [cls | (op << 2) | (params << 5)] + [offs[i] | (offs[i + 1] << 16) for i in range(0, cap, 2)]
+    offs = offs + [zo] * ((-len(offs)) % 4)  # an even number of offset words keeps the next block 8-byte aligned
+    words = [offs[i] | (offs[i + 1] << 16) for i in range(0, len(offs), 2)]
+    return [3 | (op << 2) | (params << 5), len(words)] + words
 
 
 class _Unsupported(ValueError):
@@ -135,8 +128,8 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
     n, h, p, q, pre = lv.node_phases, lv.halfpi_phases, lv.pi_products, lv.phase_pairs, lv.prefactor
     A, H, C, D = n.phases.shape[1], h.coeffs.shape[1], p.psi_const.shape[1], q.alpha.shape[1]
     approx = bool(pre.has_approximate_floatfactors)
-    if zero_row > 255:
-        raise _Unsupported("more than 254 parameters per level")
+    if zero_row * ROW_STRIDE_BYTES > 0xFFFF:
+        raise _Unsupported("more than 510 parameters per level")
 
     def rows_of(mask, const=0):
         r = [int(i) for i in np.flatnonzero(mask)]
@@ -154,10 +147,10 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
         always_zero = False
 
         def lin(rows, da=0, bmode=0, zmode=0):
-            iw = _index_words(rows, zero_row)
-            if len(iw) > 63:
-                raise _Unsupported("mask too heavy")
-            terms.append(_term_record(T_LIN | (len(iw) << 2) | ((da & 7) << 14) | (bmode << 17) | (zmode << 19), iw, None, None, zero_row))
+            terms.append(_block(OP_LIN, (da & 7) | (bmode << 3) | (zmode << 5), rows, zero_row))
+
+        def two(op, params, r1, r2):
+            terms.append(_block(OP_FIRST, 0, r1, zero_row) + _block(op, params, r2, zero_row))
 
         for j in range(min(int(n.counts[g]), A)):
             ph = int(n.phases[g, j]) & 7
@@ -202,22 +195,16 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
             r1, r2 = rows_of(p.psi_params[g, j], pc), rows_of(p.phi_params[g, j], fc)
             if not r1 or not r2:
                 continue  # psi or phi is identically 0
-            i1, i2 = _index_words(r1, zero_row), _index_words(r2, zero_row)
-            if len(i1) > 63 or len(i2) > 63:
-                raise _Unsupported("mask too heavy")
-            terms.append(_term_record(T_PI | (len(i1) << 2) | (len(i2) << 8), i1, i2, None, zero_row))
+            two(OP_PI, 0, r1, r2)
         general = []
         for j in range(min(int(q.counts[g]), D)):
             al, be = int(q.alpha[g, j]) & 7, int(q.beta[g, j]) & 7
             r1, r2 = rows_of(q.alpha_params[g, j]), rows_of(q.beta_params[g, j])
-            i1, i2 = _index_words(r1, zero_row), _index_words(r2, zero_row)
-            if len(i1) > 63 or len(i2) > 63:
-                raise _Unsupported("mask too heavy")
             combos = [monoid_exponents(pair_factor(al ^ (4 * pa), be ^ (4 * pb))) for pb in (0, 1) for pa in (0, 1)]
             nz = [c for c in combos if c not in (None, "zero")]
             monoid_ok = all(c is not None for c in combos) and nz and len({c[2] for c in nz}) == 1
             if not monoid_ok:
-                general.append((al, be, i1, i2))
+                general.append((al, be, r1, r2))
                 continue
             # value(pa, pb) as a polynomial: base + pa d10 + pb d01 + pa pb d11 in the exponents (a mod 8, b)
             ref = nz[0]
@@ -242,7 +229,7 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
                     b_base += db  # each negative unit is counted as (~p) - 1
                 units += abs(db)
             extra |= ztt << 18
-            terms.append(_term_record(T_PAIR_MONOID | (len(i1) << 2) | (len(i2) << 8), i1, i2, extra, zero_row))
+            two(OP_PAIRMON, extra, r1, r2)
 
         if units > 31:
             raise _Unsupported("b counter needs more than 5 planes")
@@ -267,17 +254,17 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
             raise _Unsupported("too many general phase pairs in one graph")
         n_idx = 3 + nb + 2 * in_table
         general_ctl = []
-        for slot, (al, be, i1, i2) in enumerate(general[:in_table]):
+        for slot, (al, be, r1, r2) in enumerate(general[:in_table]):
             general_ctl.append(al | (be << 3))
-            terms.append(_term_record(T_PAIR_GENERAL | (len(i1) << 2) | (len(i2) << 8) | (slot << 14), i1, i2, None, zero_row))
+            two(OP_PAIRGEN, slot, r1, r2)
         for combo in range(4 ** len(excess)):
             ffv = ff
             gates = []
-            for e, (al, be, i1, i2) in enumerate(excess):
+            for e, (al, be, r1, r2) in enumerate(excess):
                 pa, pb = (combo >> (2 * e)) & 1, (combo >> (2 * e + 1)) & 1
                 ffv = _zw_mul(ffv, pair_factor(al ^ (4 * pa), be ^ (4 * pb)))
                 extra = sum(3 << (6 * v + 3) for v in range(3)) | ((0xF ^ (1 << (pa + 2 * pb))) << 18)
-                gates.append(_term_record(T_PAIR_MONOID | (len(i1) << 2) | (len(i2) << 8), i1, i2, extra, zero_row))
+                gates.append(_block(OP_FIRST, 0, r1, zero_row) + _block(OP_PAIRMON, extra, r2, zero_row))
             if excess and not any(ffv):
                 continue  # this combination contributes nothing
             k1 = _zw_mul(_zw_mul(UNIT[a_s], ONE_PLUS_W_POW[r]), ffv)
@@ -285,11 +272,11 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
             if max(abs(v) for v in k1 + k2) >= 2**31:
                 raise _Unsupported("graph constants overflow int32")
             all_terms = terms + gates
-            if len(all_terms) > 0xFFFF:
+            body = [w for t in all_terms for w in t]
+            if len(body) > 0xFFFF:
                 raise _Unsupported("too many terms")
-            body = [w for t in all_terms for w in t] + [0] * 8  # slack: the kernel prefetches the next term's eight words
             words = np.zeros(SLICED_HEADER_WORDS + len(body), dtype=np.uint32)
-            words[0] = len(all_terms) | (len(general_ctl) << 16)
+            words[0] = len(body) | (len(general_ctl) << 16)
             words[1] = n_idx | (nb << 8)
             words[SLICED_HEADER_WORDS:] = np.array(body, dtype=np.uint64).astype(np.uint32)
             pad = (-len(words)) % 4

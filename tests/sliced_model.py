@@ -10,7 +10,7 @@ import numpy as np
 
 from fast_model import M32, _s32
 from tsim_b200 import pack as PK
-from tsim_b200.pack_sliced import SLICED_HEADER_WORDS
+from tsim_b200.pack_sliced import CLASS_WORDS, PI_CLASSES, SLICED_HEADER_WORDS
 
 
 def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarray):
@@ -36,8 +36,8 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
     if int(lvl[0]) == 0:
         return [("approx", np.float32(0), np.float32(0))] * N
 
-    def par2(w):
-        return rows.get((w & 0xFFFF) // 128, 0) ^ rows.get((w >> 16) // 128, 0)
+    def par4(w):
+        return rows.get(w & 255, 0) ^ rows.get((w >> 8) & 255, 0) ^ rows.get((w >> 16) & 255, 0) ^ rows.get(w >> 24, 0)
 
     for c in range(int(lvl[7]), int(lvl[7]) + int(lvl[8])):
         coff, _, ng, _ = (int(v) for v in chunks[c])
@@ -73,54 +73,74 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
                     Bp[k] ^= cy
                     cy = t
 
+            def lin_op(prm, p):
+                nonlocal Z
+                add_a(prm & 7, p)
+                bm, zm = (prm >> 3) & 3, (prm >> 5) & 3
+                if bm == 1:
+                    add_cnt(p)
+                elif bm == 2:
+                    add_cnt(~p & full)
+                if zm == 1:
+                    Z |= p
+                elif zm == 2:
+                    Z |= ~p & full
+
+            def par_words(o, n):
+                p = 0
+                for w in data[o : o + n]:
+                    p ^= par4(int(w))
+                return p
+
             o = off + SLICED_HEADER_WORDS
             end = o + n_words
-            q = 0
             while o < end:
-                hdr = int(data[o])
-                cls, op, prm = hdr & 3, (hdr >> 2) & 7, hdr >> 5
-                if cls < 3:
-                    nw = (3, 5, 7)[cls]
-                    ws = [int(v) for v in data[o + 1 : o + 1 + nw]]
-                    o += 1 + nw
-                else:
+                kind, count = int(data[o]) & 0xFFFF, int(data[o]) >> 16
+                o += 4
+                if kind < 3:  # LIN runs
+                    nw = CLASS_WORDS[kind]
+                    for _i in range(count):
+                        lin_op(int(data[o]), par_words(o + 1, nw))
+                        o += 4 if kind < 2 else 8
+                    continue
+                if kind < 9:  # PI runs
+                    c1, c2 = PI_CLASSES[kind - 3]
+                    for _i in range(count):
+                        A[2] ^= par_words(o, CLASS_WORDS[c1]) & par_words(o + 4, CLASS_WORDS[c2])
+                        o += 8
+                    continue
+                assert kind == 15
+                gend = o + count
+                q = 0
+                while o < gend:
+                    hdr = int(data[o])
+                    op, prm = hdr & 7, hdr >> 3
                     nw = int(data[o + 1])
-                    ws = [int(v) for v in data[o + 2 : o + 2 + nw]]
+                    p = par_words(o + 2, nw)
                     o += 2 + nw
-                p = 0
-                for w in ws:
-                    p ^= par2(w)
-                if op == 0:
-                    q = p
-                elif op == 1:
-                    add_a(prm & 7, p)
-                    bm, zm = (prm >> 3) & 3, (prm >> 5) & 3
-                    if bm == 1:
-                        add_cnt(p)
-                    elif bm == 2:
-                        add_cnt(~p & full)
-                    if zm == 1:
-                        Z |= p
-                    elif zm == 2:
-                        Z |= ~p & full
-                elif op == 2:
-                    A[2] ^= q & p
-                elif op == 3:
-                    gen[prm & 15] = (q, p)
-                else:
-                    ex = prm
-                    pa, pb = q, p
-                    for v, wd in enumerate((pa, pb, pa & pb)):
-                        add_a((ex >> (6 * v)) & 7, wd)
-                        db = ((ex >> (6 * v + 3)) & 7) - 3
-                        for _ in range(abs(db)):
-                            add_cnt(wd if db > 0 else (~wd & full))
-                    ztt = (ex >> 18) & 15
-                    for combo in range(4):
-                        if (ztt >> combo) & 1:
-                            wa = pa if combo & 1 else ~pa & full
-                            wb = pb if combo & 2 else ~pb & full
-                            Z |= wa & wb
+                    if op == 0:
+                        q = p
+                    elif op == 1:
+                        lin_op(prm, p)
+                    elif op == 2:
+                        A[2] ^= q & p
+                    elif op == 3:
+                        gen[prm & 15] = (q, p)
+                    else:
+                        ex = prm
+                        pa, pb = q, p
+                        for v, wd in enumerate((pa, pb, pa & pb)):
+                            add_a((ex >> (6 * v)) & 7, wd)
+                            db = ((ex >> (6 * v + 3)) & 7) - 3
+                            for _ in range(abs(db)):
+                                add_cnt(wd if db > 0 else (~wd & full))
+                        ztt = (ex >> 18) & 15
+                        for combo in range(4):
+                            if (ztt >> combo) & 1:
+                                wa = pa if combo & 1 else ~pa & full
+                                wb = pb if combo & 2 else ~pb & full
+                                Z |= wa & wb
+                assert o == gend
             assert o == end
             for s in range(N):
                 if (Z >> s) & 1:

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtsim_b200.so")
+LIB_PATH = os.environ.get("TSIM_B200_LIB") or os.path.join(_HERE, "libtsim_b200.so")  # override: kernel experiments
 
 TSB_F_BYTES, TSB_F_PACKED = 0, 1
 TSB_OUT_BYTES, TSB_OUT_PACKED = 0, 1

@@ -42,6 +42,7 @@ struct SParams {
   int smem_prev_off;
   int smem_data_off;
   int rows;  // zero_row + 1
+  uint4 sel;  // dp4a byte selectors {128 << 0, 128 << 8, 128 << 16, 128 << 24} (see par4)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -144,64 +145,95 @@ __device__ __forceinline__ void add_cnt5(uint32_t (&Bp)[5], uint32_t w) {
   }
 }
 
-// Row offsets in the block stream are byte offsets (row * 128) into this lane's column of the group's matrix.
-__device__ __forceinline__ uint32_t ld_off(const char* __restrict__ xb, uint32_t off) {
-  return *reinterpret_cast<const uint32_t*>(xb + off);
+// Row indices in the term stream are bytes, four per word.  xs = 32-bit shared-memory address of this lane's column of
+// the group's matrix (row r at xs + 128 r).  One dp4a with a selector word (128 in byte k, 0 elsewhere) turns byte k
+// into the row's address on the FMA pipe, which leaves the ALU pipe to the XORs.  The selectors arrive as kernel
+// parameters so that they stay constant-bank operands.
+__device__ __forceinline__ uint32_t ld_sh(uint32_t saddr) {
+  return *reinterpret_cast<const uint32_t*>(__cvta_shared_to_generic(saddr));
 }
-__device__ __forceinline__ uint32_t par2(const char* __restrict__ xb, uint32_t w) {
-  return ld_off(xb, w & 0xFFFFu) ^ ld_off(xb, w >> 16);
+__device__ __forceinline__ uint32_t par4(uint32_t xs, uint32_t w, const uint4& sel) {
+  return (ld_sh(__dp4a(w, sel.x, xs)) ^ ld_sh(__dp4a(w, sel.y, xs))) ^ (ld_sh(__dp4a(w, sel.z, xs)) ^ ld_sh(__dp4a(w, sel.w, xs)));
+}
+template <int N>
+__device__ __forceinline__ uint32_t par_words(uint32_t xs, const uint32_t* w, const uint4& sel) {
+  uint32_t p = par4(xs, w[0], sel);
+#pragma unroll
+  for (int i = 1; i < N; ++i) p ^= par4(xs, w[i], sel);
+  return p;
+}
+// N words (multiple of 4) from a 16-byte aligned, warp-uniform address
+template <int N>
+__device__ __forceinline__ void ld_words(const uint32_t* __restrict__ b, uint32_t (&w)[N]) {
+  static_assert(N % 4 == 0, "items are 16-byte multiples");
+#pragma unroll
+  for (int i = 0; i < N; i += 4) {
+    const uint4 v = *reinterpret_cast<const uint4*>(b + i);
+    w[i] = v.x; w[i + 1] = v.y; w[i + 2] = v.z; w[i + 3] = v.w;
+  }
 }
 
 enum SlicedOp { OP_FIRST = 0, OP_LIN = 1, OP_PI = 2, OP_PAIRGEN = 3, OP_PAIRMON = 4 };
+enum SlicedRun { RUN_LIN = 0, RUN_PI = 3, RUN_GENERIC = 15 };
 
-// phase 1: the block stream of one graph for the 32 slabs of the group -> plane rows plw[r * 32]:
-// r = 0 "some factor vanished", 1..3 a, 4..4+nb-1 the b counter, then (pa, pb) of every in-table general pair.
-// Block format: pack_sliced.py::_block.
-__device__ __forceinline__ void sliced_phase1(const uint32_t* __restrict__ cbase, uint32_t rec, const uint32_t* __restrict__ xcol,
-                                              uint32_t* __restrict__ plw) {
-  const char* __restrict__ xb = reinterpret_cast<const char*>(xcol);
-  const uint2 h0 = *reinterpret_cast<const uint2*>(cbase + rec);
-  const uint32_t nb = (h0.y >> 8) & 0xFFu;
-  uint32_t A0 = 0, A1 = 0, A2 = 0, Z = 0, q = 0;
-  uint32_t Bp[5] = {0, 0, 0, 0, 0};
-  const uint32_t* __restrict__ b = cbase + rec + kSlicedHeaderWords;
-  const uint32_t* __restrict__ end = b + (h0.x & 0xFFFFu);
+struct Planes {
+  uint32_t A0, A1, A2, Z;
+  uint32_t Bp[5];
+};
+
+__device__ __forceinline__ void lin_op(Planes& P, uint32_t prm, uint32_t p) {
+  add_a3(P.A0, P.A1, P.A2, prm & 7u, p);
+  const uint32_t bm = (prm >> 3) & 3u, zm = (prm >> 5) & 3u;
+  if (bm) add_cnt5(P.Bp, bm == 1u ? p : ~p);
+  if (zm) P.Z |= (zm == 1u ? p : ~p);
+}
+
+// LIN run: item = [params, index words]; NW = index words used, item = 4 words (NW <= 3) or 8 words
+template <int NW>
+__device__ __forceinline__ const uint32_t* lin_run(const uint32_t* __restrict__ b, uint32_t count, uint32_t xs, const uint4& sel, Planes& P) {
+  constexpr int IW = NW <= 3 ? 4 : 8;
+#pragma unroll 1
+  for (uint32_t i = 0; i < count; ++i, b += IW) {
+    uint32_t w[IW];
+    ld_words<IW>(b, w);
+    lin_op(P, w[0], par_words<NW>(xs, w + 1, sel));
+  }
+  return b;
+}
+
+// PI run: item = [4 index words psi, 4 index words phi], N1 / N2 of them used
+template <int N1, int N2>
+__device__ __forceinline__ const uint32_t* pi_run(const uint32_t* __restrict__ b, uint32_t count, uint32_t xs, const uint4& sel, Planes& P) {
+#pragma unroll 1
+  for (uint32_t i = 0; i < count; ++i, b += 8) {
+    uint32_t w[8];
+    ld_words<8>(b, w);
+    P.A2 ^= par_words<N1>(xs, w, sel) & par_words<N2>(xs, w + 4, sel);
+  }
+  return b;
+}
+
+// generic run: a stream of parity blocks (pack_sliced.py::_block) with a per-block dispatch
+__device__ __forceinline__ const uint32_t* generic_run(const uint32_t* __restrict__ b, uint32_t words, uint32_t xs, const uint4& sel, Planes& P,
+                                                        uint32_t nb, uint32_t* __restrict__ plw) {
+  const uint32_t* __restrict__ end = b + words;
+  uint32_t q = 0;
   while (b < end) {
     const uint2 h = *reinterpret_cast<const uint2*>(b);
-    const uint32_t hdr = h.x, cls = hdr & 3u;
-    uint32_t p;
-    if (cls == 0u) {
-      const uint2 w1 = *reinterpret_cast<const uint2*>(b + 2);
-      p = par2(xb, h.y) ^ par2(xb, w1.x) ^ par2(xb, w1.y);
-      b += 4;
-    } else if (cls == 1u) {
-      const uint2 w1 = *reinterpret_cast<const uint2*>(b + 2), w2 = *reinterpret_cast<const uint2*>(b + 4);
-      p = (par2(xb, h.y) ^ par2(xb, w1.x) ^ par2(xb, w1.y)) ^ (par2(xb, w2.x) ^ par2(xb, w2.y));
-      b += 6;
-    } else if (cls == 2u) {
-      const uint2 w1 = *reinterpret_cast<const uint2*>(b + 2), w2 = *reinterpret_cast<const uint2*>(b + 4);
-      const uint2 w3 = *reinterpret_cast<const uint2*>(b + 6);
-      p = (par2(xb, h.y) ^ par2(xb, w1.x) ^ par2(xb, w1.y)) ^ (par2(xb, w2.x) ^ par2(xb, w2.y)) ^ (par2(xb, w3.x) ^ par2(xb, w3.y));
-      b += 8;
-    } else {
-      const uint32_t n = h.y;
-      p = 0u;
-      for (uint32_t i = 0; i < n; i += 2) {
-        const uint2 w = *reinterpret_cast<const uint2*>(b + 2 + i);
-        p ^= par2(xb, w.x) ^ par2(xb, w.y);
-      }
-      b += 2 + n;
+    const uint32_t hdr = h.x, n = h.y;
+    uint32_t p = 0u;
+    for (uint32_t i = 0; i < n; i += 2) {
+      const uint2 w = *reinterpret_cast<const uint2*>(b + 2 + i);
+      p ^= par4(xs, w.x, sel) ^ par4(xs, w.y, sel);
     }
-    const uint32_t op = (hdr >> 2) & 7u, prm = hdr >> 5;
+    b += 2 + n;
+    const uint32_t op = hdr & 7u, prm = hdr >> 3;
     if (op == OP_FIRST) {
       q = p;
     } else if (op == OP_PI) {
-      A2 ^= q & p;
+      P.A2 ^= q & p;
     } else if (op == OP_LIN) {
-      add_a3(A0, A1, A2, prm & 7u, p);
-      const uint32_t bm = (prm >> 3) & 3u, zm = (prm >> 5) & 3u;
-      if (bm) add_cnt5(Bp, bm == 1u ? p : ~p);
-      if (zm) Z |= (zm == 1u ? p : ~p);
+      lin_op(P, prm, p);
     } else if (op == OP_PAIRGEN) {
       const uint32_t r0 = 4u + nb + 2u * (prm & 15u);
       plw[r0 * 32u] = q;
@@ -210,25 +242,59 @@ __device__ __forceinline__ void sliced_phase1(const uint32_t* __restrict__ cbase
       const uint32_t wd[3] = {q, p, q & p};
 #pragma unroll
       for (int v = 0; v < 3; ++v) {
-        add_a3(A0, A1, A2, (prm >> (6 * v)) & 7u, wd[v]);
+        add_a3(P.A0, P.A1, P.A2, (prm >> (6 * v)) & 7u, wd[v]);
         const int db = (int)((prm >> (6 * v + 3)) & 7u) - 3;
         const uint32_t w = db > 0 ? wd[v] : ~wd[v];
-        for (int r = 0; r < (db < 0 ? -db : db); ++r) add_cnt5(Bp, w);
+        for (int r = 0; r < (db < 0 ? -db : db); ++r) add_cnt5(P.Bp, w);
       }
       const uint32_t ztt = (prm >> 18) & 15u;
-      if (ztt & 1u) Z |= ~q & ~p;
-      if (ztt & 2u) Z |= q & ~p;
-      if (ztt & 4u) Z |= ~q & p;
-      if (ztt & 8u) Z |= q & p;
+      if (ztt & 1u) P.Z |= ~q & ~p;
+      if (ztt & 2u) P.Z |= q & ~p;
+      if (ztt & 4u) P.Z |= ~q & p;
+      if (ztt & 8u) P.Z |= q & p;
     }
   }
-  plw[0] = Z;
-  plw[32] = A0;
-  plw[64] = A1;
-  plw[96] = A2;
+  return b;
+}
+
+// phase 1: the term stream of one graph (typed runs, pack_sliced.py::_emit_runs) for the 32 slabs of the group ->
+// plane rows plw[r * 32]: r = 0 "some factor vanished", 1..3 a, 4..4+nb-1 the b counter, then (pa, pb) of every
+// in-table general pair.
+__device__ __forceinline__ void sliced_phase1(const uint32_t* __restrict__ cbase, uint32_t rec, const uint32_t* __restrict__ xcol,
+                                              uint32_t* __restrict__ plw, const uint4& sel) {
+  const uint32_t xs = smem_u32(xcol);
+  const uint2 h0 = *reinterpret_cast<const uint2*>(cbase + rec);
+  const uint32_t nb = (h0.y >> 8) & 0xFFu;
+  Planes P;
+  P.A0 = P.A1 = P.A2 = P.Z = 0u;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) P.Bp[i] = 0u;
+  const uint32_t* __restrict__ b = cbase + rec + kSlicedHeaderWords;
+  const uint32_t* __restrict__ end = b + (h0.x & 0xFFFFu);
+  while (b < end) {
+    const uint32_t rh = *b;
+    const uint32_t kind = rh & 0xFFFFu, count = rh >> 16;
+    b += 4;
+    switch (kind) {
+      case RUN_LIN + 0: b = lin_run<2>(b, count, xs, sel, P); break;
+      case RUN_LIN + 1: b = lin_run<3>(b, count, xs, sel, P); break;
+      case RUN_LIN + 2: b = lin_run<4>(b, count, xs, sel, P); break;
+      case RUN_PI + 0: b = pi_run<2, 2>(b, count, xs, sel, P); break;
+      case RUN_PI + 1: b = pi_run<2, 3>(b, count, xs, sel, P); break;
+      case RUN_PI + 2: b = pi_run<2, 4>(b, count, xs, sel, P); break;
+      case RUN_PI + 3: b = pi_run<3, 3>(b, count, xs, sel, P); break;
+      case RUN_PI + 4: b = pi_run<3, 4>(b, count, xs, sel, P); break;
+      case RUN_PI + 5: b = pi_run<4, 4>(b, count, xs, sel, P); break;
+      default: b = generic_run(b, count, xs, sel, P, nb, plw); break;
+    }
+  }
+  plw[0] = P.Z;
+  plw[32] = P.A0;
+  plw[64] = P.A1;
+  plw[96] = P.A2;
 #pragma unroll
   for (int i = 0; i < 5; ++i)
-    if ((uint32_t)i < nb) plw[(4 + i) * 32] = Bp[i];
+    if ((uint32_t)i < nb) plw[(4 + i) * 32] = P.Bp[i];
 }
 
 template <bool HAS_EXACT>
@@ -297,6 +363,7 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
   // re-deriving them from threadIdx inside the block loop (it did, ten instructions per block)
   uint32_t xoff = prm.smem_xt_off + grp * prm.rows * 32 + lane;
   uint32_t ploff = prm.smem_pl_off + grp * (SPLIT * kPlaneRows * 32) + lane;
+  const uint4 sel = prm.sel;
   asm volatile("" : "+r"(xoff), "+r"(ploff));
   uint32_t* xcol = smem + xoff;
   uint32_t* plg = smem + ploff;
@@ -374,7 +441,7 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
           const int n_g = (int)row[K_GRAPHS];
           if (gactive) {
             for (int w0 = 0; w0 < n_g; w0 += SPLIT) {
-              if (w0 + w < n_g) sliced_phase1(cbase, cbase[w0 + w], xcol, plg + w * (kPlaneRows * 32));
+              if (w0 + w < n_g) sliced_phase1(cbase, cbase[w0 + w], xcol, plg + w * (kPlaneRows * 32), sel);
               group_sync(grp, SPLIT * 32);
               const int nj = min(SPLIT, n_g - w0);
               for (int j = 0; j < nj; ++j)

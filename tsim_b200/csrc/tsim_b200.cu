@@ -970,7 +970,7 @@ static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long 
     k.n_groups = (n_slabs + 31) / 32; k.ng = pl.ng; k.rounds = pl.rounds;
     k.n_stages = pl.n_stages; k.stage_words = p->s_stage_words;
     k.smem_xt_off = pl.xt_off; k.smem_pl_off = pl.pl_off; k.smem_prev_off = pl.prev_off; k.smem_data_off = pl.data_off;
-    k.rows = p->s_rows;
+    k.rows = p->s_rows; k.sel = make_uint4(0x80u, 0x8000u, 0x800000u, 0x80000000u);
     sliced_fn(pl.split, p->s_has_exact)<<<pl.grid, pl.ng * pl.split * 32, pl.smem_bytes, st>>>(k);
     CU(cudaGetLastError());
   }

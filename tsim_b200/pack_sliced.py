@@ -97,25 +97,81 @@ def pair_factor(alpha: int, beta: int):
 
 
 OP_FIRST, OP_LIN, OP_PI, OP_PAIRGEN, OP_PAIRMON = 0, 1, 2, 3, 4
-ROW_STRIDE_BYTES = 128  # a row of a group's transposed parameter matrix: 32 lanes x 4 bytes
-BLOCK_ROWS = (6, 10, 14)  # rows of the three straight-line block classes
+CLASS_WORDS = (2, 3, 4)  # index words (four 8-bit row indices each) of the three straight-line parity classes
+RUN_LIN = 0  # + class (0..2)
+RUN_PI = 3  # + index of (class1, class2), class1 <= class2, in PI_CLASSES
+RUN_GENERIC = 15
+PI_CLASSES = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]
+
+
+def _index_words(rows, n_words: int, zero_row: int) -> list[int]:
+    """Row indices four per word (the kernel turns byte k into an address with one dp4a), padded with the zero row."""
+    r = list(rows) + [zero_row] * (4 * n_words - len(rows))
+    return [r[i] | (r[i + 1] << 8) | (r[i + 2] << 16) | (r[i + 3] << 24) for i in range(0, 4 * n_words, 4)]
+
+
+def _row_class(rows) -> int:
+    for cls, nw in enumerate(CLASS_WORDS):
+        if len(rows) <= 4 * nw:
+            return cls
+    return 3
 
 
 def _block(op: int, params: int, rows: list[int], zero_row: int) -> list[int]:
-    """One parity block: header word ``cls | op << 2 | params << 5`` followed by 16-bit row offsets (row * 128 bytes),
-    two per word.  Classes 0-2 hold 6 / 10 / 14 rows (padded with the all-zero row: the kernel loads them with
-    straight-line code); class 3 is ``[hdr, n_words, offsets...]`` for heavier masks.  Blocks are 8-byte aligned."""
-    if params >> 27:
+    """Generic parity block: ``[op | params << 3, n_words, index words...]`` padded to an even number of words."""
+    if params >> 29:
         raise _Unsupported("block parameters do not fit")
-    offs = [r * ROW_STRIDE_BYTES for r in rows]
-    zo = zero_row * ROW_STRIDE_BYTES
-    for cls, cap in enumerate(BLOCK_ROWS):
-        if len(offs) <= cap:
-            offs = offs + [zo] * (cap - len(offs))
-            return [cls | (op << 2) | (params << 5)] + [offs[i] | (offs[i + 1] << 16) for i in range(0, cap, 2)]
-    offs = offs + [zo] * ((-len(offs)) % 4)  # an even number of offset words keeps the next block 8-byte aligned
-    words = [offs[i] | (offs[i + 1] << 16) for i in range(0, len(offs), 2)]
-    return [3 | (op << 2) | (params << 5), len(words)] + words
+    n = max(1, (len(rows) + 3) // 4)
+    n += n % 2
+    return [op | (params << 3), n] + _index_words(rows, n, zero_row)
+
+
+def _emit_runs(terms, zero_row: int) -> list[int]:
+    """The term stream of a graph as typed runs: ``[kind | count << 16, 0, 0, 0]`` followed by ``count`` items of one
+    shape, so that the kernel dispatches once per run and then loops over straight-line code.  The order of a graph's
+    terms is irrelevant (their plane updates commute).  Runs and items are 16-byte aligned.
+
+        LIN + cls        item = [params, index words...]: 4 words for classes 0 / 1 (<= 8 / 12 rows), 8 for class 2 (<= 16)
+        PI + pair index  item = [4 index words of the lighter parity, 4 of the heavier]; the class says how many are used
+        GENERIC          count = words; items are ``_block`` streams (two-parity ops as a FIRST block + op block)
+    """
+    runs: dict[int, list[int]] = {}
+    counts: dict[int, int] = {}
+    zw = zero_row * 0x01010101
+    for t in terms:
+        if t[0] == "lin":
+            _, params, rows = t
+            cls = _row_class(rows)
+            if cls < 3:
+                kind = RUN_LIN + cls
+                iw = _index_words(rows, CLASS_WORDS[cls], zero_row)
+                item = [params] + iw + [zw] * (3 - len(iw)) if cls < 2 else [params] + iw + [zw] * 3
+                runs.setdefault(kind, []).extend(item)
+                counts[kind] = counts.get(kind, 0) + 1
+                continue
+            words = _block(OP_LIN, params, rows, zero_row)
+        else:
+            _, op, params, r1, r2 = t
+            c1, c2 = _row_class(r1), _row_class(r2)
+            if op == OP_PI and c1 < 3 and c2 < 3:
+                if c1 > c2:
+                    r1, r2, c1, c2 = r2, r1, c2, c1
+                kind = RUN_PI + PI_CLASSES.index((c1, c2))
+                runs.setdefault(kind, []).extend(_index_words(r1, 4, zero_row) + _index_words(r2, 4, zero_row))
+                counts[kind] = counts.get(kind, 0) + 1
+                continue
+            words = _block(OP_FIRST, 0, r1, zero_row) + _block(op, params, r2, zero_row)
+        runs.setdefault(RUN_GENERIC, []).extend(words)
+        counts[RUN_GENERIC] = len(runs[RUN_GENERIC])
+    body: list[int] = []
+    for kind in sorted(runs):
+        if counts[kind] > 0xFFFF:
+            raise _Unsupported("too many terms")
+        if kind == RUN_GENERIC:
+            runs[kind] += [0] * ((-len(runs[kind])) % 4)
+            counts[kind] = len(runs[kind])
+        body += [kind | (counts[kind] << 16), 0, 0, 0] + runs[kind]
+    return body
 
 
 class _Unsupported(ValueError):
@@ -128,8 +184,8 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
     n, h, p, q, pre = lv.node_phases, lv.halfpi_phases, lv.pi_products, lv.phase_pairs, lv.prefactor
     A, H, C, D = n.phases.shape[1], h.coeffs.shape[1], p.psi_const.shape[1], q.alpha.shape[1]
     approx = bool(pre.has_approximate_floatfactors)
-    if zero_row * ROW_STRIDE_BYTES > 0xFFFF:
-        raise _Unsupported("more than 510 parameters per level")
+    if zero_row > 255:
+        raise _Unsupported("more than 254 parameters per level")
 
     def rows_of(mask, const=0):
         r = [int(i) for i in np.flatnonzero(mask)]
@@ -147,10 +203,10 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
         always_zero = False
 
         def lin(rows, da=0, bmode=0, zmode=0):
-            terms.append(_block(OP_LIN, (da & 7) | (bmode << 3) | (zmode << 5), rows, zero_row))
+            terms.append(("lin", (da & 7) | (bmode << 3) | (zmode << 5), rows))
 
         def two(op, params, r1, r2):
-            terms.append(_block(OP_FIRST, 0, r1, zero_row) + _block(op, params, r2, zero_row))
+            terms.append(("two", op, params, r1, r2))
 
         for j in range(min(int(n.counts[g]), A)):
             ph = int(n.phases[g, j]) & 7
@@ -264,15 +320,14 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
                 pa, pb = (combo >> (2 * e)) & 1, (combo >> (2 * e + 1)) & 1
                 ffv = _zw_mul(ffv, pair_factor(al ^ (4 * pa), be ^ (4 * pb)))
                 extra = sum(3 << (6 * v + 3) for v in range(3)) | ((0xF ^ (1 << (pa + 2 * pb))) << 18)
-                gates.append(_block(OP_FIRST, 0, r1, zero_row) + _block(OP_PAIRMON, extra, r2, zero_row))
+                gates.append(("two", OP_PAIRMON, extra, r1, r2))
             if excess and not any(ffv):
                 continue  # this combination contributes nothing
             k1 = _zw_mul(_zw_mul(UNIT[a_s], ONE_PLUS_W_POW[r]), ffv)
             k2 = _zw_mul(k1, SQRT2)
             if max(abs(v) for v in k1 + k2) >= 2**31:
                 raise _Unsupported("graph constants overflow int32")
-            all_terms = terms + gates
-            body = [w for t in all_terms for w in t]
+            body = _emit_runs(terms + gates, zero_row)
             if len(body) > 0xFFFF:
                 raise _Unsupported("too many terms")
             words = np.zeros(SLICED_HEADER_WORDS + len(body), dtype=np.uint32)

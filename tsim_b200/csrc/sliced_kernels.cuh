@@ -27,6 +27,7 @@ struct SParams {
   const uint32_t* __restrict__ blob;     // sliced blob
   const uint32_t* __restrict__ xt;       // [sum_c F_c][slab_cap]
   uint32_t* __restrict__ ot;             // [n_draws][slab_cap]
+  float* __restrict__ pv;                // [slab_cap][32]: chain-rule state |amplitude of the prefix| per shot
   const uint32_t* __restrict__ subkeys;  // [n_draws][2]
   long long B;
   long long shot_offset;
@@ -39,10 +40,10 @@ struct SParams {
   int stage_words;
   int smem_xt_off;  // word offsets inside dynamic shared memory
   int smem_pl_off;
-  int smem_prev_off;
   int smem_data_off;
   int rows;  // zero_row + 1
-  uint4 sel;  // dp4a byte selectors {128 << 0, 128 << 8, 128 << 16, 128 << 24} (see par4)
+  uint4 sel;    // dp4a byte selectors {128 << 0, 128 << 8, 128 << 16, 128 << 24} (see par4)
+  uint4 sel_e;  // the same with 8, the byte size of a float2 decode-table entry, instead of 128 (see sliced_phase2)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -302,29 +303,58 @@ struct SlicedAcc { typedef float2 type; };
 template <>
 struct SlicedAcc<true> { typedef uint4 type; };
 
-// phase 2: shots sh0 .. sh0 + SH - 1 of every slab: index = plane bits, contribution = decode-table entry
+// 8 x 8 bit transpose: in, byte k of (lo | hi << 32) = plane k (bit s = shot s); out, byte s = index of shot s (bit k)
+__device__ __forceinline__ void transpose8x8(uint32_t& lo, uint32_t& hi) {
+  uint32_t t;
+  t = (lo ^ (lo >> 7)) & 0x00AA00AAu; lo ^= t ^ (t << 7);
+  t = (hi ^ (hi >> 7)) & 0x00AA00AAu; hi ^= t ^ (t << 7);
+  t = (lo ^ (lo >> 14)) & 0x0000CCCCu; lo ^= t ^ (t << 14);
+  t = (hi ^ (hi >> 14)) & 0x0000CCCCu; hi ^= t ^ (t << 14);
+  t = (lo ^ (hi << 4)) & 0xF0F0F0F0u; lo ^= t; hi ^= t >> 4;
+}
+
+// phase 2: this warp's SH shots of every slab (warp w of the group: shots w * SH ...): the plane bits of a shot form
+// the index of its decode-table entry.  The first eight index planes are gathered with byte permutes and one 8 x 8
+// bit transpose, and a dp4a per shot scales the index byte into the entry's address; further planes are rare.
 template <int SH, bool HAS_EXACT>
-__device__ __forceinline__ void sliced_phase2(const uint32_t* __restrict__ cbase, uint32_t rec, const uint32_t* __restrict__ plj, int sh0,
-                                              bool approx, typename SlicedAcc<HAS_EXACT>::type (&acc)[SH]) {
+__device__ __forceinline__ void sliced_phase2(const uint32_t* __restrict__ cbase, uint32_t rec, const uint32_t* __restrict__ plj, int w,
+                                              bool approx, const uint4& sel_e, typename SlicedAcc<HAS_EXACT>::type (&acc)[SH]) {
+  static_assert(SH == 8 || SH == 4, "a warp handles a byte or a nibble of every plane word");
   const uint4 h0 = *reinterpret_cast<const uint4*>(cbase + rec);
   const int n_idx = (int)(h0.y & 0xFFu);
-  const uint32_t* __restrict__ tbl = cbase + h0.z;
-  constexpr uint32_t kField = SH == 32 ? 0xFFFFFFFFu : ((1u << SH) - 1u);
-  const uint32_t zb = plj[0] >> sh0;
-  uint32_t idx[SH];
+  const uint32_t tbl = smem_u32(cbase + h0.z);
+  constexpr uint32_t kField = (1u << SH) - 1u;
+  // entries are 8 bytes (float2) in approximate levels and 16 bytes (four coefficients) in exact ones
+  const uint32_t kEntryShift = (HAS_EXACT && !approx) ? 4u : 3u;
+  const int sh0 = w * SH;
+  const uint32_t bsel = (uint32_t)(SH == 8 ? w : (w >> 1));  // byte of the plane words that holds this warp's shots
+  uint32_t pb[8];
 #pragma unroll
-  for (int s = 0; s < SH; ++s) idx[s] = 0u;
-  for (int k = 0; k < n_idx; ++k) {
-    const uint32_t pk = ((plj[(1 + k) * 32] >> sh0) & kField) << k;
-    const uint32_t m = 1u << k;
+  for (int k = 0; k < 8; ++k) pb[k] = k < n_idx ? plj[(1 + k) * 32] : 0u;
+  const uint32_t ps = bsel | ((4u + bsel) << 4);
+  uint32_t lo = __byte_perm(__byte_perm(pb[0], pb[1], ps), __byte_perm(pb[2], pb[3], ps), 0x5410);
+  uint32_t hi = __byte_perm(__byte_perm(pb[4], pb[5], ps), __byte_perm(pb[6], pb[7], ps), 0x5410);
+  transpose8x8(lo, hi);
+  uint32_t base[SH];
 #pragma unroll
-    for (int s = 0; s < SH; ++s) idx[s] |= (pk >> s) & m;
+  for (int s = 0; s < SH; ++s) base[s] = tbl;
+  for (int k = 8; k < n_idx; ++k) {
+    const uint32_t pk = ((plj[(1 + k) * 32] >> sh0) & kField) << (k + kEntryShift);
+    const uint32_t m = 1u << (k + kEntryShift);
+#pragma unroll
+    for (int s = 0; s < SH; ++s) base[s] += (pk >> s) & m;
   }
+  const uint32_t zb = plj[0] >> sh0;
+  const uint32_t r0 = SH == 8 ? lo : ((w & 1) ? hi : lo), r1 = hi;
 #pragma unroll
   for (int s = 0; s < SH; ++s) {
     if ((zb >> s) & 1u) continue;
+    const uint32_t r = s < 4 ? r0 : r1;
+    uint32_t sl = (s & 3) == 0 ? sel_e.x : (s & 3) == 1 ? sel_e.y : (s & 3) == 2 ? sel_e.z : sel_e.w;
+    if (HAS_EXACT && !approx) sl <<= 1;
+    const uint32_t ea = __dp4a(r, sl, base[s]);
     if (approx) {
-      const float2 e = *reinterpret_cast<const float2*>(tbl + 2u * idx[s]);
+      const float2 e = *reinterpret_cast<const float2*>(__cvta_shared_to_generic(ea));
       if constexpr (HAS_EXACT) {
         acc[s].x = __float_as_uint(__fadd_rn(__uint_as_float(acc[s].x), e.x));
         acc[s].y = __float_as_uint(__fadd_rn(__uint_as_float(acc[s].y), e.y));
@@ -334,7 +364,7 @@ __device__ __forceinline__ void sliced_phase2(const uint32_t* __restrict__ cbase
       }
     } else {
       if constexpr (HAS_EXACT) {
-        const uint4 e = *reinterpret_cast<const uint4*>(tbl + 4u * idx[s]);
+        const uint4 e = *reinterpret_cast<const uint4*>(__cvta_shared_to_generic(ea));
         acc[s].x += e.x; acc[s].y += e.y; acc[s].z += e.z; acc[s].w += e.w;
       }
     }
@@ -348,8 +378,8 @@ __device__ __forceinline__ void group_sync(int grp, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(nthreads) : "memory");
 }
 
-// dynamic shared memory (32-bit words): [0,64) mbarriers | xt [ng][rows][32] | planes [ng][SPLIT][kPlaneRows][32] |
-// prev [ng][32 shots][32] | stage ring
+// dynamic shared memory (32-bit words): [0,64) mbarriers | xt [ng][rows][32] | planes [ng][2][SPLIT][kPlaneRows][32] |
+// stage ring
 template <int SPLIT, bool HAS_EXACT>
 __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_kernel(const SParams prm) {
   constexpr int SH = 32 / SPLIT;
@@ -362,12 +392,11 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
   // word offsets of this thread's columns; made opaque so that the compiler keeps them in registers instead of
   // re-deriving them from threadIdx inside the block loop (it did, ten instructions per block)
   uint32_t xoff = prm.smem_xt_off + grp * prm.rows * 32 + lane;
-  uint32_t ploff = prm.smem_pl_off + grp * (SPLIT * kPlaneRows * 32) + lane;
+  uint32_t ploff = prm.smem_pl_off + grp * (2 * SPLIT * kPlaneRows * 32) + lane;  // two plane buffers per group
   const uint4 sel = prm.sel;
   asm volatile("" : "+r"(xoff), "+r"(ploff));
   uint32_t* xcol = smem + xoff;
   uint32_t* plg = smem + ploff;
-  float* pcol = reinterpret_cast<float*>(smem + prm.smem_prev_off) + grp * (32 * 32) + lane;
   uint32_t* sdata = smem + prm.smem_data_off;
 
   const int n_comp = (int)blob[H_N_COMP], n_chunks = (int)blob[H_N_CHUNKS];
@@ -397,6 +426,7 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
     for (long long q = 0; q < prm.n_stages && q < total_q; ++q) issue(q);
 
   long long q = 0;
+  uint32_t pbuf = 0;  // plane buffer of the current wave (double-buffered: one group barrier per wave)
   for (int round = 0; round < prm.rounds; ++round) {
     const int ggrp = (round * prm.ng + grp) * (int)gridDim.x + (int)blockIdx.x;
     const bool gactive = ggrp < prm.n_groups;  // uniform over the group's warps
@@ -441,12 +471,15 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
           const int n_g = (int)row[K_GRAPHS];
           if (gactive) {
             for (int w0 = 0; w0 < n_g; w0 += SPLIT) {
-              if (w0 + w < n_g) sliced_phase1(cbase, cbase[w0 + w], xcol, plg + w * (kPlaneRows * 32), sel);
+              // A warp may write the other buffer for the next wave as soon as it is through with this one: everybody
+              // passed this wave's barrier, hence finished reading that buffer in the wave before.
+              uint32_t* pw = plg + pbuf * (SPLIT * kPlaneRows * 32);
+              if (w0 + w < n_g) sliced_phase1(cbase, cbase[w0 + w], xcol, pw + w * (kPlaneRows * 32), sel);
               group_sync(grp, SPLIT * 32);
               const int nj = min(SPLIT, n_g - w0);
               for (int j = 0; j < nj; ++j)
-                sliced_phase2<SH, HAS_EXACT>(cbase, cbase[w0 + j], plg + j * (kPlaneRows * 32), w * SH, approx, acc);
-              group_sync(grp, SPLIT * 32);
+                sliced_phase2<SH, HAS_EXACT>(cbase, cbase[w0 + j], pw + j * (kPlaneRows * 32), w, approx, prm.sel_e, acc);
+              pbuf ^= 1u;
             }
           }
           __syncthreads();  // every group is done with this stage
@@ -461,6 +494,15 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
           if (k > 0) {
             k0 = prm.subkeys[2 * (draw0 + k - 1)];
             k1 = prm.subkeys[2 * (draw0 + k - 1) + 1];
+          }
+          // chain-rule state of this warp's shots lives in global memory between levels (L2-resident, 32 B per lane)
+          float4* pvp = reinterpret_cast<float4*>(prm.pv + (size_t)slab * 32 + w * SH);
+          float pvv[SH];
+#pragma unroll
+          for (int s = 0; s < SH; s += 4) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k > 0 && active) t = pvp[s >> 2];
+            pvv[s] = t.x; pvv[s + 1] = t.y; pvv[s + 2] = t.z; pvv[s + 3] = t.w;
           }
           uint32_t bits = 0;
 #pragma unroll
@@ -479,16 +521,19 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
             }
             if (empty) { re = 0.0f; im = 0.0f; }
             const float p1 = complex_abs(re, im);
-            float* pp = pcol + (w * SH + s) * 32;
             if (k == 0) {
-              *pp = p1;
+              pvv[s] = p1;
             } else {
-              const float pv = *pp;
+              const float pv = pvv[s];
               const float u = uniform_f32(k0, k1, shot0 + (unsigned long long)s);
               const bool bit = u < __fdiv_rn(p1, pv);
-              *pp = bit ? p1 : __fsub_rn(pv, p1);
+              pvv[s] = bit ? p1 : __fsub_rn(pv, p1);
               bits |= (bit ? 1u : 0u) << s;
             }
+          }
+          if (active && k < n_c) {
+#pragma unroll
+            for (int s = 0; s < SH; s += 4) pvp[s >> 2] = make_float4(pvv[s], pvv[s + 1], pvv[s + 2], pvv[s + 3]);
           }
           if (k > 0) {
             constexpr uint32_t kField = SH == 32 ? 0xFFFFFFFFu : ((1u << SH) - 1u);

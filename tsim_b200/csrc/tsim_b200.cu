@@ -605,9 +605,9 @@ static SlicedFn sliced_fn(int split, int has_exact) {
 // Shared-memory plan of one sliced launch: `ng` groups of `split` warps (sliced_kernels.cuh).
 struct SlicedPlan {
   int split = 0, ng = 0, rounds = 0, grid = 0, n_stages = 0;
-  int xt_off = 0, pl_off = 0, prev_off = 0, data_off = 0, smem_bytes = 0;
+  int xt_off = 0, pl_off = 0, data_off = 0, smem_bytes = 0;
 };
-static int sliced_group_words(int rows, int split) { return rows * 32 + split * kPlaneRows * 32 + 32 * 32; }
+static int sliced_group_words(int rows, int split) { return rows * 32 + 2 * split * kPlaneRows * 32; }  // matrix + two plane buffers
 // largest number of groups (<= cap) that leaves room for `want_stages` stages; 0 if not even one group fits
 static int sliced_fit_groups(int rows, int split, int cap, int stage_words, int want_stages, int smem_limit) {
   for (int ng = cap; ng >= 1; --ng)
@@ -940,8 +940,7 @@ static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl) {
   pl.ng = (gpc + pl.rounds - 1) / pl.rounds;
   pl.xt_off = kBarWords;
   pl.pl_off = pl.xt_off + pl.ng * p->s_rows * 32;
-  pl.prev_off = pl.pl_off + pl.ng * split * kPlaneRows * 32;
-  pl.data_off = pl.prev_off + pl.ng * 32 * 32;
+  pl.data_off = pl.pl_off + pl.ng * 2 * split * kPlaneRows * 32;
   const long long room = (long long)p->s_smem_limit / 4 - pl.data_off;
   pl.n_stages = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kMaxStages, std::max(1, n_chunks)), room / p->s_stage_words));
   pl.smem_bytes = (pl.data_off + pl.n_stages * p->s_stage_words) * 4;
@@ -966,11 +965,13 @@ static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long 
     if (!sliced_plan(p, n_slabs, pl)) return fail(TSB_ERR_UNSUPPORTED, "internal: no sliced launch plan fits in shared memory");
     SParams k;
     k.blob = p->d_blob; k.xt = d_xt; k.ot = d_ot; k.subkeys = d_subkeys; k.B = B; k.shot_offset = shot_offset;
+    k.pv = reinterpret_cast<float*>(d_ot + (((size_t)slab_cap * std::max(1, in.n_draws) + 3) & ~(size_t)3));  // 16-byte aligned
     k.n_slabs = n_slabs; k.slab_cap = (int)slab_cap;
     k.n_groups = (n_slabs + 31) / 32; k.ng = pl.ng; k.rounds = pl.rounds;
     k.n_stages = pl.n_stages; k.stage_words = p->s_stage_words;
-    k.smem_xt_off = pl.xt_off; k.smem_pl_off = pl.pl_off; k.smem_prev_off = pl.prev_off; k.smem_data_off = pl.data_off;
+    k.smem_xt_off = pl.xt_off; k.smem_pl_off = pl.pl_off; k.smem_data_off = pl.data_off;
     k.rows = p->s_rows; k.sel = make_uint4(0x80u, 0x8000u, 0x800000u, 0x80000000u);
+    k.sel_e = make_uint4(8u, 8u << 8, 8u << 16, 8u << 24);
     sliced_fn(pl.split, p->s_has_exact)<<<pl.grid, pl.ng * pl.split * 32, pl.smem_bytes, st>>>(k);
     CU(cudaGetLastError());
   }
@@ -1024,7 +1025,7 @@ int tsb_sample_device(tsb_program* p, const uint64_t* d_f, int64_t B, int64_t sh
       if (p->d_ot) cudaFree(p->d_ot);
       p->d_xt = nullptr; p->d_ot = nullptr; p->scratch_slabs = 0;
       CU(cudaMalloc(&p->d_xt, 4 * (size_t)slabs * std::max(1, p->total_F)));
-      CU(cudaMalloc(&p->d_ot, 4 * (size_t)slabs * std::max(1, p->info.n_draws)));
+      CU(cudaMalloc(&p->d_ot, 4 * ((size_t)slabs * (std::max(1, p->info.n_draws) + 32) + 4)));  // + per-shot chain-rule state
       p->scratch_slabs = slabs;
     }
     // the stream only waits for the (overlapped) norm check when the caller wants the deviations in its own buffer
@@ -1090,7 +1091,7 @@ static int ensure_slot(tsb_program* p, Slot& s, long long cap) {
   if (p->is_sliced) {
     const size_t slabs = (size_t)((cap + 31) / 32);
     CU(cudaMalloc(&s.d_xt, 4 * slabs * (size_t)std::max(1, p->total_F)));
-    CU(cudaMalloc(&s.d_ot, 4 * slabs * (size_t)std::max(1, in.n_draws)));
+    CU(cudaMalloc(&s.d_ot, 4 * (slabs * (size_t)(std::max(1, in.n_draws) + 32) + 4)));  // + per-shot chain-rule state
   }
   s.cap = cap;
   return TSB_OK;

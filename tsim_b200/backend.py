@@ -116,7 +116,7 @@ class DeviceProgram:
             if self.program is None:
                 raise ValueError("a sliced program needs the CompiledProgram to build its per-row companion")
             # companion per-row program: normalisation check of shot 0, evaluate(), pattern cache
-            self._aux = DeviceProgram(self.program, device=device, mode="auto" if mode == "sliced" else "faithful")
+            self._aux = DeviceProgram(self.program, device=device, mode="rowwise")
             _lib.check(lib.tsb_program_set_aux(self._h, self._aux._h))
         info = _lib.TsbInfo()
         _lib.check(lib.tsb_program_info(self._h, C.byref(info)))
@@ -140,19 +140,29 @@ class DeviceProgram:
     def set_pattern_cache(self, max_weight: int | None, max_entries: int = 0) -> int:
         """Tabulate the probability trees of all selected-f patterns of weight <= ``max_weight`` (0, 1, 2;
         ``None`` switches the cache off).  Purely a speed-up: sampled bits do not change.  Returns the table size."""
-        if self._aux is not None and max_weight is not None:
-            raise NotImplementedError("tsim_b200: the pattern cache works with per-row programs (mode='fast' or 'faithful')")
+        if self._aux is not None:
+            # the table walk belongs to the per-row kernels: while the cache is on, a sliced program samples through
+            # its per-row companion (same bits either way)
+            n = self._aux.set_pattern_cache(max_weight, max_entries)
+            self.pattern_cache = max_weight
+            return n
         n = C.c_int64(0)
         _lib.check(self._lib.tsb_program_set_pattern_cache(self._h, -1 if max_weight is None else int(max_weight), int(max_entries), C.byref(n)))
         self.pattern_cache = max_weight
         return int(n.value)
+
+    def _active(self):
+        """Handle that samples: the program itself, or its per-row companion while the pattern cache is on."""
+        if self._aux is not None and self.pattern_cache is not None:
+            return self._aux._h
+        return self._h
 
     def close(self) -> None:
         self._fin()
 
     def last_kernel_ms(self) -> tuple[float, int]:
         n = C.c_int(0)
-        ms = self._lib.tsb_last_kernel_ms(self._h, C.byref(n))
+        ms = self._lib.tsb_last_kernel_ms(self._active(), C.byref(n))
         return float(ms), int(n.value)
 
     # ---------------------------------------------------------------------------------------
@@ -192,7 +202,7 @@ class DeviceProgram:
         dev = np.zeros(max(1, self.info["n_components"]), dtype=np.float32)
         _lib.check(
             self._lib.tsb_sample_host(
-                self._h,
+                self._active(),
                 f.ctypes.data_as(C.c_void_p),
                 fmt,
                 B,
@@ -228,7 +238,7 @@ class DeviceProgram:
         dev = np.zeros(max(1, self.info["n_components"]), dtype=np.float32)
         _lib.check(
             self._lib.tsb_sample_noisy_host(
-                self._h, noise._h, B, int(shot_offset), k0, k1, int(noise.seed), int(call), int(skip_shot0),
+                self._active(), noise._h, B, int(shot_offset), k0, k1, int(noise.seed), int(call), int(skip_shot0),
                 out.ctypes.data_as(C.c_void_p), ofmt, dev.ctypes.data_as(C.c_void_p),
                 f_out.ctypes.data_as(C.c_void_p) if return_f else None,
             )
@@ -241,7 +251,7 @@ class DeviceProgram:
         k0, k1 = key_words(key)
         _lib.check(
             self._lib.tsb_sample_device(
-                self._h, C.c_void_p(d_f), int(B), int(shot_offset), k0, k1, C.c_void_p(d_out),
+                self._active(), C.c_void_p(d_f), int(B), int(shot_offset), k0, k1, C.c_void_p(d_out),
                 C.c_void_p(d_norm_dev) if d_norm_dev else None, C.c_void_p(stream) if stream else None,
             )
         )

@@ -37,6 +37,7 @@ VERSION = 5
 MODE_FAITHFUL = 0
 MODE_FAST = 1
 MODE_SLICED = 2
+SLICED_AUTO_MAX_BYTES = 4 << 20  # mode="auto" keeps the per-row records beyond this size of the sliced data region
 
 HEADER_WORDS = 32
 COMP_WORDS = 8
@@ -215,13 +216,23 @@ def pack_program(
     max_chunk_words: int = 8192,
     joint: bool = False,
 ) -> PackedProgram:
-    """Build the device blob.  ``mode``: "faithful", "fast" or "auto" (fast when provably exact).
+    """Build the device blob.  ``mode``: "faithful", "fast", "sliced", "rowwise" (fast when provably exact, else
+    faithful) or "auto" (sliced when provably exact and compact, else as "rowwise").
 
     ``joint=True`` accepts the two-level programs of ``CompiledStateProbs`` (``mode="joint"`` in
     ``compile_program``: level 1 plugs all outputs at once); such a blob can only be *evaluated*.
     """
     exact_ok, bound_info = reorder_is_exact(program)
-    if mode == "auto":
+    if mode == "auto" and exact_ok and not joint:
+        # fastest first: the bit-sliced records, unless their decode tables blow up (graphs with many general phase
+        # pairs) -- every CTA streams the whole data region once per batch
+        try:
+            pp = pack_program(program, mode="sliced", max_chunk_words=max_chunk_words)
+            if pp.stats["data_bytes"] <= SLICED_AUTO_MAX_BYTES:
+                return pp
+        except ValueError:
+            pass
+    if mode in ("auto", "rowwise"):
         if exact_ok:
             try:
                 return pack_program(program, mode="fast", max_chunk_words=max_chunk_words, joint=joint)

@@ -363,7 +363,7 @@ class _CompiledSamplerBase:
             f"{s['max_outputs_per_component']} outputs for largest cc, ≤ {s['max_params']} parameters, "
             f"{s['A_terms']} A terms, {s['B_terms']} B terms, {s['C_terms']} C terms, {s['D_terms']} D terms, "
             f"{info['data_bytes']} B packed on cuda:{self._device_program.device}, "
-            f"{'resident' if info['resident'] else 'streamed'}, mode={'fast' if info['mode'] else 'faithful'})"
+            f"{'resident' if info['resident'] else 'streamed'}, mode={('faithful', 'fast', 'sliced')[info['mode']]})"
         )
 
 

@@ -86,6 +86,25 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
                 elif zm == 2:
                     Z |= ~p & full
 
+            def pair_op(op, prm, pa, pb):
+                nonlocal Z
+                if op == 3:
+                    gen[prm & 15] = (pa, pb)
+                    return
+                assert op == 4
+                ex = prm
+                for v, wd in enumerate((pa, pb, pa & pb)):
+                    add_a((ex >> (6 * v)) & 7, wd)
+                    db = ((ex >> (6 * v + 3)) & 7) - 3
+                    for _ in range(abs(db)):
+                        add_cnt(wd if db > 0 else (~wd & full))
+                ztt = (ex >> 18) & 15
+                for combo in range(4):
+                    if (ztt >> combo) & 1:
+                        wa = pa if combo & 1 else ~pa & full
+                        wb = pb if combo & 2 else ~pb & full
+                        Z |= wa & wb
+
             def par_words(o, n):
                 p = 0
                 for w in data[o : o + n]:
@@ -97,11 +116,21 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
             while o < end:
                 kind, count = int(data[o]) & 0xFFFF, int(data[o]) >> 16
                 o += 4
-                if kind < 3:  # LIN runs
-                    nw = CLASS_WORDS[kind]
+                if kind < 3 or 9 <= kind < 12:  # LIN / LIN2 runs
+                    cls = kind % 3
+                    nw = CLASS_WORDS[cls]
                     for _i in range(count):
+                        if kind >= 9:
+                            assert int(data[o]) == 2
                         lin_op(int(data[o]), par_words(o + 1, nw))
-                        o += 4 if kind < 2 else 8
+                        o += 4 if cls < 2 else 8
+                    continue
+                if 12 <= kind < 15:  # PAIR runs
+                    nw = CLASS_WORDS[kind - 12]
+                    for _i in range(count):
+                        hdr = int(data[o])
+                        pair_op(hdr & 7, hdr >> 3, par_words(o + 4, nw), par_words(o + 8, nw))
+                        o += 12
                     continue
                 if kind < 9:  # PI runs
                     c1, c2 = PI_CLASSES[kind - 3]
@@ -124,22 +153,8 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
                         lin_op(prm, p)
                     elif op == 2:
                         A[2] ^= q & p
-                    elif op == 3:
-                        gen[prm & 15] = (q, p)
                     else:
-                        ex = prm
-                        pa, pb = q, p
-                        for v, wd in enumerate((pa, pb, pa & pb)):
-                            add_a((ex >> (6 * v)) & 7, wd)
-                            db = ((ex >> (6 * v + 3)) & 7) - 3
-                            for _ in range(abs(db)):
-                                add_cnt(wd if db > 0 else (~wd & full))
-                        ztt = (ex >> 18) & 15
-                        for combo in range(4):
-                            if (ztt >> combo) & 1:
-                                wa = pa if combo & 1 else ~pa & full
-                                wb = pb if combo & 2 else ~pb & full
-                                Z |= wa & wb
+                        pair_op(op, prm, q, p)
                 assert o == gend
             assert o == end
             for s in range(N):

@@ -175,7 +175,7 @@ __device__ __forceinline__ void ld_words(const uint32_t* __restrict__ b, uint32_
 }
 
 enum SlicedOp { OP_FIRST = 0, OP_LIN = 1, OP_PI = 2, OP_PAIRGEN = 3, OP_PAIRMON = 4 };
-enum SlicedRun { RUN_LIN = 0, RUN_PI = 3, RUN_GENERIC = 15 };
+enum SlicedRun { RUN_LIN = 0, RUN_PI = 3, RUN_LIN2 = 9, RUN_PAIR = 12, RUN_GENERIC = 15 };
 
 struct Planes {
   uint32_t A0, A1, A2, Z;
@@ -214,6 +214,59 @@ __device__ __forceinline__ const uint32_t* pi_run(const uint32_t* __restrict__ b
   return b;
 }
 
+// two-parity ops of the phase-pair family
+__device__ __forceinline__ void pair_op(Planes& P, uint32_t op, uint32_t prm, uint32_t q, uint32_t p, uint32_t nb, uint32_t* __restrict__ plw) {
+  if (op == OP_PAIRGEN) {
+    const uint32_t r0 = 4u + nb + 2u * (prm & 15u);
+    plw[r0 * 32u] = q;
+    plw[(r0 + 1u) * 32u] = p;
+    return;
+  }
+  const uint32_t wd[3] = {q, p, q & p};
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    add_a3(P.A0, P.A1, P.A2, (prm >> (6 * v)) & 7u, wd[v]);
+    const int db = (int)((prm >> (6 * v + 3)) & 7u) - 3;
+    const uint32_t w = db > 0 ? wd[v] : ~wd[v];
+    for (int r = 0; r < (db < 0 ? -db : db); ++r) add_cnt5(P.Bp, w);
+  }
+  const uint32_t ztt = (prm >> 18) & 15u;
+  if (ztt & 1u) P.Z |= ~q & ~p;
+  if (ztt & 2u) P.Z |= q & ~p;
+  if (ztt & 4u) P.Z |= ~q & p;
+  if (ztt & 8u) P.Z |= q & p;
+}
+
+// LIN2 run: a += 2 p and nothing else
+template <int NW>
+__device__ __forceinline__ const uint32_t* lin2_run(const uint32_t* __restrict__ b, uint32_t count, uint32_t xs, const uint4& sel, Planes& P) {
+  constexpr int IW = NW <= 3 ? 4 : 8;
+#pragma unroll 1
+  for (uint32_t i = 0; i < count; ++i, b += IW) {
+    uint32_t w[IW];
+    ld_words<IW>(b, w);
+    const uint32_t p = par_words<NW>(xs, w + 1, sel);
+    P.A2 ^= P.A1 & p;
+    P.A1 ^= p;
+  }
+  return b;
+}
+
+// PAIR run: item = [op | params << 3, -, -, -, 4 index words, 4 index words], NW of each used
+template <int NW>
+__device__ __forceinline__ const uint32_t* pair_run(const uint32_t* __restrict__ b, uint32_t count, uint32_t xs, const uint4& sel, Planes& P,
+                                                     uint32_t nb, uint32_t* __restrict__ plw) {
+#pragma unroll 1
+  for (uint32_t i = 0; i < count; ++i, b += 12) {
+    const uint32_t hdr = *b;
+    uint32_t w[8];
+    ld_words<8>(b + 4, w);
+    const uint32_t q = par_words<NW>(xs, w, sel), p = par_words<NW>(xs, w + 4, sel);
+    pair_op(P, hdr & 7u, hdr >> 3, q, p, nb, plw);
+  }
+  return b;
+}
+
 // generic run: a stream of parity blocks (pack_sliced.py::_block) with a per-block dispatch
 __device__ __forceinline__ const uint32_t* generic_run(const uint32_t* __restrict__ b, uint32_t words, uint32_t xs, const uint4& sel, Planes& P,
                                                         uint32_t nb, uint32_t* __restrict__ plw) {
@@ -235,24 +288,8 @@ __device__ __forceinline__ const uint32_t* generic_run(const uint32_t* __restric
       P.A2 ^= q & p;
     } else if (op == OP_LIN) {
       lin_op(P, prm, p);
-    } else if (op == OP_PAIRGEN) {
-      const uint32_t r0 = 4u + nb + 2u * (prm & 15u);
-      plw[r0 * 32u] = q;
-      plw[(r0 + 1u) * 32u] = p;
     } else {
-      const uint32_t wd[3] = {q, p, q & p};
-#pragma unroll
-      for (int v = 0; v < 3; ++v) {
-        add_a3(P.A0, P.A1, P.A2, (prm >> (6 * v)) & 7u, wd[v]);
-        const int db = (int)((prm >> (6 * v + 3)) & 7u) - 3;
-        const uint32_t w = db > 0 ? wd[v] : ~wd[v];
-        for (int r = 0; r < (db < 0 ? -db : db); ++r) add_cnt5(P.Bp, w);
-      }
-      const uint32_t ztt = (prm >> 18) & 15u;
-      if (ztt & 1u) P.Z |= ~q & ~p;
-      if (ztt & 2u) P.Z |= q & ~p;
-      if (ztt & 4u) P.Z |= ~q & p;
-      if (ztt & 8u) P.Z |= q & p;
+      pair_op(P, op, prm, q, p, nb, plw);
     }
   }
   return b;
@@ -286,6 +323,12 @@ __device__ __forceinline__ void sliced_phase1(const uint32_t* __restrict__ cbase
       case RUN_PI + 3: b = pi_run<3, 3>(b, count, xs, sel, P); break;
       case RUN_PI + 4: b = pi_run<3, 4>(b, count, xs, sel, P); break;
       case RUN_PI + 5: b = pi_run<4, 4>(b, count, xs, sel, P); break;
+      case RUN_LIN2 + 0: b = lin2_run<2>(b, count, xs, sel, P); break;
+      case RUN_LIN2 + 1: b = lin2_run<3>(b, count, xs, sel, P); break;
+      case RUN_LIN2 + 2: b = lin2_run<4>(b, count, xs, sel, P); break;
+      case RUN_PAIR + 0: b = pair_run<2>(b, count, xs, sel, P, nb, plw); break;
+      case RUN_PAIR + 1: b = pair_run<3>(b, count, xs, sel, P, nb, plw); break;
+      case RUN_PAIR + 2: b = pair_run<4>(b, count, xs, sel, P, nb, plw); break;
       default: b = generic_run(b, count, xs, sel, P, nb, plw); break;
     }
   }

@@ -100,6 +100,8 @@ OP_FIRST, OP_LIN, OP_PI, OP_PAIRGEN, OP_PAIRMON = 0, 1, 2, 3, 4
 CLASS_WORDS = (2, 3, 4)  # index words (four 8-bit row indices each) of the three straight-line parity classes
 RUN_LIN = 0  # + class (0..2)
 RUN_PI = 3  # + index of (class1, class2), class1 <= class2, in PI_CLASSES
+RUN_LIN2 = 9  # + class: linear terms that only add 2 to ``a`` (the half-pi family after merging)
+RUN_PAIR = 12  # + max(class1, class2): PAIRGEN / PAIRMON items
 RUN_GENERIC = 15
 PI_CLASSES = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]
 
@@ -132,6 +134,9 @@ def _emit_runs(terms, zero_row: int) -> list[int]:
     terms is irrelevant (their plane updates commute).  Runs and items are 16-byte aligned.
 
         LIN + cls        item = [params, index words...]: 4 words for classes 0 / 1 (<= 8 / 12 rows), 8 for class 2 (<= 16)
+        LIN2 + cls       the same for params == 2 (a += 2 p and nothing else): the kernel skips the generic update
+        PAIR + cls       item = [op | params << 3, 0, 0, 0, 4 index words of the first parity, 4 of the second];
+                         cls = the heavier class, used for both
         PI + pair index  item = [4 index words of the lighter parity, 4 of the heavier]; the class says how many are used
         GENERIC          count = words; items are ``_block`` streams (two-parity ops as a FIRST block + op block)
     """
@@ -143,7 +148,7 @@ def _emit_runs(terms, zero_row: int) -> list[int]:
             _, params, rows = t
             cls = _row_class(rows)
             if cls < 3:
-                kind = RUN_LIN + cls
+                kind = (RUN_LIN2 if params == 2 else RUN_LIN) + cls
                 iw = _index_words(rows, CLASS_WORDS[cls], zero_row)
                 item = [params] + iw + [zw] * (3 - len(iw)) if cls < 2 else [params] + iw + [zw] * 3
                 runs.setdefault(kind, []).extend(item)
@@ -158,6 +163,11 @@ def _emit_runs(terms, zero_row: int) -> list[int]:
                     r1, r2, c1, c2 = r2, r1, c2, c1
                 kind = RUN_PI + PI_CLASSES.index((c1, c2))
                 runs.setdefault(kind, []).extend(_index_words(r1, 4, zero_row) + _index_words(r2, 4, zero_row))
+                counts[kind] = counts.get(kind, 0) + 1
+                continue
+            if op in (OP_PAIRGEN, OP_PAIRMON) and c1 < 3 and c2 < 3:
+                kind = RUN_PAIR + max(c1, c2)
+                runs.setdefault(kind, []).extend([op | (params << 3), 0, 0, 0] + _index_words(r1, 4, zero_row) + _index_words(r2, 4, zero_row))
                 counts[kind] = counts.get(kind, 0) + 1
                 continue
             words = _block(OP_FIRST, 0, r1, zero_row) + _block(op, params, r2, zero_row)
@@ -202,8 +212,16 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
         terms: list[list[int]] = []
         always_zero = False
 
+        # Everything that flips the top bit of ``a`` linearly in a parity (da & 4 of a linear term, the cross terms of
+        # the pi family's constants) is XOR-linear in the parameters: the masks are merged into one term per graph.
+        m4: set[int] = set()
+
         def lin(rows, da=0, bmode=0, zmode=0):
-            terms.append(("lin", (da & 7) | (bmode << 3) | (zmode << 5), rows))
+            if da & 4:
+                m4.symmetric_difference_update(rows)
+                da &= 3
+            if da or bmode or zmode:
+                terms.append(("lin", (da & 7) | (bmode << 3) | (zmode << 5), rows))
 
         def two(op, params, r1, r2):
             terms.append(("two", op, params, r1, r2))
@@ -247,11 +265,17 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
                 continue
             lin(rows, da=c)
         for j in range(C):
+            # (psi' + pc)(phi' + fc) = psi' phi' + pc phi' + fc psi' + pc fc: only the first product needs two parities
             pc, fc = int(p.psi_const[g, j]) & 1, int(p.phi_const[g, j]) & 1
-            r1, r2 = rows_of(p.psi_params[g, j], pc), rows_of(p.phi_params[g, j], fc)
-            if not r1 or not r2:
-                continue  # psi or phi is identically 0
-            two(OP_PI, 0, r1, r2)
+            r1, r2 = rows_of(p.psi_params[g, j]), rows_of(p.phi_params[g, j])
+            if pc:
+                m4.symmetric_difference_update(r2)
+            if fc:
+                m4.symmetric_difference_update(r1)
+            if pc and fc:
+                a_s += 4
+            if r1 and r2:
+                two(OP_PI, 0, r1, r2)
         general = []
         for j in range(min(int(q.counts[g]), D)):
             al, be = int(q.alpha[g, j]) & 7, int(q.beta[g, j]) & 7
@@ -287,6 +311,8 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
             extra |= ztt << 18
             two(OP_PAIRMON, extra, r1, r2)
 
+        if m4:
+            terms.append(("lin", 4, sorted(m4)))
         if units > 31:
             raise _Unsupported("b counter needs more than 5 planes")
         nb = max(1, units.bit_length())

@@ -388,14 +388,15 @@ __device__ __forceinline__ void sliced_phase2(const uint32_t* __restrict__ cbase
     for (int s = 0; s < SH; ++s) base[s] += (pk >> s) & m;
   }
   const uint32_t zb = plj[0] >> sh0;
+  const uint32_t zero_entry = smem_u32(cbase + rec + 4);  // reserved header words: a shot whose value vanished adds 0
   const uint32_t r0 = SH == 8 ? lo : ((w & 1) ? hi : lo), r1 = hi;
 #pragma unroll
   for (int s = 0; s < SH; ++s) {
-    if ((zb >> s) & 1u) continue;
     const uint32_t r = s < 4 ? r0 : r1;
     uint32_t sl = (s & 3) == 0 ? sel_e.x : (s & 3) == 1 ? sel_e.y : (s & 3) == 2 ? sel_e.z : sel_e.w;
     if (HAS_EXACT && !approx) sl <<= 1;
-    const uint32_t ea = __dp4a(r, sl, base[s]);
+    uint32_t ea = __dp4a(r, sl, base[s]);
+    ea = ((zb >> s) & 1u) ? zero_entry : ea;
     if (approx) {
       const float2 e = *reinterpret_cast<const float2*>(__cvta_shared_to_generic(ea));
       if constexpr (HAS_EXACT) {

@@ -22,7 +22,7 @@ Graph record (uint32 words):
     [1]  n_index_bits | n_b_planes << 8
     [2]  offset of the decode table (filled in when the chunk is assembled)
     [3]  record words
-    [4..7] reserved
+    [4..7] zero (the decode entry of a shot whose value vanished)
     then the block stream ([0] low half = its length in words).  A block computes one parity (see ``_block``) and applies
     an op to it:
         FIRST    keep the parity as q (first half of a two-parity term)

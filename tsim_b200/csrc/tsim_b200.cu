@@ -464,21 +464,21 @@ static int fail(int code, const std::string& msg) {
 
 constexpr int kSlots = 3;            // pipeline depth of tsb_sample_host
 constexpr long long kSliceDefault = 262144;  // shots per pipeline slice (best of the sweep in tools/sweep_slice.py)
-static long long slice_shots() {
+static long long slice_env() {
   static long long v = [] {
     if (const char* e = getenv("TSIM_B200_SLICE")) {
       long long x = atoll(e);
       if (x >= 1024) return x;
     }
-    return kSliceDefault;
+    return 0ll;
   }();
   return v;
 }
-#define kSlice slice_shots()
 
 struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t k_start = nullptr, k_stop = nullptr;
+  cudaEvent_t t_h0 = nullptr, t_h1 = nullptr, t_d1 = nullptr;  // TSIM_B200_TRACE: copy-in start / end, copy-out end
   uint8_t* d_in_bytes = nullptr;   // raw host rows (bytes format) or packed rows
   uint64_t* d_f = nullptr;
   uint64_t* d_out = nullptr;
@@ -525,6 +525,11 @@ struct tsb_program {
   uint32_t* d_ot = nullptr;
   long long scratch_slabs = 0;
 };
+
+// Shots per slice of the host pipelines (TSIM_B200_SLICE overrides; TSIM_B200_TRACE=1 prints the timeline).  Measured on
+// cfg2 with 10^6 shots: the host-to-device copy of the reference's byte rows (63 MB at ~49 GB/s = 1.3 ms) is the critical
+// path, 262144-shot slices leave the shortest tail behind it (tools/sweep_slice.py, tools/e2e_trace.py).
+static long long pipeline_slice(const tsb_program*) { return slice_env() ? slice_env() : kSliceDefault; }
 
 const char* tsb_last_error(void) { return g_err.c_str(); }
 
@@ -748,6 +753,9 @@ static void free_slot(Slot& s) {
   if (s.d_xt) cudaFree(s.d_xt);
   if (s.d_ot) cudaFree(s.d_ot);
   if (s.k_start) cudaEventDestroy(s.k_start);
+  if (s.t_h0) cudaEventDestroy(s.t_h0);
+  if (s.t_h1) cudaEventDestroy(s.t_h1);
+  if (s.t_d1) cudaEventDestroy(s.t_d1);
   if (s.k_stop) cudaEventDestroy(s.k_stop);
   if (s.stream) cudaStreamDestroy(s.stream);
   s = Slot();
@@ -950,7 +958,7 @@ static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl) {
 // K0t -> K1s -> K2a -> K1c on one stream
 static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long long shot_offset, const uint32_t* d_subkeys,
                          uint64_t* d_out, float* d_norm_dev, cudaStream_t st, uint32_t* d_xt, uint32_t* d_ot, long long slab_cap,
-                         bool join = false) {
+                         bool join = false, cudaEvent_t k1s_start = nullptr, cudaEvent_t k1s_stop = nullptr) {
   if (B <= 0) return TSB_OK;
   const tsb_info& in = p->info;
   const int n_slabs = (int)((B + 31) / 32);
@@ -972,8 +980,10 @@ static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long 
     k.smem_xt_off = pl.xt_off; k.smem_pl_off = pl.pl_off; k.smem_data_off = pl.data_off;
     k.rows = p->s_rows; k.sel = make_uint4(0x80u, 0x8000u, 0x800000u, 0x80000000u);
     k.sel_e = make_uint4(8u, 8u << 8, 8u << 16, 8u << 24);
+    if (k1s_start) CU(cudaEventRecord(k1s_start, st));  // tsb_last_kernel_ms reports the dominant kernel alone
     sliced_fn(pl.split, p->s_has_exact)<<<pl.grid, pl.ng * pl.split * 32, pl.smem_bytes, st>>>(k);
     CU(cudaGetLastError());
+    if (k1s_stop) CU(cudaEventRecord(k1s_stop, st));
   }
   assemble_out_kernel<<<tblocks, 256, 0, st>>>(p->d_blob, d_f, d_ot, B, n_slabs, (int)slab_cap, d_out);
   CU(cudaGetLastError());
@@ -1030,9 +1040,9 @@ int tsb_sample_device(tsb_program* p, const uint64_t* d_f, int64_t B, int64_t sh
     }
     // the stream only waits for the (overlapped) norm check when the caller wants the deviations in its own buffer
     int rc = launch_sliced(p, d_f, B, shot_offset, p->d_subkeys, d_out, d_norm_dev ? d_norm_dev : p->d_norm_dev, st, p->d_xt,
-                           p->d_ot, p->scratch_slabs, d_norm_dev != nullptr);
+                           p->d_ot, p->scratch_slabs, d_norm_dev != nullptr, p->ev_a, p->ev_b);
     if (rc) return rc;
-    CU(cudaEventRecord(p->ev_b, st));
+    if (p->info.n_draws == 0) CU(cudaEventRecord(p->ev_b, st));  // no sampling kernel ran: empty interval
     p->last_launches = B > 0 ? 5 : 0;
     p->last_ms = -1.f;
     return TSB_OK;
@@ -1071,6 +1081,9 @@ static int ensure_slot(tsb_program* p, Slot& s, long long cap) {
     CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&s.k_start));
     CU(cudaEventCreate(&s.k_stop));
+    CU(cudaEventCreate(&s.t_h0));
+    CU(cudaEventCreate(&s.t_h1));
+    CU(cudaEventCreate(&s.t_d1));
     CU(cudaMalloc(&s.d_subkeys, 8 * (size_t)std::max(1, in.n_draws)));
   }
   if (s.cap >= cap) return TSB_OK;
@@ -1138,9 +1151,18 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
     for (int i = 0; i < in.n_components; ++i) norm_dev[i] = 0.f;
   if (B == 0) return TSB_OK;
   CU(cudaMemsetAsync(p->d_norm_dev, 0, sizeof(float) * std::max(1, in.n_components), p->stream));
+  static const bool trace = getenv("TSIM_B200_TRACE") != nullptr;  // per-slice timeline on stderr
+  if (trace) CU(cudaEventRecord(p->ev_a, p->stream));
   CU(cudaStreamSynchronize(p->stream));
+  auto dump = [&](const Slot& s, int idx) {
+    float h0 = 0, h1 = 0, k0t = 0, k1t = 0, d1 = 0;
+    cudaEventElapsedTime(&h0, p->ev_a, s.t_h0); cudaEventElapsedTime(&h1, p->ev_a, s.t_h1);
+    cudaEventElapsedTime(&k0t, p->ev_a, s.k_start); cudaEventElapsedTime(&k1t, p->ev_a, s.k_stop);
+    cudaEventElapsedTime(&d1, p->ev_a, s.t_d1);
+    fprintf(stderr, "[tsb trace] slice %d: h2d %.3f-%.3f  kernels %.3f-%.3f  d2h done %.3f ms\n", idx, h0, h1, k0t, k1t, d1);
+  };
 
-  const long long slice = std::min<long long>(kSlice, B);
+  const long long slice = std::min<long long>(pipeline_slice(p), B);
   const size_t in_row = f_format == TSB_F_BYTES ? (size_t)in.num_f : (size_t)in.words_f64 * 8;
   const size_t out_row = out_format == TSB_OUT_BYTES ? (size_t)in.num_outputs : (size_t)in.words_out64 * 8;
   int n_slices = (int)((B + slice - 1) / slice);
@@ -1150,6 +1172,7 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
     if (rc) return rc;
     if (i >= kSlots) {
       CU(cudaStreamSynchronize(s.stream));  // slot reuse: previous slice in this slot has fully drained
+      if (trace) dump(s, i - kSlots);
       if (s.timed) {
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, s.k_start, s.k_stop));
@@ -1161,6 +1184,7 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
     derive_subkeys_kernel<<<1, 32, 0, s.stream>>>(k0, k1, in.n_draws, s.d_subkeys);
     CU(cudaGetLastError());
     const uint8_t* src = (const uint8_t*)f + (size_t)lo * in_row;
+    if (trace) CU(cudaEventRecord(s.t_h0, s.stream));
     if (f_format == TSB_F_BYTES) {
       if (in.num_f > 0) CU(cudaMemcpyAsync(s.d_in_bytes, src, (size_t)n * in_row, cudaMemcpyHostToDevice, s.stream));
       rc = tsb_pack_f_device(p, s.d_in_bytes, n, s.d_f, s.stream);
@@ -1168,6 +1192,7 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
     } else {
       CU(cudaMemcpyAsync(s.d_f, src, (size_t)n * in_row, cudaMemcpyHostToDevice, s.stream));
     }
+    if (trace) CU(cudaEventRecord(s.t_h1, s.stream));
     CU(cudaEventRecord(s.k_start, s.stream));
     rc = p->is_sliced ? launch_sliced(p, s.d_f, n, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream, s.d_xt, s.d_ot, (s.cap + 31) / 32)
                       : launch_sample(p, s.d_f, n, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream, s.d_heavy + 1, s.d_heavy);
@@ -1185,11 +1210,13 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
         CU(cudaMemcpyAsync(dst, s.d_out, (size_t)n * out_row, cudaMemcpyDeviceToHost, s.stream));
       }
     }
+    if (trace) CU(cudaEventRecord(s.t_d1, s.stream));
   }
   for (int i = 0; i < kSlots; ++i) {
     Slot& s = p->slots[i];
     if (!s.stream) continue;
     CU(cudaStreamSynchronize(s.stream));
+    if (trace && s.timed) dump(s, -1 - i);
     if (s.timed) {
       float ms = 0.f;
       CU(cudaEventElapsedTime(&ms, s.k_start, s.k_stop));
@@ -1397,7 +1424,7 @@ int tsb_sample_noisy_host(tsb_program* p, tsb_noise* n, int64_t B, int64_t shot_
   if (B == 0) return TSB_OK;
   CU(cudaMemsetAsync(p->d_norm_dev, 0, sizeof(float) * std::max(1, in.n_components), p->stream));
   CU(cudaStreamSynchronize(p->stream));
-  const long long slice = std::min<long long>(kSlice, B);
+  const long long slice = std::min<long long>(pipeline_slice(p), B);
   const size_t out_row = out_format == TSB_OUT_BYTES ? (size_t)in.num_outputs : (size_t)in.words_out64 * 8;
   const int n_slices = (int)((B + slice - 1) / slice);
   for (int i = 0; i < n_slices; ++i) {

@@ -669,4 +669,115 @@ __global__ void __launch_bounds__(128) norm_check_kernel(const uint32_t* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K1c, parallel form for MODE_FAST companions: the graphs of an evaluation are spread over the CTA's threads (each
+// evaluates one graph into a private accumulator), then one thread adds the contributions in graph order -- the same
+// additions, in the same order, as the sequential evaluator (adding to a zero accumulator is exact).
+// One CTA per component.  Dynamic shared memory: (2 n_c + 1) floats, then max_graphs x 4 words of contributions.
+// ---------------------------------------------------------------------------------------------
+template <int W, class Src>
+__device__ __forceinline__ uint32_t fast_graph_words(const Src& src, uint32_t off) {
+  const uint32_t h = src.ld(off);
+  const uint32_t nL = h & 0xFFFu, nPi = (h >> 12) & 0xFFFu, nD = h >> 24, nM = src.ld(off + 7);
+  return kFastHeaderWords + round4(nL * fast_lin_stride(W)) + round4(nPi * fast_pi_stride(W)) + nM * fast_mpair_stride(W) +
+         nD * fast_pair_stride(W);
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) norm_check_fast_kernel(const uint32_t* __restrict__ blob, const uint64_t* __restrict__ f_row0,
+                                                              const uint64_t* __restrict__ out_row0, float* __restrict__ norm_dev) {
+  __shared__ Tables tb;
+  extern __shared__ float vals[];
+  init_tables(&tb, threadIdx.x, blockDim.x);
+  const int ci = blockIdx.x;
+  const uint32_t* __restrict__ comp = blob + blob[H_OFF_COMP] + ci * kCompWords;
+  const int F = (int)comp[C_F], n_c = (int)comp[C_NC], first_draw = (int)comp[C_FIRST_DRAW];
+  const uint32_t* __restrict__ sel = blob + blob[H_OFF_FSEL] + comp[C_FSEL_OFF];
+  const uint32_t* __restrict__ dest = blob + blob[H_OFF_DEST];
+  const uint32_t* __restrict__ chunk_tab = blob + blob[H_OFF_CHUNK];
+  const GmemSrc src{blob + blob[H_OFF_DATA]};
+  const int n_evals = 2 * n_c + 1;
+  uint4* contrib = reinterpret_cast<uint4*>(vals + ((n_evals + 3) & ~3));
+  __syncthreads();
+  for (int t = 0; t < n_evals; ++t) {
+    const int k = (t + 1) >> 1;
+    const uint32_t trybit = (uint32_t)(t & 1);
+    uint32_t x[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      uint32_t xv = 0;
+      const int lim = min(32, F - 32 * w);
+      for (int b = 0; b < lim; ++b) {
+        const uint32_t fi = sel[32 * w + b];
+        xv |= (uint32_t)((f_row0[fi >> 6] >> (fi & 63u)) & 1ull) << b;
+      }
+      for (int j = 0; j < k; ++j) {
+        const int pos = F + j;
+        if ((pos >> 5) != w) continue;
+        uint32_t bit;
+        if (j == k - 1) {
+          bit = trybit;
+        } else {
+          const uint32_t d = dest[first_draw + j];
+          bit = (uint32_t)((out_row0[d >> 6] >> (d & 63u)) & 1ull);
+        }
+        xv |= bit << (pos & 31);
+      }
+      x[w] = xv;
+    }
+    x[W - 1] |= 0x80000000u;  // the always-one parameter of MODE_FAST
+    const uint32_t* __restrict__ lvl = blob + blob[H_OFF_LEVEL] + (comp[C_FIRST_LEVEL] + k) * kLevelWords;
+    const bool approx = (lvl[L_FLAGS] & 1u) != 0u;
+    const int G = (int)lvl[L_G];
+    const int first_chunk = (int)lvl[L_FIRST_CHUNK], nck = (int)lvl[L_N_CHUNKS];
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+      // locate graph g: chunk, then walk the variable-length records of that chunk
+      int c = 0, g0 = 0;
+      while (c < nck && g0 + (int)chunk_tab[(first_chunk + c) * kChunkWords + K_GRAPHS] <= g) {
+        g0 += (int)chunk_tab[(first_chunk + c) * kChunkWords + K_GRAPHS];
+        ++c;
+      }
+      uint32_t off = chunk_tab[(first_chunk + c) * kChunkWords + K_OFF];
+      for (int i = g0; i < g; ++i) off += fast_graph_words<W>(src, off);
+      LevelAcc acc;
+      acc.reset();
+      eval_chunk_fast<W>(src, off, 1, approx, x, acc, &tb);
+      contrib[g] = approx ? make_uint4(__float_as_uint(acc.re), __float_as_uint(acc.im), 0u, 0u)
+                          : make_uint4(acc.c.c0, acc.c.c1, acc.c.c2, acc.c.c3);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      LevelAcc acc;
+      acc.reset();
+      for (int g = 0; g < G; ++g) {
+        const uint4 cg = contrib[g];
+        if (approx) {
+          acc.re = __fadd_rn(acc.re, __uint_as_float(cg.x));
+          acc.im = __fadd_rn(acc.im, __uint_as_float(cg.y));
+        } else {
+          acc.c.c0 += cg.x; acc.c.c1 += cg.y; acc.c.c2 += cg.z; acc.c.c3 += cg.w;
+        }
+      }
+      float re, im;
+      finish_level<kModeFast>(acc, approx, (int)lvl[L_P_LO], re, im);
+      if (G == 0) { re = 0.0f; im = 0.0f; }
+      vals[t] = complex_abs(re, im);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float prev = vals[0], dev = 0.0f;
+    for (int k = 1; k <= n_c; ++k) {
+      const float p1 = vals[2 * k - 1], p0 = vals[2 * k];
+      const float norm = __fdiv_rn(__fadd_rn(p0, p1), prev);
+      const float d = fabsf(__fsub_rn(norm, 1.0f));
+      dev = (dev != dev || d != d) ? __uint_as_float(0x7FC00000u) : fmaxf(dev, d);
+      const uint32_t dd = dest[first_draw + k - 1];
+      const bool bit = ((out_row0[dd >> 6] >> (dd & 63u)) & 1ull) != 0ull;
+      prev = bit ? p1 : __fsub_rn(prev, p1);
+    }
+    norm_dev[ci] = dev;
+  }
+}
+
 }  // namespace tsb

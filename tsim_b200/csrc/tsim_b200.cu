@@ -926,6 +926,20 @@ static NormFn norm_fn_for(int W) {
   }
 }
 
+static NormFn norm_fast_fn(int W) {
+  switch (W) {
+    case 1: return norm_check_fast_kernel<1>;
+    case 2: return norm_check_fast_kernel<2>;
+    case 3: return norm_check_fast_kernel<3>;
+    case 4: return norm_check_fast_kernel<4>;
+    case 5: return norm_check_fast_kernel<5>;
+    case 6: return norm_check_fast_kernel<6>;
+    case 7: return norm_check_fast_kernel<7>;
+    case 8: return norm_check_fast_kernel<8>;
+    default: return nullptr;
+  }
+}
+
 // Groups per CTA, split and ring depth for a batch of n_slabs slabs.  Few groups per SM -> 8 warps per group (so that a
 // thin slice still keeps 16+ warps on an SM), otherwise 4.
 static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl) {
@@ -995,7 +1009,18 @@ static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long 
     CU(cudaEventRecord(p->ev_fork, st));
     CU(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
     NormFn fn = a->info.mode == kModeFast ? norm_fn_for<kModeFast>(a->info.words) : norm_fn_for<kModeFaithful>(a->info.words);
-    fn<<<in.n_components, 128, (2 * p->max_nc + 1) * sizeof(float), p->side>>>(a->d_blob, p->d_row0, p->d_row0 + in.words_f64, d_norm_dev);
+    if (a->info.mode == kModeFast && norm_fast_fn(a->info.words)) {
+      // graphs of an evaluation spread over the CTA (sliced_kernels.cuh: norm_check_fast_kernel)
+      const uint32_t* ab = a->host_blob.data();
+      uint32_t max_g = 1;
+      for (uint32_t i = 0; i < ab[H_N_LEVELS]; ++i) max_g = std::max(max_g, ab[ab[H_OFF_LEVEL] + i * kLevelWords + L_G]);
+      const size_t sm = (size_t)((2 * p->max_nc + 1 + 3) & ~3) * sizeof(float) + (size_t)max_g * 16;
+      if (sm <= 40000) {
+        norm_fast_fn(a->info.words)<<<in.n_components, 256, sm, p->side>>>(a->d_blob, p->d_row0, p->d_row0 + in.words_f64, d_norm_dev);
+        fn = nullptr;
+      }
+    }
+    if (fn) fn<<<in.n_components, 128, (2 * p->max_nc + 1) * sizeof(float), p->side>>>(a->d_blob, p->d_row0, p->d_row0 + in.words_f64, d_norm_dev);
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev_join, p->side));
     if (join) CU(cudaStreamWaitEvent(st, p->ev_join, 0));

@@ -387,7 +387,7 @@ def run_gpu(args):
         "kernel_ms": k_ms,
         "step_ms_isolated": step_ms_isolated,
         "algorithmic_bytes": int(alg_bytes),
-        "note": "shared-memory / issue bound by construction (about 2e4 integer ops and 4e3 shared-memory reads per shot vs 16 B of mandatory HBM traffic); see DESIGN.md",
+        "note": "shared-memory / issue bound by construction (about 2e4 instructions and 150 shared-memory word reads per shot vs 16 B of mandatory HBM traffic); see DESIGN.md",
     }
 
     # ---- CPU baseline beside it (N = 1 only): oracle on all host cores over a bounded sample

@@ -1,7 +1,7 @@
 #!/bin/bash
 # One GPU-box iteration on the sliced kernel: sliced parity tests, bench (sliced), ncu full capture.  Logs in gpurun_out/.
 mkdir -p gpurun_out
-timeout -s KILL 900 python -m pytest tests -m gpu -x -q > gpurun_out/t_sliced.log 2>&1
+timeout -s KILL 900 python -m pytest tests -m gpu -x -q -k sliced > gpurun_out/t_sliced.log 2>&1
 echo "sliced tests rc=$?"; tail -3 gpurun_out/t_sliced.log
 timeout -s KILL 600 python bench.py --no-cpu --no-extras --steps 10 --warmup 3 > gpurun_out/bench_sliced.json 2> gpurun_out/bench_sliced.err
 echo "bench rc=$?"; python - <<'PY'

@@ -946,6 +946,9 @@ static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl) {
   const int n_groups = std::max(1, (n_slabs + 31) / 32);
   pl.grid = std::max(1, std::min(p->sm_count, n_groups));
   const int gpc = (n_groups + pl.grid - 1) / pl.grid;  // groups per CTA
+  // the smallest grid with that many groups per CTA: the kernel is no slower, and the SMs left over (8 of 148 for 10^6
+  // shots) take the neighbouring kernels of the pipeline, the norm check and NCCL's all-gather instead of queueing them
+  pl.grid = (n_groups + gpc - 1) / gpc;
   int split = (p->s_has_exact || gpc < 4) ? 8 : 4;
   if (const char* e = getenv("TSIM_B200_SLICED_SPLIT")) {  // tuning knob
     const int v = atoi(e);

@@ -73,7 +73,7 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
 int tsb_program_destroy(tsb_program* p);
 int tsb_program_info(const tsb_program* p, tsb_info* info);
 
-/* A bit-sliced (mode 2) program samples 32 shots per thread and cannot evaluate single rows; the normalisation
+/* A bit-sliced (mode 2) program works on words of 32 shots and cannot evaluate single rows; the normalisation
  * check of shot 0 (sampler.py:66-72) and tsb_evaluate_host run on a companion per-row program of the same
  * CompiledProgram.  The companion is not owned: destroy it after the sliced program. */
 int tsb_program_set_aux(tsb_program* p, tsb_program* aux);

@@ -95,3 +95,54 @@ def test_graphs_with_many_general_pairs_are_split_into_gated_variants(approx):
                 assert np.array_equal(g[1], ssum.coeffs[s]) and g[2] == int(ssum.power[s]), s
             else:
                 assert not np.any(g[1])
+
+
+def test_sliced_chunk_layout_invariants():
+    """Alignment and bounds the kernel relies on (16-byte items, zero entry in the record header, whole waves per chunk)."""
+    from tsim_b200.pack_sliced import MAX_CHUNK_WORDS, SLICED_HEADER_WORDS
+    from tsim_b200.synthetic import synthetic_program
+
+    prog = synthetic_program("cfg2_distill35")
+    pp = PK.pack_program(prog, mode="sliced")
+    blob = pp.blob
+    data = blob[int(blob[PK.H_OFF_DATA]) :]
+    chunks = blob[int(blob[PK.H_OFF_CHUNK]) :][: int(blob[PK.H_N_CHUNKS]) * 4].reshape(-1, 4)
+    levels = blob[int(blob[PK.H_OFF_LEVEL]) :][: int(blob[PK.H_N_LEVELS]) * PK.LEVEL_WORDS].reshape(-1, PK.LEVEL_WORDS)
+    assert int(blob[PK.H_OFF_DATA]) % 32 == 0
+    for lv in levels:
+        first, n = int(lv[7]), int(lv[8])
+        assert sum(int(c[2]) for c in chunks[first : first + n]) == int(lv[0])
+        for ci, (off, words, ng, _) in enumerate(chunks[first : first + n]):
+            off, words, ng = int(off), int(words), int(ng)
+            assert off % 4 == 0 and words % 4 == 0 and words <= MAX_CHUNK_WORDS
+            if ci + 1 < n:
+                assert ng % 8 == 0  # only the last chunk of a level may end with a partial wave
+            chunk = data[off : off + words]
+            end_of_records = None
+            for g in range(ng):
+                rec = int(chunk[g])
+                assert rec % 4 == 0 and rec >= ((ng + 3) & ~3)
+                hdr = chunk[rec : rec + SLICED_HEADER_WORDS]
+                n_idx, nb = int(hdr[1]) & 0xFF, (int(hdr[1]) >> 8) & 0xFF
+                assert 3 + nb <= n_idx <= 11 and not hdr[4:8].any()
+                body = int(hdr[0]) & 0xFFFF
+                assert body % 4 == 0 and int(hdr[3]) == SLICED_HEADER_WORDS + body
+                tbl = int(hdr[2])
+                assert tbl % 4 == 0 and tbl + 2 * (1 << n_idx) <= words
+                end_of_records = rec + int(hdr[3])
+                assert tbl >= end_of_records or g + 1 < ng
+
+
+def test_auto_mode_prefers_sliced_then_rowwise():
+    from tsim_b200.synthetic import synthetic_program
+
+    assert PK.pack_program(synthetic_program("cfg2_distill35")).mode == PK.MODE_SLICED
+    assert PK.pack_program(synthetic_program("cfg2_distill35"), mode="rowwise").mode == PK.MODE_FAST
+    # decode tables of graphs with many general phase pairs are too large to stream: the per-row records stay
+    assert PK.pack_program(synthetic_program("cfg4_cultivation_d3")).mode == PK.MODE_FAST
+    # a program whose int32 arithmetic may wrap keeps the reference's operation order
+    rng = np.random.default_rng(5)
+    lv = random_level(rng, G=4, P=6, A=3, H=2, C=2, D=1, approx=False, density=0.4)
+    lv.prefactor.floatfactor[:] = 1 << 29
+    prog = _one_level_program(lv, 6)
+    assert PK.pack_program(prog).mode == PK.MODE_FAITHFUL

@@ -215,6 +215,7 @@ def pack_program(
     mode: str | int = "auto",
     max_chunk_words: int = 8192,
     joint: bool = False,
+    sliced_budget_bytes: int | None = None,
 ) -> PackedProgram:
     """Build the device blob.  ``mode``: "faithful", "fast", "sliced", "rowwise" (fast when provably exact, else
     faithful) or "auto" (sliced when provably exact and compact, else as "rowwise").
@@ -227,7 +228,7 @@ def pack_program(
         # fastest first: the bit-sliced records, unless their decode tables blow up (graphs with many general phase
         # pairs) -- every CTA streams the whole data region once per batch
         try:
-            pp = pack_program(program, mode="sliced", max_chunk_words=max_chunk_words)
+            pp = pack_program(program, mode="sliced", max_chunk_words=max_chunk_words, sliced_budget_bytes=SLICED_AUTO_MAX_BYTES)
             if pp.stats["data_bytes"] <= SLICED_AUTO_MAX_BYTES:
                 return pp
         except ValueError:
@@ -317,7 +318,8 @@ def pack_program(
             elif mode_id == MODE_SLICED:
                 from .pack_sliced import sliced_level_chunks, sliced_level_records
 
-                graphs, (A, H, C, D), p_lo = sliced_level_records(lv, max_p, max_p + 1)
+                left = None if sliced_budget_bytes is None else max(0, sliced_budget_bytes // 4 - data_off)
+                graphs, (A, H, C, D), p_lo = sliced_level_records(lv, max_p, max_p + 1, budget_words=left)
                 graph_lists = []
             else:
                 from .pack_fast import fast_level_records  # local import: keeps this module lean

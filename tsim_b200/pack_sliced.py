@@ -188,7 +188,7 @@ class _Unsupported(ValueError):
     pass
 
 
-def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
+def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int, budget_words: int | None = None):
     """-> (list of per-graph uint32 records, (A, H, C, D), p_lo).  Raises ValueError if a graph does not fit."""
     G = lv.num_graphs
     n, h, p, q, pre = lv.node_phases, lv.halfpi_phases, lv.pi_products, lv.phase_pairs, lv.prefactor
@@ -372,6 +372,10 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int):
             )
 
     p_lo = min(shifts_base) if shifts_base else 0
+    if budget_words is not None:  # fail before the tables are built (mode="auto" gives up on bulky programs)
+        need = sum(len(r) for r in recs) + sum((2 if approx else 4) << d["n_idx"] for d in decode)
+        if need > budget_words:
+            raise _Unsupported("sliced data region exceeds the size budget")
     tables = []
     for d, sb in zip(decode, shifts_base):
         sh = sb - p_lo

@@ -75,3 +75,36 @@ def test_other_baseline_configs_match_oracle(name, B, mode):
     if name == "cfg3_surface_d5":
         full = oracle.sample_program(prog, f, (1, 1), check_norm=False)
         assert np.array_equal(got, full)
+
+
+@pytest.mark.parametrize("approx,B", [(True, 2_200_000), (False, 700_001)])
+def test_sliced_multi_round_launches_match_per_row_kernel(approx, B):
+    """Device-resident batches larger than one wave of slab groups (several rounds per CTA; 8-way split for the exact
+    branch): the sliced kernel must reproduce the per-row kernel bit for bit (which the other tests pin to the oracle)."""
+    import torch
+
+    from test_gpu_parity import _random_program
+    from tsim_b200.backend import DeviceProgram
+
+    prog = synthetic_program("cfg2_distill35") if approx else _random_program(21, approx=False, n_comp=2, n_c=3, F=12, num_f=30, G=9)
+    nf = prog.infer_num_f()
+    cs = ChannelSampler.from_bit_probs(noise_probs(nf, 2e-3), seed=3)
+    f = torch.from_numpy(cs.sample_packed(B).view(np.int64)).cuda()
+    outs = {}
+    for mode in ("sliced", "fast"):
+        dp = DeviceProgram(prog, mode=mode)
+        out = torch.zeros((B, dp.info["words_out64"]), dtype=torch.int64, device="cuda")
+        dev = torch.zeros(max(1, dp.info["n_components"]), dtype=torch.float32, device="cuda")
+        dp.sample_device(f.data_ptr(), B, (9, 1), out.data_ptr(), d_norm_dev=dev.data_ptr())
+        torch.cuda.synchronize()
+        outs[mode] = (out.cpu().numpy(), dev.cpu().numpy())
+        if mode == "sliced":
+            assert dp.info["mode"] == 2
+    assert np.array_equal(outs["sliced"][0], outs["fast"][0])
+    assert np.array_equal(outs["sliced"][1], outs["fast"][1])
+    # and a window of it against the oracle
+    lo = B - 2048
+    fb = np.unpackbits(f[lo:].cpu().numpy().view(np.uint8), axis=1, bitorder="little", count=nf)
+    want = oracle.sample_program(prog, fb, (9, 1), shot_offset=lo, check_norm=False)
+    got = np.unpackbits(outs["sliced"][0][lo:].view(np.uint8), axis=1, bitorder="little", count=prog.num_outputs).astype(bool)
+    assert np.array_equal(got, want)

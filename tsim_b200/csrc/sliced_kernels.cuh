@@ -670,10 +670,12 @@ __global__ void __launch_bounds__(128) norm_check_kernel(const uint32_t* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1c, parallel form for MODE_FAST companions: the graphs of an evaluation are spread over the CTA's threads (each
-// evaluates one graph into a private accumulator), then one thread adds the contributions in graph order -- the same
-// additions, in the same order, as the sequential evaluator (adding to a zero accumulator is exact).
-// One CTA per component.  Dynamic shared memory: (2 n_c + 1) floats, then max_graphs x 4 words of contributions.
+// K1c, parallel form for MODE_FAST companions: all (evaluation, graph) pairs of a component are evaluated at once, one
+// thread each, into private accumulators; then one thread per evaluation adds the contributions in graph order -- the
+// same additions, in the same order, as the sequential evaluator (adding to a zero accumulator is exact).  The
+// component's records are staged in shared memory first when they fit (STAGED), else read through L2.
+// One CTA per component.  Dynamic shared memory (words): vals [ne4] | x [n_evals][W] | graph offsets [n_c + 1][max_g] |
+// contributions [n_evals][max_g][4] | staged records.
 // ---------------------------------------------------------------------------------------------
 template <int W, class Src>
 __device__ __forceinline__ uint32_t fast_graph_words(const Src& src, uint32_t off) {
@@ -683,88 +685,134 @@ __device__ __forceinline__ uint32_t fast_graph_words(const Src& src, uint32_t of
          nD * fast_pair_stride(W);
 }
 
-template <int W>
-__global__ void __launch_bounds__(256) norm_check_fast_kernel(const uint32_t* __restrict__ blob, const uint64_t* __restrict__ f_row0,
-                                                              const uint64_t* __restrict__ out_row0, float* __restrict__ norm_dev) {
+template <int W, class Src>
+__device__ __forceinline__ void norm_check_items(const Src& src, const uint32_t* __restrict__ blob, const uint32_t* __restrict__ comp,
+                                                 int n_c, int max_g, const uint32_t* __restrict__ xs, uint32_t* __restrict__ goff,
+                                                 uint4* __restrict__ contrib, const Tables* tb) {
+  const uint32_t* __restrict__ chunk_tab = blob + blob[H_OFF_CHUNK];
+  // graph offsets: one thread per level walks the variable-length records
+  for (int k = threadIdx.x; k <= n_c; k += blockDim.x) {
+    const uint32_t* __restrict__ lvl = blob + blob[H_OFF_LEVEL] + (comp[C_FIRST_LEVEL] + k) * kLevelWords;
+    const int first_chunk = (int)lvl[L_FIRST_CHUNK], nck = (int)lvl[L_N_CHUNKS];
+    int g = 0;
+    for (int c = 0; c < nck; ++c) {
+      const uint32_t* row = chunk_tab + (first_chunk + c) * kChunkWords;
+      uint32_t off = row[K_OFF];
+      for (int i = 0; i < (int)row[K_GRAPHS]; ++i, ++g) {
+        goff[k * max_g + g] = off;
+        off += fast_graph_words<W>(src, off);
+      }
+    }
+  }
+  __syncthreads();
+  const int n_evals = 2 * n_c + 1;
+  for (int item = threadIdx.x; item < n_evals * max_g; item += blockDim.x) {
+    const int t = item / max_g, g = item - t * max_g;
+    const int k = (t + 1) >> 1;
+    const uint32_t* __restrict__ lvl = blob + blob[H_OFF_LEVEL] + (comp[C_FIRST_LEVEL] + k) * kLevelWords;
+    if (g >= (int)lvl[L_G]) continue;
+    const bool approx = (lvl[L_FLAGS] & 1u) != 0u;
+    uint32_t x[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) x[w] = xs[t * W + w];
+    LevelAcc acc;
+    acc.reset();
+    eval_chunk_fast<W>(src, goff[k * max_g + g], 1, approx, x, acc, tb);
+    contrib[item] = approx ? make_uint4(__float_as_uint(acc.re), __float_as_uint(acc.im), 0u, 0u)
+                           : make_uint4(acc.c.c0, acc.c.c1, acc.c.c2, acc.c.c3);
+  }
+}
+
+template <int W, bool STAGED>
+__global__ void __launch_bounds__(512) norm_check_fast_kernel(const uint32_t* __restrict__ blob, const uint64_t* __restrict__ f_row0,
+                                                              const uint64_t* __restrict__ out_row0, float* __restrict__ norm_dev, int max_g) {
   __shared__ Tables tb;
-  extern __shared__ float vals[];
+  extern __shared__ __align__(16) float vals[];
   init_tables(&tb, threadIdx.x, blockDim.x);
   const int ci = blockIdx.x;
   const uint32_t* __restrict__ comp = blob + blob[H_OFF_COMP] + ci * kCompWords;
   const int F = (int)comp[C_F], n_c = (int)comp[C_NC], first_draw = (int)comp[C_FIRST_DRAW];
   const uint32_t* __restrict__ sel = blob + blob[H_OFF_FSEL] + comp[C_FSEL_OFF];
   const uint32_t* __restrict__ dest = blob + blob[H_OFF_DEST];
-  const uint32_t* __restrict__ chunk_tab = blob + blob[H_OFF_CHUNK];
-  const GmemSrc src{blob + blob[H_OFF_DATA]};
   const int n_evals = 2 * n_c + 1;
-  uint4* contrib = reinterpret_cast<uint4*>(vals + ((n_evals + 3) & ~3));
-  __syncthreads();
-  for (int t = 0; t < n_evals; ++t) {
+  uint32_t* xs = reinterpret_cast<uint32_t*>(vals) + ((n_evals + 3) & ~3);
+  uint32_t* goff = xs + ((n_evals * W + 3) & ~3);
+  uint4* contrib = reinterpret_cast<uint4*>(goff + (((n_c + 1) * max_g + 3) & ~3));
+  // parameter vectors of the evaluations: t = 0 is level 0, t = 2k-1 level k trying bit 1, t = 2k trying bit 0
+  for (int i = threadIdx.x; i < n_evals * W; i += blockDim.x) {
+    const int t = i / W, w = i - t * W;
     const int k = (t + 1) >> 1;
     const uint32_t trybit = (uint32_t)(t & 1);
-    uint32_t x[W];
-#pragma unroll
-    for (int w = 0; w < W; ++w) {
-      uint32_t xv = 0;
-      const int lim = min(32, F - 32 * w);
-      for (int b = 0; b < lim; ++b) {
-        const uint32_t fi = sel[32 * w + b];
-        xv |= (uint32_t)((f_row0[fi >> 6] >> (fi & 63u)) & 1ull) << b;
-      }
-      for (int j = 0; j < k; ++j) {
-        const int pos = F + j;
-        if ((pos >> 5) != w) continue;
-        uint32_t bit;
-        if (j == k - 1) {
-          bit = trybit;
-        } else {
-          const uint32_t d = dest[first_draw + j];
-          bit = (uint32_t)((out_row0[d >> 6] >> (d & 63u)) & 1ull);
-        }
-        xv |= bit << (pos & 31);
-      }
-      x[w] = xv;
+    uint32_t xv = 0;
+    const int lim = min(32, F - 32 * w);
+    for (int b = 0; b < lim; ++b) {
+      const uint32_t fi = sel[32 * w + b];
+      xv |= (uint32_t)((f_row0[fi >> 6] >> (fi & 63u)) & 1ull) << b;
     }
-    x[W - 1] |= 0x80000000u;  // the always-one parameter of MODE_FAST
+    for (int j = 0; j < k; ++j) {
+      const int pos = F + j;
+      if ((pos >> 5) != w) continue;
+      uint32_t bit;
+      if (j == k - 1) {
+        bit = trybit;
+      } else {
+        const uint32_t d = dest[first_draw + j];
+        bit = (uint32_t)((out_row0[d >> 6] >> (d & 63u)) & 1ull);
+      }
+      xv |= bit << (pos & 31);
+    }
+    if (w == W - 1) xv |= 0x80000000u;  // the always-one parameter of MODE_FAST
+    xs[i] = xv;
+  }
+  const uint32_t* __restrict__ gdata = blob + blob[H_OFF_DATA];
+  if constexpr (STAGED) {
+    // the component's chunks are contiguous in the data region: [lo, hi)
+    const uint32_t* __restrict__ chunk_tab = blob + blob[H_OFF_CHUNK];
+    const uint32_t* __restrict__ lv0 = blob + blob[H_OFF_LEVEL] + comp[C_FIRST_LEVEL] * kLevelWords;
+    uint32_t lo = 0, hi = 0;
+    bool any = false;
+    for (int k = 0; k <= n_c; ++k) {
+      const uint32_t* lvl = lv0 + k * kLevelWords;
+      for (uint32_t c = 0; c < lvl[L_N_CHUNKS]; ++c) {
+        const uint32_t* row = chunk_tab + (lvl[L_FIRST_CHUNK] + c) * kChunkWords;
+        if (!any) { lo = row[K_OFF]; any = true; }
+        hi = row[K_OFF] + row[K_WORDS];
+      }
+    }
+    uint4* staged = contrib + n_evals * max_g;
+    const uint4* __restrict__ g4 = reinterpret_cast<const uint4*>(gdata + lo);
+    for (uint32_t i = threadIdx.x; i < (hi - lo) / 4; i += blockDim.x) staged[i] = g4[i];
+    __syncthreads();
+    const SmemSrc src{reinterpret_cast<const uint32_t*>(staged) - lo};
+    norm_check_items<W>(src, blob, comp, n_c, max_g, xs, goff, contrib, &tb);
+  } else {
+    __syncthreads();
+    const GmemSrc src{gdata};
+    norm_check_items<W>(src, blob, comp, n_c, max_g, xs, goff, contrib, &tb);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < n_evals; t += blockDim.x) {
+    const int k = (t + 1) >> 1;
     const uint32_t* __restrict__ lvl = blob + blob[H_OFF_LEVEL] + (comp[C_FIRST_LEVEL] + k) * kLevelWords;
     const bool approx = (lvl[L_FLAGS] & 1u) != 0u;
     const int G = (int)lvl[L_G];
-    const int first_chunk = (int)lvl[L_FIRST_CHUNK], nck = (int)lvl[L_N_CHUNKS];
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-      // locate graph g: chunk, then walk the variable-length records of that chunk
-      int c = 0, g0 = 0;
-      while (c < nck && g0 + (int)chunk_tab[(first_chunk + c) * kChunkWords + K_GRAPHS] <= g) {
-        g0 += (int)chunk_tab[(first_chunk + c) * kChunkWords + K_GRAPHS];
-        ++c;
+    LevelAcc acc;
+    acc.reset();
+    for (int g = 0; g < G; ++g) {
+      const uint4 cg = contrib[t * max_g + g];
+      if (approx) {
+        acc.re = __fadd_rn(acc.re, __uint_as_float(cg.x));
+        acc.im = __fadd_rn(acc.im, __uint_as_float(cg.y));
+      } else {
+        acc.c.c0 += cg.x; acc.c.c1 += cg.y; acc.c.c2 += cg.z; acc.c.c3 += cg.w;
       }
-      uint32_t off = chunk_tab[(first_chunk + c) * kChunkWords + K_OFF];
-      for (int i = g0; i < g; ++i) off += fast_graph_words<W>(src, off);
-      LevelAcc acc;
-      acc.reset();
-      eval_chunk_fast<W>(src, off, 1, approx, x, acc, &tb);
-      contrib[g] = approx ? make_uint4(__float_as_uint(acc.re), __float_as_uint(acc.im), 0u, 0u)
-                          : make_uint4(acc.c.c0, acc.c.c1, acc.c.c2, acc.c.c3);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      LevelAcc acc;
-      acc.reset();
-      for (int g = 0; g < G; ++g) {
-        const uint4 cg = contrib[g];
-        if (approx) {
-          acc.re = __fadd_rn(acc.re, __uint_as_float(cg.x));
-          acc.im = __fadd_rn(acc.im, __uint_as_float(cg.y));
-        } else {
-          acc.c.c0 += cg.x; acc.c.c1 += cg.y; acc.c.c2 += cg.z; acc.c.c3 += cg.w;
-        }
-      }
-      float re, im;
-      finish_level<kModeFast>(acc, approx, (int)lvl[L_P_LO], re, im);
-      if (G == 0) { re = 0.0f; im = 0.0f; }
-      vals[t] = complex_abs(re, im);
-    }
-    __syncthreads();
+    float re, im;
+    finish_level<kModeFast>(acc, approx, (int)lvl[L_P_LO], re, im);
+    if (G == 0) { re = 0.0f; im = 0.0f; }
+    vals[t] = complex_abs(re, im);
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
     float prev = vals[0], dev = 0.0f;
     for (int k = 1; k <= n_c; ++k) {

@@ -926,18 +926,54 @@ static NormFn norm_fn_for(int W) {
   }
 }
 
-static NormFn norm_fast_fn(int W) {
+typedef void (*NormFastFn)(const uint32_t*, const uint64_t*, const uint64_t*, float*, int);
+template <bool STAGED>
+static NormFastFn norm_fast_fn(int W) {
   switch (W) {
-    case 1: return norm_check_fast_kernel<1>;
-    case 2: return norm_check_fast_kernel<2>;
-    case 3: return norm_check_fast_kernel<3>;
-    case 4: return norm_check_fast_kernel<4>;
-    case 5: return norm_check_fast_kernel<5>;
-    case 6: return norm_check_fast_kernel<6>;
-    case 7: return norm_check_fast_kernel<7>;
-    case 8: return norm_check_fast_kernel<8>;
+    case 1: return norm_check_fast_kernel<1, STAGED>;
+    case 2: return norm_check_fast_kernel<2, STAGED>;
+    case 3: return norm_check_fast_kernel<3, STAGED>;
+    case 4: return norm_check_fast_kernel<4, STAGED>;
+    case 5: return norm_check_fast_kernel<5, STAGED>;
+    case 6: return norm_check_fast_kernel<6, STAGED>;
+    case 7: return norm_check_fast_kernel<7, STAGED>;
+    case 8: return norm_check_fast_kernel<8, STAGED>;
     default: return nullptr;
   }
+}
+
+// Launch the parallel norm check on a MODE_FAST companion; false if its scratch does not fit in shared memory.
+static bool launch_norm_fast(const tsb_program* p, const tsb_program* a, float* d_norm_dev) {
+  const uint32_t* ab = a->host_blob.data();
+  const int W = a->info.words;
+  int max_g = 1, max_nc = 0;
+  long long max_range = 0;
+  for (uint32_t i = 0; i < ab[H_N_LEVELS]; ++i) max_g = std::max<int>(max_g, (int)ab[ab[H_OFF_LEVEL] + i * kLevelWords + L_G]);
+  for (uint32_t c = 0; c < ab[H_N_COMP]; ++c) {
+    const uint32_t* comp = ab + ab[H_OFF_COMP] + c * kCompWords;
+    max_nc = std::max<int>(max_nc, (int)comp[C_NC]);
+    long long lo = -1, hi = 0;
+    for (uint32_t k = 0; k < comp[C_N_LEVELS]; ++k) {
+      const uint32_t* lvl = ab + ab[H_OFF_LEVEL] + (comp[C_FIRST_LEVEL] + k) * kLevelWords;
+      for (uint32_t j = 0; j < lvl[L_N_CHUNKS]; ++j) {
+        const uint32_t* row = ab + ab[H_OFF_CHUNK] + (lvl[L_FIRST_CHUNK] + j) * kChunkWords;
+        if (lo < 0) lo = row[K_OFF];
+        hi = (long long)row[K_OFF] + row[K_WORDS];
+      }
+    }
+    if (lo >= 0) max_range = std::max(max_range, hi - lo);
+  }
+  const long long n_evals = 2ll * max_nc + 1;
+  const long long base_words = ((n_evals + 3) & ~3ll) + ((n_evals * W + 3) & ~3ll) + (((max_nc + 1ll) * max_g + 3) & ~3ll) + n_evals * max_g * 4;
+  const long long limit = p->s_smem_limit - (long long)sizeof(Tables) - 1024;
+  const bool staged = (base_words + max_range) * 4 <= limit;
+  const long long bytes = (base_words + (staged ? max_range : 0)) * 4;
+  if (bytes > limit) return false;
+  NormFastFn fn = staged ? norm_fast_fn<true>(W) : norm_fast_fn<false>(W);
+  if (!fn) return false;
+  if (bytes > 40000 && cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return false;
+  fn<<<p->info.n_components, 512, (size_t)bytes, p->side>>>(a->d_blob, p->d_row0, p->d_row0 + p->info.words_f64, d_norm_dev, max_g);
+  return true;
 }
 
 // Groups per CTA, split and ring depth for a batch of n_slabs slabs.  Few groups per SM -> 8 warps per group (so that a
@@ -1012,17 +1048,7 @@ static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long 
     CU(cudaEventRecord(p->ev_fork, st));
     CU(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
     NormFn fn = a->info.mode == kModeFast ? norm_fn_for<kModeFast>(a->info.words) : norm_fn_for<kModeFaithful>(a->info.words);
-    if (a->info.mode == kModeFast && norm_fast_fn(a->info.words)) {
-      // graphs of an evaluation spread over the CTA (sliced_kernels.cuh: norm_check_fast_kernel)
-      const uint32_t* ab = a->host_blob.data();
-      uint32_t max_g = 1;
-      for (uint32_t i = 0; i < ab[H_N_LEVELS]; ++i) max_g = std::max(max_g, ab[ab[H_OFF_LEVEL] + i * kLevelWords + L_G]);
-      const size_t sm = (size_t)((2 * p->max_nc + 1 + 3) & ~3) * sizeof(float) + (size_t)max_g * 16;
-      if (sm <= 40000) {
-        norm_fast_fn(a->info.words)<<<in.n_components, 256, sm, p->side>>>(a->d_blob, p->d_row0, p->d_row0 + in.words_f64, d_norm_dev);
-        fn = nullptr;
-      }
-    }
+    if (a->info.mode == kModeFast && launch_norm_fast(p, a, d_norm_dev)) fn = nullptr;
     if (fn) fn<<<in.n_components, 128, (2 * p->max_nc + 1) * sizeof(float), p->side>>>(a->d_blob, p->d_row0, p->d_row0 + in.words_f64, d_norm_dev);
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev_join, p->side));

@@ -47,15 +47,15 @@ struct SParams {
 };
 
 // ---------------------------------------------------------------------------------------------
-// K0t: f rows -> transposed words.  One warp per slab, lane = shot.
+// K0t: f rows -> transposed words.  One warp per slab, lane = shot; a block of eight slabs writes each row as one sector.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) transpose_in_kernel(const uint32_t* __restrict__ blob, const uint64_t* __restrict__ f,
                                                            long long B, int n_slabs, int slab_cap, uint32_t* __restrict__ xt) {
-  const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (warp >= n_slabs) return;
+  __shared__ uint32_t tile[32][9];  // [row][slab of the block]: rows leave as 32-byte bursts of eight slabs
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slab0 = (int)blockIdx.x * 8, warp = slab0 + wl;
   const long long row = (long long)warp * 32 + lane;
-  const bool active = row < B;
+  const bool active = warp < n_slabs && row < B;
   const int wf = (int)blob[H_WF64];
   const uint32_t* __restrict__ fsel = blob + blob[H_OFF_FSEL];
   const uint32_t* __restrict__ comp_tab = blob + blob[H_OFF_COMP];
@@ -74,7 +74,11 @@ __global__ void __launch_bounds__(256) transpose_in_kernel(const uint32_t* __res
       const uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
       if (lane == j) mine = word;
     }
-    if (lane < lim) xt[(size_t)(i0 + lane) * slab_cap + warp] = mine;
+    tile[lane][wl] = mine;
+    __syncthreads();
+    const int r = threadIdx.x >> 3, c = threadIdx.x & 7;
+    if (r < lim && slab0 + c < n_slabs) xt[(size_t)(i0 + r) * slab_cap + slab0 + c] = tile[r][c];
+    __syncthreads();
   }
 }
 

@@ -1,15 +1,23 @@
-// MODE_SLICED pipeline: bit-sliced evaluation, 32 shots per thread.
+// MODE_SLICED pipeline: the default sampling path, bit-sliced over shots.
 //
-//   K0t transpose_in_kernel   packed f rows            -> XT[param row][slab]   (one 32-bit word = 32 shots)
-//   K1s sample_sliced_kernel  XT + g (TMA-staged)      -> OT[draw][slab]        (bit-sliced output bits)
-//   K2a assemble_out_kernel   OT + direct bits of f    -> packed output rows
-//   K1c norm_check_kernel     shot 0 re-evaluated with the per-row evaluator (needs the companion fast/faithful blob)
+//   K0t transpose_in_kernel     packed f rows            -> XT[param row][slab]   (one 32-bit word = 32 shots)
+//   K1s sample_sliced_kernel    XT + g (TMA-staged)      -> OT[draw][slab]        (bit-sliced output bits)
+//   K2a assemble_out_kernel     OT + direct bits of f    -> packed output rows
+//   K1c norm_check_fast_kernel  shot 0 re-evaluated on the companion per-row blob (norm_check_kernel: sequential fallback)
 //
-// K1s: a thread owns a slab of 32 shots.  Its parameter matrix lives transposed in shared memory (a private column
-// per thread: row i = bit i of the 32 shots), so the GF(2) contraction of a term for all 32 shots is the XOR of the
-// rows its mask selects -- no popcount, cost proportional to the mask weight.  The exponents of the monoid element
-// w^a (1+sqrt2)^b are accumulated as bit-planes; only the decode of a graph's value, the sum over graphs and the
-// draw run per shot (fully unrolled over the slab, accumulators in registers).  Record format: pack_sliced.py.
+// What K1s replaces in the reference (all file:line relative to /root/reference/src/tsim):
+//   * the chain rule over the outputs of a component, `_sample_component` (sampler.py:45-81): level k evaluates
+//     |E_k(f, m_<k, 1)|, draws bit k with jax.random.bernoulli on the in-batch shot index (threefry, sampler.py:74-75),
+//     keeps prev = bit ? p1 : prev - p1; components in program order with the key threaded through (sampler.py:134-148);
+//   * `evaluate` (compile/evaluate.py:33-59): per graph, the product of the four term families (compile/terms.py:56-73
+//     node phases, :94-107 half-pi phases, :125-144 pi products, :164-187 phase pairs) times the prefactor, summed over
+//     graphs -- exactly (Z[w] fixed point, core/exact_scalar.py:52-137) or, with approximate float factors, as a
+//     sequential complex64 sum in graph order (evaluate.py:56-59);
+//   * `matmul_gf2` (utils/linalg.py:81-102): every parity <mask, x> mod 2.
+// Here a parity for 32 shots is the XOR of the rows of the transposed parameter matrix that the mask names (no GEMM, no
+// popcount); the families' monoid exponents (pack_fast.py) accumulate as bit-planes; a graph's value times its prefactor
+// is looked up in a decode table built at pack time (pack_sliced.py) with the reference's float32 operation order, so
+// sums, |amp| and draws see the same bits as the per-row kernels and the oracle.  Record format: pack_sliced.py.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -1,38 +1,44 @@
-"""MODE_SLICED records: the same monoid arithmetic as MODE_FAST, evaluated bit-sliced.
+"""MODE_SLICED records: the same monoid arithmetic as MODE_FAST, evaluated bit-sliced over shots.
 
-In MODE_SLICED one thread owns a *slab* of 32 shots.  The slab's parameter matrix is kept transposed
-(row i = bit i of the 32 shots), so a term's GF(2) contraction for all 32 shots is the XOR of the rows
-selected by its mask -- no popcount, and a cost proportional to the mask's weight.  The exponents of the
-monoid element ``w^a (1+sqrt2)^b`` (see ``pack_fast.py``) are accumulated as bit-planes (3 planes for
-``a``, a bit-sliced counter for ``b``, one plane for "some factor vanished"); only the final decode of
-a graph's value and the sum over graphs run per shot.
+A *slab* is 32 shots; its parameter matrix is kept transposed (row i = bit i of the 32 shots), so a term's GF(2)
+contraction (``utils/linalg.py:81-102`` in the reference) for all 32 shots is the XOR of the rows selected by its mask --
+no popcount, and a cost proportional to the mask's weight.  The exponents of the monoid element ``w^a (1+sqrt2)^b``
+(see ``pack_fast.py``; term families ``compile/terms.py:56-187``) are accumulated as bit-planes (3 planes for ``a``, a
+bit-sliced counter for ``b``, one plane for "some factor vanished").
 
 The planes of a graph form an index ``a | cnt << 3 | pair parities << (3 + nb)`` into a per-graph *decode table*
 built here at pack time: entry = the graph's contribution to the level sum for that index -- ``(re, im)`` float32 of
-``to_complex(value) * approximate_floatfactor * 2^power2`` in the approximate branch (same op order as the per-row
-kernels, so the bits are identical), or the four int32 coefficients of ``value << shift`` in the exact branch.  The
-device therefore never decodes a monoid element; per shot and graph it gathers the index bits and adds one entry.
+``to_complex(value) * approximate_floatfactor * 2^power2`` in the approximate branch (``compile/evaluate.py:56-59``; same
+op order as the per-row kernels and the oracle, so the bits are identical), or the four int32 coefficients of
+``value << shift`` in the exact branch (``:52-54``).  The device therefore never decodes a monoid element; per shot and
+graph it gathers the index bits and adds one entry.
+
+Pack-time algebra: every contribution that flips the top bit of ``a`` linearly in a parity (da & 4 of node / half-pi
+terms, the cross terms ``pc phi' + fc psi'`` of the pi family's constants) is merged into one mask per graph (XOR of the
+masks); half-pi terms are then ``a += 2 p``.  A graph with more general (odd-odd) phase pairs than the table index can
+hold is split into variants, one per (pa, pb) combination of the excess pairs, gated so that exactly one contributes.
 
 Chunk (the unit of the TMA stage ring) = directory (record offset of every graph, padded to 4 words) | graph
 records | decode tables.  All offsets are in words relative to the chunk start.
 
 Graph record (uint32 words):
 
-    [0]  n_terms | n_general_pairs << 16
+    [0]  words of the term stream | n_general_pairs (in the table index) << 16
     [1]  n_index_bits | n_b_planes << 8
     [2]  offset of the decode table (filled in when the chunk is assembled)
     [3]  record words
     [4..7] zero (the decode entry of a shot whose value vanished)
-    then the block stream ([0] low half = its length in words).  A block computes one parity (see ``_block``) and applies
-    an op to it:
-        FIRST    keep the parity as q (first half of a two-parity term)
+    then the term stream as typed runs (``_emit_runs``): LIN / LIN2 / PI / PAIR items with straight-line parities of
+    8 / 12 / 16 rows, and a generic block stream (``_block``) for heavier masks.  Ops:
         LIN      params da (3 bits) | bmode << 3 (1: count p, 2: count ~p) | zmode << 5 (1: Z |= p, 2: Z |= ~p)
         PI       A2 ^= q & p
         PAIRGEN  params slot: (q, p) become index planes of the decode table
         PAIRMON  params: for v in (q, p, q & p): da_v (3 bits), db_v + 3 (3 bits); bits 18-21 truth table of the
                  vanishing combinations (bit q + 2 p)
+        FIRST    (generic stream only) keep the parity as q, the first half of a two-parity term
 
-Row indices: parameter i -> row i; row ``one_row`` is all ones (constants of the pi family), ``zero_row`` all zeros.
+Row indices (8 bits, four per word): parameter i -> row i; ``zero_row`` is all zeros (padding); ``one_row`` is all ones
+(kept for generic use: the pi constants are folded away at pack time).
 """
 
 from __future__ import annotations

@@ -200,8 +200,11 @@ def run_gpu(args):
         # memory); the launch plan leaves 8 SMs free.  Eight NCCL channels make the all-gather fit into those SMs so that
         # it overlaps the next step's kernel instead of queueing behind it (N = 8: 7.0e9 -> 7.7e9 shots/s).
         os.environ.setdefault("NCCL_MAX_NCHANNELS", "8")
-        if os.environ.get("NCCL_DEBUG", "VERSION") == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints one JSON line
+        # NCCL prints its version banner on stdout when the first communicator comes up: send fd 1 to stderr until the
+        # warm-up is over, so that rank 0's stdout carries the one JSON line and nothing else
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0:
         build()
@@ -250,6 +253,9 @@ def run_gpu(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms, lib_ms = [], []

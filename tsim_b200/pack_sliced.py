@@ -318,7 +318,13 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int, 
             two(OP_PAIRMON, extra, r1, r2)
 
         if m4:
-            terms.append(("lin", 4, sorted(m4)))
+            # A2 ^= parity(m4) is linear, so a heavy merged mask goes out as pieces of at most 16 rows: they ride the
+            # straight-line LIN runs instead of the generic block stream
+            rows4 = sorted(m4)
+            n_pieces = (len(rows4) + 15) // 16
+            per = (len(rows4) + n_pieces - 1) // n_pieces
+            for i in range(0, len(rows4), per):
+                terms.append(("lin", 4, rows4[i : i + per]))
         if units > 31:
             raise _Unsupported("b counter needs more than 5 planes")
         nb = max(1, units.bit_length())

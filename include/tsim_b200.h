@@ -108,7 +108,8 @@ int tsb_pack_f_device(tsb_program* p, const uint8_t* d_bytes, int64_t B, uint64_
 int tsb_unpack_out_device(tsb_program* p, const uint64_t* d_packed, int64_t B, uint8_t* d_bytes, void* stream);
 
 /* device time (ms, CUDA events on the launch stream) of the sampling kernel launches of the last
- * tsb_sample_device / tsb_sample_host call, and how many launches that was */
+ * tsb_sample_device / tsb_sample_host call, and how many launches that was.  After tsb_sample_device on a bit-sliced
+ * program the interval is the sampling kernel alone (sample_sliced_kernel, without the transpose / assemble helpers). */
 float tsb_last_kernel_ms(tsb_program* p, int* n_launches);
 
 /* ---- K5: error-mechanism sampler on the device (statistical parity with ChannelSampler.sample,

@@ -379,12 +379,14 @@ def run_gpu(args):
     peak, peak_kind = measured_peaks()
     alg_bytes = dp.packed.g_bytes + shots * 8 * (wf + wo)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, ncu_pipes = None, None
     kernel_name = "sample_sliced_kernel" if info["mode"] == 2 else "sample_kernel"
     tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(tpath) and args.workload == WORKLOAD and shots == 1_000_000:
         try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on this workload
-            traffic = json.load(open(tpath)).get(kernel_name, {}).get("dram_bytes_per_launch")
+            entry = json.load(open(tpath)).get(kernel_name, {})
+            traffic = entry.get("dram_bytes_per_launch")
+            ncu_pipes = entry.get("ncu_pipes")
         except Exception:
             traffic = None
     roofline = {
@@ -399,6 +401,8 @@ def run_gpu(args):
         "kernel_ms": k_ms,
         "step_ms_isolated": step_ms_isolated,
         "algorithmic_bytes": int(alg_bytes),
+        # the ceilings that actually bind this kernel (issue slots, shared-memory wavefronts), from the committed ncu capture
+        "ncu_pipes": ncu_pipes,
         "note": "shared-memory / issue bound by construction (about 2e4 instructions and 150 shared-memory word reads per shot vs 16 B of mandatory HBM traffic); see DESIGN.md",
     }
 

@@ -146,3 +146,23 @@ def test_auto_mode_prefers_sliced_then_rowwise():
     lv.prefactor.floatfactor[:] = 1 << 29
     prog = _one_level_program(lv, 6)
     assert PK.pack_program(prog).mode == PK.MODE_FAITHFUL
+
+
+def test_headline_program_all_levels_bit_identical_to_oracle():
+    """The benchmark program (cfg2 shape, approximate branch): decode tables + plane arithmetic of every level."""
+    from tsim_b200.synthetic import synthetic_program
+
+    prog = synthetic_program("cfg2_distill35")
+    pp = PK.pack_program(prog)
+    assert pp.mode == PK.MODE_SLICED
+    rng = np.random.default_rng(1)
+    comp = prog.components[0]
+    F = len(comp.f_selection)
+    for k, lv in enumerate(comp.compiled_scalar_graphs):
+        xs = (rng.random((24, F + k)) < 0.2).astype(np.uint8)
+        xs[0] = 0
+        xs[1] = 1
+        got = sliced_model.evaluate_level(pp, 0, k, xs)
+        re, im = E.evaluate_parts(lv, xs)
+        for s, g in enumerate(got):
+            assert np.float32(g[1]).tobytes() == re[s].tobytes() and np.float32(g[2]).tobytes() == im[s].tobytes(), (k, s)

@@ -375,7 +375,30 @@ class CompiledMeasurementSampler(_CompiledSamplerBase):
 
 
 def _packed_columns(rows: np.ndarray, lo: int, hi: int) -> np.ndarray:
-    """Columns ``[lo, hi)`` of packed ``uint64[B, W]`` rows as ``np.packbits(..., bitorder="little")`` bytes."""
+    """Columns ``[lo, hi)`` of packed ``uint64[B, W]`` rows as ``np.packbits(..., bitorder="little")`` bytes.
+
+    Up to 64 columns (the detector / observable split of a typical program) are cut out with contiguous word
+    operations and one narrowing cast; wider ranges take the word-by-word form."""
+    B, W = rows.shape
+    n = hi - lo
+    nb = (n + 7) // 8
+    if n <= 0:
+        return np.zeros((B, 0), dtype=np.uint8)
+    if n > 64:
+        return _packed_columns_words(rows, lo, hi)
+    w, sh = divmod(lo, 64)
+    v = rows[:, w] >> np.uint64(sh) if sh else rows[:, w]
+    if sh and sh + n > 64 and w + 1 < W:
+        v = v | (rows[:, w + 1] << np.uint64(64 - sh))
+    if n < 64:
+        v = v & np.uint64((1 << n) - 1)
+    width = 1 if nb <= 1 else 2 if nb <= 2 else 4 if nb <= 4 else 8
+    out = v.astype({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[width]).view(np.uint8).reshape(B, width)
+    return out if nb == width else np.ascontiguousarray(out[:, :nb])
+
+
+def _packed_columns_words(rows: np.ndarray, lo: int, hi: int) -> np.ndarray:
+    """General form of ``_packed_columns`` for column ranges that straddle more than eight bytes."""
     B, W = rows.shape
     n = hi - lo
     n_words = max(1, (n + 63) // 64)

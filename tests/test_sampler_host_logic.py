@@ -215,3 +215,22 @@ def test_probability_of_matches_closed_form():
         sp.probability_of(state, batch_size=0)
     with pytest.raises(ValueError):
         sp.probability_of(np.zeros(3), batch_size=4)
+
+
+def test_packed_column_slicing_matches_packbits():
+    """`_packed_columns` (bit_packed=True path) == np.packbits of the bool columns, for any range and row width."""
+    from tsim_b200 import sampler as S
+
+    rng = np.random.default_rng(0)
+    for W, n_out in ((1, 20), (1, 64), (2, 100), (3, 160), (2, 128)):
+        bits = rng.integers(0, 2, size=(257, n_out)).astype(bool)
+        pk = np.packbits(bits, axis=1, bitorder="little")
+        tmp = np.zeros((257, 8 * W), np.uint8)
+        tmp[:, : pk.shape[1]] = pk
+        rows = tmp.view(np.uint64).copy()
+        for _ in range(120):
+            lo = int(rng.integers(0, n_out + 1))
+            hi = int(rng.integers(lo, n_out + 1))
+            want = np.packbits(bits[:, lo:hi], axis=1, bitorder="little")
+            got = S._packed_columns(rows, lo, hi)
+            assert got.dtype == np.uint8 and got.shape == want.shape and np.array_equal(got, want), (W, n_out, lo, hi)

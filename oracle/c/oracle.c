@@ -96,6 +96,46 @@ static int parity(const uint32_t* x, const uint32_t* m, int W) {
   return __builtin_popcount(t) & 1;
 }
 
+/* One graph's exact product T_g = N * U[phase] * Pp * ff (evaluate.py:40-50) for parameter vector x[W]; advances *rp
+ * past the graph's record and hands back the prefactor's power2 and approximate float factor. */
+static zw graph_term(const uint32_t** rp, const uint32_t* x, int W, int A, int H, int C, int D, int32_t* Tp, int32_t* power2,
+                     float* are, float* aim) {
+  const uint32_t* r = *rp;
+  zw N = {{1,0,0,0}}; int32_t Np = 0;
+  for (int j = 0; j < A; ++j, r += W + 1) {
+    int par = parity(x, r, W); uint32_t ctl = r[W];
+    zw f = {{1,0,0,0}};
+    if (ctl & 8u) { int k = ((par << 2) + (int)ctl) & 7; for (int i = 0; i < 4; ++i) f.c[i] = (uint32_t)(UNIT[k][i] + (i == 0)); }
+    if (j == 0) N = f; else { N = zw_mul(N, f); reduce1(&N, &Np); }
+  }
+  if (A > 0) fixpoint(&N, &Np);
+  int h = 0;
+  for (int j = 0; j < H; ++j, r += W + 1) h += parity(x, r, W) * (int)(r[W] & 7u);
+  int e = 0;
+  for (int j = 0; j < C; ++j, r += 2 * W + 1) {
+    uint32_t cst = r[2 * W];
+    e ^= (parity(x, r, W) ^ (int)(cst & 1u)) & (parity(x, r + W, W) ^ (int)((cst >> 1) & 1u));
+  }
+  zw Pp = {{1,0,0,0}}; int32_t Pq = 0;
+  for (int j = 0; j < D; ++j, r += 2 * W + 1) {
+    uint32_t ctl = r[2 * W];
+    zw f = {{1,0,0,0}};
+    if (ctl & 64u) {
+      int a = ((int)(ctl & 7u) + 4 * parity(x, r, W)) & 7, b = ((int)((ctl >> 3) & 7u) + 4 * parity(x, r + W, W)) & 7, cc = (a + b) & 7;
+      for (int i = 0; i < 4; ++i) f.c[i] = (uint32_t)((i == 0) + UNIT[a][i] + UNIT[b][i] - UNIT[cc][i]);
+    }
+    if (j == 0) Pp = f; else { Pp = zw_mul(Pp, f); reduce1(&Pp, &Pq); }
+  }
+  if (D > 0) fixpoint(&Pp, &Pq);
+  int ph = (h + 4 * e + (int)r[0]) & 7;
+  zw U, ff; for (int i = 0; i < 4; ++i) { U.c[i] = (uint32_t)UNIT[ph][i]; ff.c[i] = r[1 + i]; }
+  *power2 = (int32_t)r[5]; memcpy(are, &r[6], 4); memcpy(aim, &r[7], 4);
+  r += PREFACTOR_WORDS;
+  *rp = r;
+  *Tp = Np + Pq;
+  return zw_mul(zw_mul(zw_mul(N, U), Pp), ff);
+}
+
 /* |evaluate(level)| for one parameter vector x[W] */
 static float eval_level(const uint32_t* blob, const uint32_t* lvl, const uint32_t* x, int W) {
   const uint32_t* chunk_tab = blob + blob[H_OFF_CHUNK];
@@ -107,38 +147,8 @@ static float eval_level(const uint32_t* blob, const uint32_t* lvl, const uint32_
     const uint32_t* r = data + chunk_tab[c * CHUNK_WORDS];
     int ng = (int)chunk_tab[c * CHUNK_WORDS + 2];
     for (int g = 0; g < ng; ++g) {
-      zw N = {{1,0,0,0}}; int32_t Np = 0;
-      for (int j = 0; j < A; ++j, r += W + 1) {
-        int par = parity(x, r, W); uint32_t ctl = r[W];
-        zw f = {{1,0,0,0}};
-        if (ctl & 8u) { int k = ((par << 2) + (int)ctl) & 7; for (int i = 0; i < 4; ++i) f.c[i] = (uint32_t)(UNIT[k][i] + (i == 0)); }
-        if (j == 0) N = f; else { N = zw_mul(N, f); reduce1(&N, &Np); }
-      }
-      if (A > 0) fixpoint(&N, &Np);
-      int h = 0;
-      for (int j = 0; j < H; ++j, r += W + 1) h += parity(x, r, W) * (int)(r[W] & 7u);
-      int e = 0;
-      for (int j = 0; j < C; ++j, r += 2 * W + 1) {
-        uint32_t cst = r[2 * W];
-        e ^= (parity(x, r, W) ^ (int)(cst & 1u)) & (parity(x, r + W, W) ^ (int)((cst >> 1) & 1u));
-      }
-      zw Pp = {{1,0,0,0}}; int32_t Pq = 0;
-      for (int j = 0; j < D; ++j, r += 2 * W + 1) {
-        uint32_t ctl = r[2 * W];
-        zw f = {{1,0,0,0}};
-        if (ctl & 64u) {
-          int a = ((int)(ctl & 7u) + 4 * parity(x, r, W)) & 7, b = ((int)((ctl >> 3) & 7u) + 4 * parity(x, r + W, W)) & 7, cc = (a + b) & 7;
-          for (int i = 0; i < 4; ++i) f.c[i] = (uint32_t)((i == 0) + UNIT[a][i] + UNIT[b][i] - UNIT[cc][i]);
-        }
-        if (j == 0) Pp = f; else { Pp = zw_mul(Pp, f); reduce1(&Pp, &Pq); }
-      }
-      if (D > 0) fixpoint(&Pp, &Pq);
-      int ph = (h + 4 * e + (int)r[0]) & 7;
-      zw U, ff; for (int i = 0; i < 4; ++i) { U.c[i] = (uint32_t)UNIT[ph][i]; ff.c[i] = r[1 + i]; }
-      int32_t power2 = (int32_t)r[5]; float are, aim; memcpy(&are, &r[6], 4); memcpy(&aim, &r[7], 4);
-      r += PREFACTOR_WORDS;
-      zw T = zw_mul(zw_mul(zw_mul(N, U), Pp), ff);
-      int32_t Tp = Np + Pq;
+      int32_t Tp, power2; float are, aim;
+      zw T = graph_term(&r, x, W, A, H, C, D, &Tp, &power2, &are, &aim);
       if (!approx) {
         if (!started) { S = T; Sp = Tp + power2; started = 1; } else add_p(&S, &Sp, T, Tp + power2);
       } else {
@@ -156,6 +166,66 @@ static float eval_level(const uint32_t* blob, const uint32_t* lvl, const uint32_
   return cabs_xla(re, im);
 }
 
+/* ---- float64 "truth" and an alternative float32 lowering, for the margin census (tso_census) -------------------
+ * truth: every graph's exact Z[w] value converted to complex double (error ~1e-16 relative), times the stored
+ *        complex64 factor widened to double, times 2^power2, summed in double; |.| by hypot.
+ * alt:   a different but equally legitimate float32 lowering of evaluate.py:56-59 -- pairwise (tree) reduction over
+ *        the graphs, FMA-contracted complex product, |z| = sqrtf(re*re + im*im) -- to count how many draws depend on
+ *        the choices XLA is free to make. */
+typedef struct { double re, im; } cd;
+static cd zw_to_cd(zw c, int32_t p) {
+  const double s = 0.70710678118654752440;
+  double c0 = (double)(int32_t)c.c[0], c1 = (double)(int32_t)c.c[1], c2 = (double)(int32_t)c.c[2], c3 = (double)(int32_t)c.c[3];
+  cd z; z.re = ldexp(c0 + (c1 + c3) * s, p); z.im = ldexp(c2 + (c1 - c3) * s, p);
+  return z;
+}
+#define CENSUS_MAXG 4096
+static float tree_sum(const float* v, int n) {  /* pairwise reduction */
+  if (n <= 0) return 0.0f;
+  if (n == 1) return v[0];
+  int m = n / 2;
+  volatile float a = tree_sum(v, m), b = tree_sum(v + m, n - m);
+  return a + b;
+}
+static void eval_level_census(const uint32_t* blob, const uint32_t* lvl, const uint32_t* x, int W, double* p64, float* palt) {
+  const uint32_t* chunk_tab = blob + blob[H_OFF_CHUNK];
+  const uint32_t* data = blob + blob[H_OFF_DATA];
+  const int G = (int)lvl[0], A = (int)lvl[2], H = (int)lvl[3], C = (int)lvl[4], D = (int)lvl[5], approx = lvl[6] & 1;
+  *p64 = 0.0; *palt = 0.0f;
+  if (G == 0) return;
+  double sre = 0.0, sim = 0.0;
+  static __thread float tr[CENSUS_MAXG], ti[CENSUS_MAXG];
+  int n = 0;
+  zw S = {{0,0,0,0}}; int32_t Sp = 0; int started = 0;
+  for (uint32_t c = lvl[7]; c < lvl[7] + lvl[8]; ++c) {
+    const uint32_t* r = data + chunk_tab[c * CHUNK_WORDS];
+    int ng = (int)chunk_tab[c * CHUNK_WORDS + 2];
+    for (int g = 0; g < ng; ++g) {
+      int32_t Tp, power2; float are, aim;
+      zw T = graph_term(&r, x, W, A, H, C, D, &Tp, &power2, &are, &aim);
+      cd z = zw_to_cd(T, Tp);
+      if (approx) {
+        double ur = z.re * (double)are - z.im * (double)aim, ui = z.re * (double)aim + z.im * (double)are;
+        sre += ldexp(ur, power2); sim += ldexp(ui, power2);
+        float tre, tim; to_complex(T, Tp, &tre, &tim);
+        float pw = pow2f(power2);
+        float ure = fmaf(tre, are, -(tim * aim)), uim = fmaf(tre, aim, tim * are);
+        if (n < CENSUS_MAXG) { tr[n] = ure * pw; ti[n] = uim * pw; ++n; }
+      } else {
+        sre += ldexp(z.re, power2); sim += ldexp(z.im, power2);
+        if (!started) { S = T; Sp = Tp + power2; started = 1; } else add_p(&S, &Sp, T, Tp + power2);
+      }
+    }
+  }
+  *p64 = hypot(sre, sim);
+  float are_, aim_;
+  if (approx) {
+    are_ = tree_sum(tr, n); aim_ = tree_sum(ti, n);
+  } else {
+    fixpoint(&S, &Sp); to_complex(S, Sp, &are_, &aim_);
+  }
+  *palt = sqrtf(fmaf(are_, are_, aim_ * aim_));
+}
 static void derive_subkeys(uint32_t k0, uint32_t k1, int n, uint32_t* out) {
   for (int j = 0; j < n; ++j) {
     uint32_t a0 = 0, a1 = 0, b0 = 0, b1 = 1;
@@ -221,3 +291,77 @@ int tso_sample(const uint32_t* blob, const uint8_t* f, int64_t B, int64_t shot_o
   return 0;
 }
 
+
+/* Margin census of the draws of rows [0, B): the float32 path above decides the bits (so prefixes are the reference
+ * path's), and every draw is re-judged with the float64 truth and with the alternative float32 lowering.
+ *   stats[0] draws            stats[1] draws with |u - q32| <= tol * q32 ("margin draws")
+ *   stats[2] draws OUTSIDE the margin whose bit differs under float64 (must be 0 for the margin to mean anything)
+ *   stats[3] draws whose bit differs under float64 (all inside the margin if stats[2] == 0)
+ *   stats[4] draws whose bit differs under the alternative float32 lowering
+ *   stats[5] draws with a non-finite or non-positive ratio (degenerate: prev == 0 etc.), not judged
+ *   stats[6], stats[7]: as stats[1], stats[2] for the wider tolerance tol_wide
+ * maxrel[0]: max |q32 - q64| / q64 over judged draws; maxrel[1]: the same for the alternative lowering. */
+int tso_census(const uint32_t* blob, const uint8_t* f, int64_t B, int64_t shot_offset, uint32_t k0, uint32_t k1, double tol,
+               double tol_wide, int64_t* stats, double* maxrel) {
+  if (blob[H_MODE] != 0u || blob[H_W] > MAXW) return -1;
+  const int W = (int)blob[H_W], num_f = (int)blob[H_NUM_F];
+  const int n_comp = (int)blob[H_N_COMP], n_draws = (int)blob[H_N_DRAWS];
+  const uint32_t* comp_tab = blob + blob[H_OFF_COMP];
+  const uint32_t* level_tab = blob + blob[H_OFF_LEVEL];
+  const uint32_t* fsel = blob + blob[H_OFF_FSEL];
+  for (uint32_t i = 0; i < blob[H_N_LEVELS]; ++i)
+    if (level_tab[i * LEVEL_WORDS] > CENSUS_MAXG) return -2;
+  uint32_t* subkeys = (uint32_t*)malloc(8 * (size_t)(n_draws > 0 ? n_draws : 1));
+  derive_subkeys(k0, k1, n_draws, subkeys);
+  for (int i = 0; i < 8; ++i) stats[i] = 0;
+  maxrel[0] = maxrel[1] = 0.0;
+  for (int64_t s = 0; s < B; ++s) {
+    const uint8_t* fr = f + s * num_f;
+    const uint64_t shot = (uint64_t)(shot_offset + s);
+    for (int ci = 0; ci < n_comp; ++ci) {
+      const uint32_t* comp = comp_tab + ci * COMP_WORDS;
+      const int F = (int)comp[0], n_c = (int)comp[1], first_draw = (int)comp[3];
+      const uint32_t* sel = fsel + comp[2];
+      uint32_t x[MAXW]; memset(x, 0, sizeof x);
+      for (int i = 0; i < F; ++i) x[i >> 5] |= (uint32_t)(fr[sel[i]] & 1u) << (i & 31);
+      float prev = 0.0f, prev_alt = 0.0f; double prev64 = 0.0;
+      for (int k = 0; k <= n_c; ++k) {
+        const uint32_t* lvl = level_tab + (comp[4] + k) * LEVEL_WORDS;
+        const int pos = F + k - 1;
+        if (k > 0) x[pos >> 5] |= 1u << (pos & 31);
+        float p1 = eval_level(blob, lvl, x, W), p1_alt; double p1_64;
+        eval_level_census(blob, lvl, x, W, &p1_64, &p1_alt);
+        if (k == 0) { prev = p1; prev64 = p1_64; prev_alt = p1_alt; continue; }
+        float u = uniform_f32(subkeys[2*(first_draw+k-1)], subkeys[2*(first_draw+k-1)+1], shot);
+        volatile float q = p1 / prev;
+        int bit = u < q;
+        double q64 = p1_64 / prev64;
+        volatile float qa = p1_alt / prev_alt;
+        stats[0] += 1;
+        if (!(q64 > 0.0) || !isfinite(q64) || !(q > 0.0f) || !isfinite((double)q)) {
+          /* degenerate draw (vanishing marginal on this prefix): nothing to judge unless the two disagree on the bit */
+          stats[5] += 1;
+          if (bit != ((double)u < q64)) stats[3] += 1;
+        } else {
+          int in_margin = fabs((double)u - (double)q) <= tol * (double)q;
+          int bit64 = (double)u < q64;
+          int in_wide = fabs((double)u - (double)q) <= tol_wide * (double)q;
+          if (in_margin) stats[1] += 1;
+          if (in_wide) stats[6] += 1;
+          if (bit64 != bit) { stats[3] += 1; if (!in_margin) stats[2] += 1; if (!in_wide) stats[7] += 1; }
+          if ((u < qa) != bit) stats[4] += 1;
+          double rel = fabs((double)q - q64) / q64, rela = fabs((double)qa - q64) / q64;
+          if (rel > maxrel[0]) maxrel[0] = rel;
+          if (rela > maxrel[1]) maxrel[1] = rela;
+        }
+        volatile float rest = prev - p1; volatile float rest_alt = prev_alt - p1_alt;
+        prev = bit ? p1 : rest;
+        prev_alt = bit ? p1_alt : rest_alt;
+        prev64 = bit ? p1_64 : prev64 - p1_64;
+        if (!bit) x[pos >> 5] &= ~(1u << (pos & 31));
+      }
+    }
+  }
+  free(subkeys);
+  return 0;
+}

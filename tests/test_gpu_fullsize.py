@@ -18,7 +18,7 @@ def cfg2(request):
     return prog, DeviceProgram(prog, mode=request.param)
 
 
-def test_million_shots_deterministic_sharded_and_spot_checked(cfg2):
+def test_million_shots_deterministic_sharded_and_fully_checked(cfg2):
     prog, dp = cfg2
     B = 1_000_000
     cs = ChannelSampler.from_bit_probs(noise_probs(prog.infer_num_f()), seed=12345)
@@ -31,9 +31,15 @@ def test_million_shots_deterministic_sharded_and_spot_checked(cfg2):
     cuts = [0, 1, 100_003, 250_000, 499_999, 500_512, 777_777, 999_999, B]
     parts = [dp.sample(f[lo:hi], key, shot_offset=lo, packed_out=True)[0] for lo, hi in zip(cuts[:-1], cuts[1:])]
     assert np.array_equal(np.concatenate(parts), a)
-    # spot check against the oracle on three windows of the batch (RNG counters = in-batch indices)
+    # every one of the 10^6 shots against the C restatement of the oracle (all host cores, a few seconds), and three
+    # windows against the NumPy oracle itself (RNG counters = in-batch indices)
+    from oracle import cport
+
     bits = np.unpackbits(a.view(np.uint8), axis=1, bitorder="little", count=prog.num_outputs).astype(bool)
     fb = np.unpackbits(f.view(np.uint8), axis=1, bitorder="little", count=prog.infer_num_f())
+    want_all, want_dev = cport.sample_program(prog, fb, key, return_deviations=True, threads=cport.max_threads())
+    assert np.array_equal(bits, want_all), f"{np.count_nonzero(bits != want_all)} differing bits in 10^6 shots"
+    assert np.array_equal(np.asarray(dev_a, np.float32), np.asarray(want_dev, np.float32))
     for lo in (0, 314_159, B - 1024):
         want = oracle.sample_program(prog, fb[lo : lo + 1024], key, shot_offset=lo, check_norm=False)
         assert np.array_equal(bits[lo : lo + 1024], want)
@@ -72,9 +78,10 @@ def test_other_baseline_configs_match_oracle(name, B, mode):
     want, want_dev = oracle.sample_program(prog, f[:n], (1, 1), return_deviations=True, check_norm=False)
     assert np.array_equal(got[:n], want)
     assert np.array_equal(np.asarray(dev, np.float32), np.asarray(want_dev, np.float32))
-    if name == "cfg3_surface_d5":
-        full = oracle.sample_program(prog, f, (1, 1), check_norm=False)
-        assert np.array_equal(got, full)
+    from oracle import cport
+
+    full = cport.sample_program(prog, f, (1, 1), threads=cport.max_threads())  # the whole batch, C restatement
+    assert np.array_equal(got, full)
 
 
 @pytest.mark.parametrize("approx,B", [(True, 2_200_000), (False, 700_001)])

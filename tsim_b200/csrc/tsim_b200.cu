@@ -723,8 +723,10 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
   }
   p->smem_data_off = fixed_words;
   const int smem_bytes = (int)((fixed_words + used) * 4);
+  // the attribute is per kernel function and device, not per program: always the device maximum, so that a second
+  // (smaller) program of the same (mode, W) cannot lower the limit under an earlier, larger one
   if (mode != kModeSliced)
-    CUB(cudaFuncSetAttribute((const void*)sample_fn(mode, W), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CUB(cudaFuncSetAttribute((const void*)sample_fn(mode, W), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
 
   tsb_info& in = p->info;
   in.mode = mode; in.words = W; in.num_f = (int)blob[H_NUM_F]; in.num_outputs = (int)blob[H_N_OUT];
@@ -971,7 +973,8 @@ static bool launch_norm_fast(const tsb_program* p, const tsb_program* a, float* 
   if (bytes > limit) return false;
   NormFastFn fn = staged ? norm_fast_fn<true>(W) : norm_fast_fn<false>(W);
   if (!fn) return false;
-  if (bytes > 40000 && cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return false;
+  // per function and device (not per program): raise it to the most any program may ask for
+  if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit) != cudaSuccess) return false;
   fn<<<p->info.n_components, 512, (size_t)bytes, p->side>>>(a->d_blob, p->d_row0, p->d_row0 + p->info.words_f64, d_norm_dev, max_g);
   return true;
 }

@@ -55,10 +55,17 @@ class ShardedDetectorSampler:
             n = hi - lo
             d_f = torch.empty((max(n, 1), wf), dtype=torch.int64, device=dev)
             d_out = torch.zeros((max(n, 1), wo), dtype=torch.int64, device=dev)
+            owns_shot0 = n > 0 and lo == 0  # the normalisation check (sampler.py:66-72, 149-161) belongs to in-batch shot 0
+            d_dev = torch.zeros(max(1, self.dp.info["n_components"]), dtype=torch.float32, device=dev) if owns_shot0 else None
             if n:
                 self.noise.sample_device(d_f.data_ptr(), n, shot_offset=lo, call=call, stream=stream)
-                self.dp.sample_device(d_f.data_ptr(), n, sub, d_out.data_ptr(), shot_offset=lo, stream=stream)
+                self.dp.sample_device(d_f.data_ptr(), n, sub, d_out.data_ptr(), shot_offset=lo, stream=stream,
+                                      d_norm_dev=d_dev.data_ptr() if owns_shot0 else 0)
             parts.append(gather_packed_rows(d_out[:n], batch, self.rank, self.world))
+            if owns_shot0:
+                from .sampler import check_norm_deviations
+
+                check_norm_deviations(d_dev.cpu().numpy()[: self.dp.info["n_components"]])
         out = parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
         return out[:shots]
 

@@ -318,6 +318,10 @@ def scalar_graphs_from_tsim(csg: Any) -> CompiledScalarGraphs:
 def from_tsim(program: Any, *, num_f: int | None = None) -> CompiledProgram:
     """Convert a tsim ``CompiledProgram`` (core/types.py:80-107) to NumPy."""
     if isinstance(program, CompiledProgram):
+        if num_f is not None and int(num_f) > program.infer_num_f():
+            from dataclasses import replace
+
+            return replace(program, num_f=int(num_f))  # wider f rows than the program references: columns ignored
         return program
     comps = []
     for c in program.components:

@@ -34,27 +34,37 @@ _VANISHING = (
     "as a bug at https://github.com/QuEraComputing/tsim/issues/new."
 )
 
-_device_cache: "weakref.WeakKeyDictionary[Any, DeviceProgram]" = weakref.WeakKeyDictionary()
-_device_cache_by_id: dict[int, tuple[Any, DeviceProgram]] = {}
+_device_cache: dict[tuple[int, int, str], tuple[Any, DeviceProgram]] = {}
+_DEVICE_CACHE_MAX = 16
 
 
-def device_program_for(program: Any, *, device: int = 0, mode: str = "auto") -> DeviceProgram:
-    """Upload ``program`` once per object and reuse the handle on later calls."""
+def _cache_evict(key) -> None:
+    _device_cache.pop(key, None)
+
+
+def device_program_for(program: Any, *, device: int = 0, mode: str = "auto", num_f: int | None = None) -> DeviceProgram:
+    """Upload ``program`` once per (object, device, mode) and reuse the handle on later calls.
+
+    tsim's programs are equinox modules (unhashable), so the cache is keyed on ``id`` and an entry dies with its
+    program (``weakref.finalize``) or, for objects that cannot be weakly referenced, when the cache exceeds
+    ``_DEVICE_CACHE_MAX`` entries (oldest first)."""
     if isinstance(program, DeviceProgram):
         return program
+    key = (id(program), int(device), str(mode))
+    hit = _device_cache.get(key)
+    if hit is not None and (hit[0] is None or hit[0]() is program):
+        return hit[1]
+    dp = DeviceProgram(from_tsim(program, num_f=num_f), device=device, mode=mode)
     try:
-        dp = _device_cache.get(program)
-        if dp is None:
-            dp = DeviceProgram(program, device=device, mode=mode)
-            _device_cache[program] = dp
-        return dp
-    except TypeError:  # unhashable / not weak-referenceable (e.g. an equinox module)
-        hit = _device_cache_by_id.get(id(program))
-        if hit is not None and hit[0] is program:
-            return hit[1]
-        dp = DeviceProgram(program, device=device, mode=mode)
-        _device_cache_by_id[id(program)] = (program, dp)
-        return dp
+        ref = weakref.ref(program)
+        weakref.finalize(program, _cache_evict, key)
+    except TypeError:
+        ref = None
+        dp._pin = program  # keeps id(program) from being reused while the entry lives
+    _device_cache[key] = (ref, dp)
+    while len(_device_cache) > _DEVICE_CACHE_MAX:
+        _device_cache.pop(next(iter(_device_cache)))
+    return dp
 
 
 def check_norm_deviations(devs) -> None:
@@ -71,29 +81,96 @@ def check_norm_deviations(devs) -> None:
             )
 
 
+class HostBits(np.ndarray):
+    """Result rows in (pinned) host memory.  tsim's ``copy_d2h`` asks an array where it lives before it issues a raw
+    ``cudaMemcpy`` on ``unsafe_buffer_pointer()`` (``utils/cuda_helpers.py:32-45, 120-130``): this one answers "cpu"."""
+
+    class _Cpu:
+        platform = "cpu"
+
+    def devices(self):
+        return {self._Cpu()}
+
+
 def sample_program(program: Any, f_params: Any, key: Any) -> np.ndarray:
     """Sample all outputs of a compiled program (reference ``sample_program``, sampler.py:117-167).
 
     ``program``: tsim / tsim_b200 ``CompiledProgram`` or a ``DeviceProgram``; ``f_params``: array
     ``[batch, num_f]`` of 0/1; ``key``: jax PRNG key or ``(k0, k1)``.  Returns ``bool[batch, num_outputs]``.
     """
-    dp = device_program_for(program)
     f = np.asarray(f_params)
+    # the f vector may be wider than the highest index the program references (reference: simply ignored)
+    dp = device_program_for(program, num_f=f.shape[1] if f.ndim == 2 else None)
     if dp.num_outputs == 0:
         return np.zeros((f.shape[0], 0), dtype=np.bool_)
     bits, devs = dp.sample(f, key)
     check_norm_deviations(devs)
-    return bits
+    return bits.view(HostBits)
+
+
+class _JnpShim:
+    """``jax.numpy`` as seen by ``tsim.sampler`` after :func:`install`: host results stay on the host when
+    ``_sample_batches`` concatenates its batches (sampler.py:411) instead of being uploaded by ``jnp.concatenate``."""
+
+    def __init__(self, jnp):
+        self._jnp = jnp
+
+    def __getattr__(self, name):
+        return getattr(self._jnp, name)
+
+    def concatenate(self, arrays, axis=0, **kw):
+        arrays = list(arrays)
+        if arrays and all(isinstance(a, np.ndarray) for a in arrays):
+            return np.concatenate(arrays, axis=axis).view(HostBits)
+        return self._jnp.concatenate(arrays, axis=axis, **kw)
+
+
+_installed: dict[str, Any] = {}
 
 
 def install() -> bool:
-    """Rebind ``tsim.sampler.sample_program`` to the B200 backend.  False if tsim is not importable."""
+    """Rebind ``tsim.sampler.sample_program`` to the B200 backend.  False if tsim is not importable.
+
+    The reference's ``_sample_batches`` then hands our host-resident result to ``jnp.concatenate`` and ``copy_d2h``
+    (sampler.py:411-413); both names are rebound inside ``tsim.sampler`` as well so that host rows pass through
+    untouched (no re-upload, no raw ``cudaMemcpy`` on a host pointer).  :func:`uninstall` restores all three."""
     try:
         import tsim.sampler as ts
     except Exception:
         return False
+    if _installed:
+        return True
+    _installed.update(sample_program=ts.sample_program, copy_d2h=getattr(ts, "copy_d2h", None), jnp=getattr(ts, "jnp", None))
     ts.sample_program = sample_program
+    ref_copy = _installed["copy_d2h"]
+    if ref_copy is not None:
+
+        def copy_d2h(src, *, dst=None):
+            if isinstance(src, np.ndarray):  # already on the host (page-locked pool of the backend)
+                if dst is None:
+                    return np.asarray(src)
+                dst[...] = src
+                return dst
+            return ref_copy(src, dst=dst)
+
+        ts.copy_d2h = copy_d2h
+    if _installed["jnp"] is not None:
+        ts.jnp = _JnpShim(_installed["jnp"])
     return True
+
+
+def uninstall() -> None:
+    """Undo :func:`install`."""
+    if not _installed:
+        return
+    import tsim.sampler as ts
+
+    ts.sample_program = _installed["sample_program"]
+    if _installed["copy_d2h"] is not None:
+        ts.copy_d2h = _installed["copy_d2h"]
+    if _installed["jnp"] is not None:
+        ts.jnp = _installed["jnp"]
+    _installed.clear()
 
 
 class _CompiledSamplerBase:
@@ -119,7 +196,7 @@ class _CompiledSamplerBase:
             seed = int(np.random.default_rng().integers(0, 2**30))
         # jax.random.key(seed) (sampler.py:198)
         self._key = key_words(key) if key is not None else ((int(seed) >> 32) & 0xFFFFFFFF, int(seed) & 0xFFFFFFFF)
-        self._program: CompiledProgram = from_tsim(program)
+        self._program: CompiledProgram = from_tsim(program, num_f=getattr(channel_sampler, "num_f", None))
         self._device_program = DeviceProgram(self._program, device=device, mode=mode, joint=joint)
         self._channel_sampler = channel_sampler
         self._num_detectors = int(self._program.num_detectors if num_detectors is None else num_detectors)

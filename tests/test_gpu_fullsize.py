@@ -10,7 +10,7 @@ from tsim_b200.synthetic import noise_probs, synthetic_program
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["fast", "sliced"])
+@pytest.fixture(scope="module", params=["fast", "sliced", "sliced-direct"])  # "sliced" = with its default pattern cache
 def cfg2(request):
     from tsim_b200.backend import DeviceProgram
 
@@ -65,7 +65,7 @@ def test_byte_and_packed_interfaces_agree_at_size(cfg2):
     assert np.array_equal(np.packbits(bits, axis=1, bitorder="little"), packed.view(np.uint8)[:, : (prog.num_outputs + 7) // 8])
 
 
-@pytest.mark.parametrize("mode", ["fast", "sliced"])
+@pytest.mark.parametrize("mode", ["fast", "sliced", "sliced-direct"])
 @pytest.mark.parametrize("name,B", [("cfg4_cultivation_d3", 4096), ("cfg5_distill85", 4096), ("cfg3_surface_d5", 200_000)])
 def test_other_baseline_configs_match_oracle(name, B, mode):
     from tsim_b200.backend import DeviceProgram
@@ -98,17 +98,18 @@ def test_sliced_multi_round_launches_match_per_row_kernel(approx, B):
     cs = ChannelSampler.from_bit_probs(noise_probs(nf, 2e-3), seed=3)
     f = torch.from_numpy(cs.sample_packed(B).view(np.int64)).cuda()
     outs = {}
-    for mode in ("sliced", "fast"):
+    for mode in ("sliced", "sliced-direct", "fast"):
         dp = DeviceProgram(prog, mode=mode)
         out = torch.zeros((B, dp.info["words_out64"]), dtype=torch.int64, device="cuda")
         dev = torch.zeros(max(1, dp.info["n_components"]), dtype=torch.float32, device="cuda")
         dp.sample_device(f.data_ptr(), B, (9, 1), out.data_ptr(), d_norm_dev=dev.data_ptr())
         torch.cuda.synchronize()
         outs[mode] = (out.cpu().numpy(), dev.cpu().numpy())
-        if mode == "sliced":
-            assert dp.info["mode"] == 2
-    assert np.array_equal(outs["sliced"][0], outs["fast"][0])
-    assert np.array_equal(outs["sliced"][1], outs["fast"][1])
+        if mode.startswith("sliced"):
+            assert dp.info["mode"] == 2 and (dp.pattern_cache is None) == mode.endswith("-direct")
+    for mode in ("sliced", "sliced-direct"):
+        assert np.array_equal(outs[mode][0], outs["fast"][0])
+        assert np.array_equal(outs[mode][1], outs["fast"][1])
     # and a window of it against the oracle
     lo = B - 2048
     fb = np.unpackbits(f[lo:].cpu().numpy().view(np.uint8), axis=1, bitorder="little", count=nf)

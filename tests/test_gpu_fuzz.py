@@ -57,7 +57,7 @@ def test_fuzz_all_modes(seed):
     prog, f, key = _random_case(seed)
     want, want_dev = _oracle_bits(prog, f, key)
     wd = np.asarray(want_dev, np.float32).view(np.uint32)
-    for mode in ("faithful", "fast", "sliced"):
+    for mode in ("faithful", "fast", "sliced", "sliced-direct"):
         try:
             dp = DeviceProgram(prog, mode=mode)
         except ValueError:

@@ -15,7 +15,7 @@ from tsim_b200.synthetic import noise_probs, random_level, synthetic_component, 
 
 pytestmark = pytest.mark.gpu
 
-MODES = ("faithful", "fast", "sliced")
+MODES = ("faithful", "fast", "sliced", "sliced-direct")  # "sliced" runs with its default pattern cache, "-direct" without
 
 
 def _device_program(prog, mode, **kw):
@@ -127,16 +127,16 @@ def test_cfg2_shape_matches_oracle_resident_and_streamed(mode, monkeypatch):
     key = oracle.split((0, 0))[1]
     want, want_dev = _oracle(prog, f, key)
     dp = _device_program(prog, mode)
-    assert dp.info["resident"] == (0 if mode == "sliced" else 1)  # sliced CTAs spend their shared memory on per-shot state
+    assert dp.info["resident"] == (0 if mode.startswith("sliced") else 1)  # sliced CTAs spend their shared memory on per-shot state
     got, dev = dp.sample(f, key)
     assert np.array_equal(got, want) and _dev_equal(dev, want_dev)
     # packed formats
     gotp, _ = dp.sample(pack_f_rows(f), key, packed_out=True)
     assert np.array_equal(np.unpackbits(gotp.view(np.uint8), axis=1, bitorder="little", count=prog.num_outputs).astype(bool), want)
     # same program through the streamed path (shared memory capped -> chunk ring)
-    monkeypatch.setenv("TSIM_B200_SMEM_LIMIT", str((140 if mode == "sliced" else 64) * 1024))
+    monkeypatch.setenv("TSIM_B200_SMEM_LIMIT", str((140 if mode.startswith("sliced") else 64) * 1024))
     dps = _device_program(prog, mode)
-    assert dps.info["resident"] == 0 and (mode != "sliced" or dps.info["threads"] < dp.info["threads"])
+    assert dps.info["resident"] == 0 and (not mode.startswith("sliced") or dps.info["threads"] < dp.info["threads"])
     got2, dev2 = dps.sample(f, key)
     assert np.array_equal(got2, want) and _dev_equal(dev2, want_dev)
 

@@ -6,7 +6,7 @@ from tsim_b200.backend import DeviceProgram
 from tsim_b200.synthetic import synthetic_program
 
 prog = synthetic_program("cfg2_distill35")
-dps = {m: DeviceProgram(prog, mode=m) for m in ("sliced", "fast")}
+dps = {m: DeviceProgram(prog, mode=m) for m in ("sliced-direct", "sliced", "fast")}
 for B in (1024, 8192, 32768, 65536, 131072, 200000, 262144, 524288):
     f = torch.zeros((B, 1), dtype=torch.int64, device="cuda")
     out = torch.zeros((B, 1), dtype=torch.int64, device="cuda")

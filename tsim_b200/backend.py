@@ -3,6 +3,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from typing import Any
 
@@ -11,6 +12,9 @@ import numpy as np
 from . import _lib
 from .pack import MODE_SLICED, PackedProgram, pack_program
 from .program import CompiledProgram, from_tsim
+
+
+PATTERN_CACHE_AUTO_WEIGHT = 3  # "auto": up to three flipped selected f bits per component (table capped by the library)
 
 
 def key_words(key: Any) -> tuple[int, int]:
@@ -97,11 +101,18 @@ _result_pool = PinnedPool()
 class DeviceProgram:
     """A compiled program uploaded to one GPU (``tsb_program`` handle)."""
 
-    def __init__(self, program: CompiledProgram | PackedProgram | Any, *, device: int = 0, mode: str = "auto", joint: bool = False):
+    def __init__(self, program: CompiledProgram | PackedProgram | Any, *, device: int = 0, mode: str = "auto", joint: bool = False,
+                 pattern_cache: int | None | str = "default"):
+        """``pattern_cache``: ``"default"`` = the ``TSIM_B200_PATTERN_CACHE`` environment variable (``off`` or a weight 0..3),
+        else ``"auto"`` for sliced programs (the largest weight whose table stays L2-sized) and off for per-row ones;
+        an int or ``None`` sets it explicitly.  The cache never changes sampled bits (see ``set_pattern_cache``)."""
         lib = _lib.load()
         self._lib = lib
         self.device = int(device)
         self.pattern_cache = None
+        if isinstance(mode, str) and mode.endswith("-direct"):  # e.g. "sliced-direct": the records of `mode`, no pattern cache
+            mode = mode[: -len("-direct")]
+            pattern_cache = None
         self._aux = None
         if isinstance(program, PackedProgram):
             packed = program
@@ -121,6 +132,20 @@ class DeviceProgram:
         info = _lib.TsbInfo()
         _lib.check(lib.tsb_program_info(self._h, C.byref(info)))
         self.info = info.as_dict()
+        if pattern_cache == "default":
+            env = os.environ.get("TSIM_B200_PATTERN_CACHE", "").strip().lower()
+            if env in ("off", "none", "-1"):
+                pattern_cache = None
+            elif env.isdigit():
+                pattern_cache = int(env)
+            else:
+                pattern_cache = "auto" if packed.mode == MODE_SLICED else None
+        if self.joint or self.info["n_draws"] == 0:
+            pattern_cache = None
+        if pattern_cache == "auto":
+            pattern_cache = PATTERN_CACHE_AUTO_WEIGHT
+        if pattern_cache is not None:
+            self.set_pattern_cache(int(pattern_cache))
 
     def _create(self, packed: PackedProgram):
         blob = np.ascontiguousarray(packed.blob, dtype=np.uint32)
@@ -138,23 +163,19 @@ class DeviceProgram:
         return self.info["num_outputs"]
 
     def set_pattern_cache(self, max_weight: int | None, max_entries: int = 0) -> int:
-        """Tabulate the probability trees of all selected-f patterns of weight <= ``max_weight`` (0, 1, 2;
-        ``None`` switches the cache off).  Purely a speed-up: sampled bits do not change.  Returns the table size."""
-        if self._aux is not None:
-            # the table walk belongs to the per-row kernels: while the cache is on, a sliced program samples through
-            # its per-row companion (same bits either way)
-            n = self._aux.set_pattern_cache(max_weight, max_entries)
-            self.pattern_cache = max_weight
-            return n
+        """Tabulate the probability trees ``|E_k(pattern, prefix)|`` of all selected-f patterns of weight <= ``max_weight``
+        (0..3; per component the largest weight <= ``max_weight`` whose table fits ``max_entries``; ``None`` switches the
+        cache off).  The chain rule of ``_sample_component`` (reference ``sampler.py:45-81``) is a pure function of the
+        selected f bits, so light shots walk the table and draw; the rest take the full evaluation (for a sliced program
+        K0t / K1s / K2a over the list of remaining rows).  Purely a speed-up: sampled bits do not change.  Returns the
+        table size in entries."""
         n = C.c_int64(0)
         _lib.check(self._lib.tsb_program_set_pattern_cache(self._h, -1 if max_weight is None else int(max_weight), int(max_entries), C.byref(n)))
         self.pattern_cache = max_weight
         return int(n.value)
 
     def _active(self):
-        """Handle that samples: the program itself, or its per-row companion while the pattern cache is on."""
-        if self._aux is not None and self.pattern_cache is not None:
-            return self._aux._h
+        """Handle that samples."""
         return self._h
 
     def close(self) -> None:

@@ -52,18 +52,30 @@ struct SParams {
   int rows;  // zero_row + 1
   uint4 sel;    // dp4a byte selectors {128 << 0, 128 << 8, 128 << 16, 128 << 24} (see par4)
   uint4 sel_e;  // the same with 8, the byte size of a float2 decode-table entry, instead of 128 (see sliced_phase2)
+  // optional indirection (HAS_ROWS kernels; memoised path pass 2, post-selection survivors): slot i of the launch is
+  // batch row rows[i], i < *n_rows -- the count is only known on the device, so the kernel derives n_slabs, n_groups and
+  // rounds itself.  The row index is also the shot's RNG counter (sampler.py:75: bernoulli over the whole batch).
+  const uint32_t* __restrict__ row_list;
+  const uint32_t* __restrict__ n_rows;
 };
 
 // ---------------------------------------------------------------------------------------------
 // K0t: f rows -> transposed words.  One warp per slab, lane = shot; a block of eight slabs writes each row as one sector.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) transpose_in_kernel(const uint32_t* __restrict__ blob, const uint64_t* __restrict__ f,
-                                                           long long B, int n_slabs, int slab_cap, uint32_t* __restrict__ xt) {
+                                                           long long B, int n_slabs, int slab_cap, uint32_t* __restrict__ xt,
+                                                           const uint32_t* __restrict__ row_list, const uint32_t* __restrict__ n_rows) {
   __shared__ uint32_t tile[32][9];  // [row][slab of the block]: rows leave as 32-byte bursts of eight slabs
   const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slab0 = (int)blockIdx.x * 8, warp = slab0 + wl;
-  const long long row = (long long)warp * 32 + lane;
-  const bool active = warp < n_slabs && row < B;
+  if (row_list) {  // the launch covers the worst case; the live count sits on the device
+    B = (long long)*n_rows;
+    n_slabs = (int)((B + 31) / 32);
+    if (slab0 >= n_slabs) return;
+  }
+  const long long slot = (long long)warp * 32 + lane;
+  const bool active = warp < n_slabs && slot < B;
+  const long long row = (row_list && active) ? (long long)row_list[slot] : slot;
   const int wf = (int)blob[H_WF64];
   const uint32_t* __restrict__ fsel = blob + blob[H_OFF_FSEL];
   const uint32_t* __restrict__ comp_tab = blob + blob[H_OFF_COMP];
@@ -95,12 +107,18 @@ __global__ void __launch_bounds__(256) transpose_in_kernel(const uint32_t* __res
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) assemble_out_kernel(const uint32_t* __restrict__ blob, const uint64_t* __restrict__ f,
                                                            const uint32_t* __restrict__ ot, long long B, int n_slabs, int slab_cap,
-                                                           uint64_t* __restrict__ out) {
+                                                           uint64_t* __restrict__ out, const uint32_t* __restrict__ row_list,
+                                                           const uint32_t* __restrict__ n_rows) {
   const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
+  if (row_list) {
+    B = (long long)*n_rows;
+    n_slabs = (int)((B + 31) / 32);
+  }
   if (warp >= n_slabs) return;
-  const long long row = (long long)warp * 32 + lane;
-  if (row >= B) return;
+  const long long slot = (long long)warp * 32 + lane;
+  if (slot >= B) return;
+  const long long row = row_list ? (long long)row_list[slot] : slot;
   const int wf = (int)blob[H_WF64], wo = (int)blob[H_WOUT64];
   const int n_direct = (int)blob[H_N_DIRECT], n_draws = (int)blob[H_N_DRAWS];
   const uint32_t* __restrict__ direct_tab = blob + blob[H_OFF_DIRECT];
@@ -436,9 +454,18 @@ __device__ __forceinline__ void group_sync(int grp, int nthreads) {
 
 // dynamic shared memory (32-bit words): [0,64) mbarriers | xt [ng][rows][32] | planes [ng][2][SPLIT][kPlaneRows][32] |
 // stage ring
-template <int SPLIT, bool HAS_EXACT>
+template <int SPLIT, bool HAS_EXACT, bool HAS_ROWS>
 __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_kernel(const SParams prm) {
   constexpr int SH = 32 / SPLIT;
+  int n_slabs = prm.n_slabs, n_groups = prm.n_groups, rounds = prm.rounds;
+  if constexpr (HAS_ROWS) {
+    const long long nr = (long long)*prm.n_rows;
+    n_slabs = (int)((nr + 31) / 32);
+    n_groups = (n_slabs + 31) / 32;
+    if ((int)blockIdx.x >= n_groups) return;  // this CTA owns no group in any round
+    const int gpc = (n_groups + (int)gridDim.x - 1) / (int)gridDim.x;
+    rounds = (gpc + prm.ng - 1) / prm.ng;
+  }
   typedef typename SlicedAcc<HAS_EXACT>::type Acc;
   extern __shared__ __align__(128) uint32_t smem[];
   const uint32_t* __restrict__ blob = prm.blob;
@@ -469,7 +496,7 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
   }
   __syncthreads();
 
-  const long long total_q = (long long)prm.rounds * n_chunks;
+  const long long total_q = (long long)rounds * n_chunks;
   auto issue = [&](long long q) {
     const int ch = (int)(q % n_chunks);
     const uint32_t* row = chunk_tab + ch * kChunkWords;
@@ -483,11 +510,11 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
 
   long long q = 0;
   uint32_t pbuf = 0;  // plane buffer of the current wave (double-buffered: one group barrier per wave)
-  for (int round = 0; round < prm.rounds; ++round) {
+  for (int round = 0; round < rounds; ++round) {
     const int ggrp = (round * prm.ng + grp) * (int)gridDim.x + (int)blockIdx.x;
-    const bool gactive = ggrp < prm.n_groups;  // uniform over the group's warps
+    const bool gactive = ggrp < n_groups;  // uniform over the group's warps
     const int slab = ggrp * 32 + lane;
-    const bool active = gactive && slab < prm.n_slabs;
+    const bool active = gactive && slab < n_slabs;
     const unsigned long long shot0 =
         (unsigned long long)prm.shot_offset + (unsigned long long)slab * 32ull + (unsigned long long)(w * SH);
 
@@ -560,6 +587,16 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
             if (k > 0 && active) t = pvp[s >> 2];
             pvv[s] = t.x; pvv[s + 1] = t.y; pvv[s + 2] = t.z; pvv[s + 3] = t.w;
           }
+          uint32_t rid[SH];  // HAS_ROWS: batch row (= RNG counter) of each shot of this lane's slab
+          if constexpr (HAS_ROWS) {
+            const uint4* rp = reinterpret_cast<const uint4*>(prm.row_list + (size_t)slab * 32 + w * SH);
+#pragma unroll
+            for (int s = 0; s < SH; s += 4) {
+              uint4 t = make_uint4(0u, 0u, 0u, 0u);
+              if (k > 0 && active) t = rp[s >> 2];
+              rid[s] = t.x; rid[s + 1] = t.y; rid[s + 2] = t.z; rid[s + 3] = t.w;
+            }
+          }
           uint32_t bits = 0;
 #pragma unroll
           for (int s = 0; s < SH; ++s) {
@@ -581,7 +618,9 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
               pvv[s] = p1;
             } else {
               const float pv = pvv[s];
-              const float u = uniform_f32(k0, k1, shot0 + (unsigned long long)s);
+              const unsigned long long ctr = HAS_ROWS ? (unsigned long long)prm.shot_offset + (unsigned long long)rid[s]
+                                                      : shot0 + (unsigned long long)s;
+              const float u = uniform_f32(k0, k1, ctr);
               const bool bit = u < __fdiv_rn(p1, pv);
               pvv[s] = bit ? p1 : __fsub_rn(pv, p1);
               bits |= (bit ? 1u : 0u) << s;

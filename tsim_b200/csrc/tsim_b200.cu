@@ -302,10 +302,18 @@ __global__ void pack_params_kernel(const uint8_t* __restrict__ bytes, long long 
 // (program, pattern, prefix), so it is tabulated once per program with the very same evaluator the
 // sampling kernel uses (bit-identical values); a light shot then needs only table walks + its draws.
 // Table of one component: [pattern][node], node(k, prefix) = k == 0 ? 0 : 2^(k-1) + prefix.
-// Pattern ids: 0 = no bit, 1 + i = bit i, 1 + F + j(j-1)/2 + i = bits i < j.
+// Pattern ids (combinatorial number system): 0 = no bit, 1 + i = bit i, 1 + F + C(j,2) + i = bits i < j,
+// 1 + F + C(F,2) + C(l,3) + C(j,2) + i = bits i < j < l.
 // =============================================================================================
 constexpr int kCacheMetaWords = 4;  // per component: table offset (floats), F, n_c, wmax (0xFFFFFFFF = no table)
 constexpr int kCacheMaxWords64 = 8;
+constexpr int kCacheMaxWeight = 3;
+
+__host__ __device__ inline long long choose2(long long n) { return n * (n - 1) / 2; }
+__host__ __device__ inline long long choose3(long long n) { return n * (n - 1) * (n - 2) / 6; }
+__host__ __device__ inline long long cache_patterns(long long F, int w) {
+  return 1 + (w >= 1 ? F : 0) + (w >= 2 ? choose2(F) : 0) + (w >= 3 ? choose3(F) : 0);
+}
 
 template <int W, int MODE>
 __global__ void __launch_bounds__(256) cache_build_kernel(const uint32_t* __restrict__ blob, int comp_index, int wmax,
@@ -318,17 +326,26 @@ __global__ void __launch_bounds__(256) cache_build_kernel(const uint32_t* __rest
   const uint32_t* __restrict__ comp = blob + blob[H_OFF_COMP] + comp_index * kCompWords;
   const int F = (int)comp[C_F], n_c = (int)comp[C_NC];
   const int nodes = 1 << n_c;
-  const int pid = (int)(t / nodes), node = (int)(t % nodes);
+  const long long pid = t / nodes;
+  const int node = (int)(t % nodes);
   const int k = node == 0 ? 0 : 32 - __clz(node);
   const int prefix = node == 0 ? 0 : node - (1 << (k - 1));
-  int b0 = -1, b1 = -1;
+  int b0 = -1, b1 = -1, b2 = -1;
   if (pid >= 1 && pid <= F) {
     b0 = pid - 1;
   } else if (pid > F) {
-    int t2 = pid - 1 - F, j = 1;
-    while ((j + 1) * j / 2 <= t2) ++j;
+    long long t2 = pid - 1 - F;
+    if (t2 >= choose2(F)) {
+      t2 -= choose2(F);
+      int l = 2;
+      while (choose3(l + 1) <= t2) ++l;
+      b2 = l;
+      t2 -= choose3(l);
+    }
+    int j = 1;
+    while (choose2(j + 1) <= t2) ++j;
     b1 = j;
-    b0 = t2 - j * (j - 1) / 2;
+    b0 = (int)(t2 - choose2(j));
   }
   (void)wmax;
   uint32_t x[W];
@@ -337,6 +354,7 @@ __global__ void __launch_bounds__(256) cache_build_kernel(const uint32_t* __rest
     uint32_t v = 0;
     if (b0 >= 0 && (b0 >> 5) == w) v |= 1u << (b0 & 31);
     if (b1 >= 0 && (b1 >> 5) == w) v |= 1u << (b1 & 31);
+    if (b2 >= 0 && (b2 >> 5) == w) v |= 1u << (b2 & 31);
     for (int j = 0; j < k; ++j) {  // prefix bits m_0 .. m_{k-2}, then the trying bit 1
       const int pos = F + j;
       const uint32_t bit = (j == k - 1) ? 1u : (uint32_t)((prefix >> j) & 1);
@@ -372,6 +390,7 @@ struct LightParams {
   uint32_t* __restrict__ heavy_count;
   long long B;
   long long shot_offset;
+  int shot0_heavy;  // per-row programs: in-batch shot 0 carries the norm check, so it takes the full evaluation
 };
 
 // pass 1: table walks for light shots; everything else (and shot 0, which carries the norm check) is queued
@@ -382,7 +401,7 @@ __global__ void __launch_bounds__(256) light_kernel(const LightParams prm) {
   const unsigned long long shot = (unsigned long long)(prm.shot_offset + i);
   const int wf = (int)blob[H_WF64], wo = (int)blob[H_WOUT64];
   const int n_comp = (int)blob[H_N_COMP], n_direct = (int)blob[H_N_DIRECT];
-  bool heavy = active && shot == 0ull;
+  bool heavy = active && shot == 0ull && prm.shot0_heavy;
   uint64_t fw[kCacheMaxWords64], ow[kCacheMaxWords64];
   if (active && !heavy) {
     for (int w = 0; w < wf; ++w) fw[w] = prm.f[i * wf + w];
@@ -402,17 +421,21 @@ __global__ void __launch_bounds__(256) light_kernel(const LightParams prm) {
       const uint32_t* __restrict__ meta = prm.cache_meta + ci * kCacheMetaWords;
       const int F = (int)comp[C_F], n_c = (int)comp[C_NC], wmax = (int)meta[3];
       const uint32_t* __restrict__ sel = fsel + comp[C_FSEL_OFF];
-      int wgt = 0, p0 = 0, p1 = 0;
+      int wgt = 0, p0 = 0, p1 = 0, p2 = 0;
       for (int b = 0; b < F; ++b) {
         const uint32_t fi = sel[b];
         if ((fw[fi >> 6] >> (fi & 63u)) & 1ull) {
           if (wgt == 0) p0 = b;
           else if (wgt == 1) p1 = b;
+          else if (wgt == 2) p2 = b;
           ++wgt;
         }
       }
       if (wgt > wmax) { heavy = true; break; }  // wmax == -1: no table for this component
-      const int pid = wgt == 0 ? 0 : (wgt == 1 ? 1 + p0 : 1 + F + p1 * (p1 - 1) / 2 + p0);
+      const long long pid = wgt == 0 ? 0
+                          : wgt == 1 ? 1 + p0
+                          : wgt == 2 ? 1 + F + choose2(p1) + p0
+                                     : 1 + F + choose2(F) + choose3(p2) + choose2(p1) + p0;
       const float* __restrict__ T = prm.cache + meta[0] + ((size_t)pid << n_c);
       float prev = T[0];
       uint32_t prefix = 0;
@@ -463,6 +486,8 @@ static int fail(int code, const std::string& msg) {
   } while (0)
 
 constexpr int kSlots = 3;            // pipeline depth of tsb_sample_host
+constexpr int kHeavyRows = 4;        // word offset of the row list inside a heavy buffer (the count sits at word 0)
+static size_t heavy_bytes(long long cap) { return 4 * ((size_t)cap + kHeavyRows + 64); }
 constexpr long long kSliceDefault = 262144;  // shots per pipeline slice (best of the sweep in tools/sweep_slice.py)
 static long long slice_env() {
   static long long v = [] {
@@ -484,7 +509,7 @@ struct Slot {
   uint64_t* d_out = nullptr;
   uint8_t* d_out_bytes = nullptr;
   uint32_t* d_subkeys = nullptr;
-  uint32_t* d_heavy = nullptr;  // [cap + 1]: count, then row indices (pattern-cache pass 2)
+  uint32_t* d_heavy = nullptr;  // pattern-cache pass 2: count at [0], row indices from [kHeavyRows] (16-byte aligned)
   uint32_t* d_xt = nullptr;     // sliced mode: transposed parameters [total_F][cap/32]
   uint32_t* d_ot = nullptr;     // sliced mode: bit-sliced outputs [n_draws][cap/32]
   long long cap = 0;
@@ -514,6 +539,8 @@ struct tsb_program {
   long long cache_entries = 0;
   uint32_t* d_heavy = nullptr;  // for tsb_sample_device
   long long heavy_cap = 0;
+  uint32_t* h_heavy_seen = nullptr;  // pinned: heavy-row count of an earlier memoised sliced launch (launch-shape hint only)
+  long long heavy_seen_B = 0;
   // MODE_SLICED
   int is_sliced = 0, s_has_exact = 0, s_rows = 0, s_smem_limit = 0, s_stage_words = 0;
   int total_F = 0, max_nc = 0;
@@ -602,9 +629,13 @@ static EvalFn eval_fn_for(int W) {
 }
 typedef void (*SlicedFn)(const SParams);
 // exact-branch accumulators are four words per shot: only the 8-way split keeps them in registers
-static SlicedFn sliced_fn(int split, int has_exact) {
-  if (has_exact) return sample_sliced_kernel<8, true>;
-  return split == 4 ? sample_sliced_kernel<4, false> : sample_sliced_kernel<8, false>;
+static SlicedFn sliced_fn(int split, int has_exact, bool rows = false) {
+  if (rows) {
+    if (has_exact) return sample_sliced_kernel<8, true, true>;
+    return split == 4 ? sample_sliced_kernel<4, false, true> : sample_sliced_kernel<8, false, true>;
+  }
+  if (has_exact) return sample_sliced_kernel<8, true, false>;
+  return split == 4 ? sample_sliced_kernel<4, false, false> : sample_sliced_kernel<8, false, false>;
 }
 
 // Shared-memory plan of one sliced launch: `ng` groups of `split` warps (sliced_kernels.cuh).
@@ -619,7 +650,7 @@ static int sliced_fit_groups(int rows, int split, int cap, int stage_words, int 
     if (((long long)kBarWords + (long long)ng * sliced_group_words(rows, split) + (long long)want_stages * stage_words) * 4 <= smem_limit) return ng;
   return 0;
 }
-static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl);
+static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl, bool row_list, long long expect_rows);
 static SampleFn sample_fn(int mode, int W) { return mode == kModeFast ? sample_fn_for<kModeFast>(W) : sample_fn_for<kModeFaithful>(W); }
 static EvalFn eval_fn(int mode, int W) { return mode == kModeFast ? eval_fn_for<kModeFast>(W) : eval_fn_for<kModeFaithful>(W); }
 
@@ -656,6 +687,8 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
   CUB(cudaMalloc(&p->d_norm_dev, sizeof(float) * std::max(1, n_comp)));
   CUB(cudaMemset(p->d_norm_dev, 0, sizeof(float) * std::max(1, n_comp)));
   CUB(cudaHostAlloc(&p->h_norm_dev, sizeof(float) * std::max(1, n_comp), cudaHostAllocDefault));
+  CUB(cudaHostAlloc(&p->h_heavy_seen, 4, cudaHostAllocDefault));
+  *p->h_heavy_seen = 0;
   CUB(cudaMalloc(&p->d_subkeys, 8 * std::max(1, n_draws)));
   CUB(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   CUB(cudaEventCreate(&p->ev_a));
@@ -694,7 +727,8 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
       return bail(TSB_ERR_UNSUPPORTED);
     }
     for (int split : {4, 8})
-      CUB(cudaFuncSetAttribute((const void*)sliced_fn(split, p->s_has_exact), cudaFuncAttributeMaxDynamicSharedMemorySize, lim_smem));
+      for (bool rows : {false, true})
+        CUB(cudaFuncSetAttribute((const void*)sliced_fn(split, p->s_has_exact, rows), cudaFuncAttributeMaxDynamicSharedMemorySize, lim_smem));
     fixed_words = kBarWords;
   }
   fixed_words = (fixed_words + 31) & ~31;  // 128-byte align the data region
@@ -736,7 +770,7 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
   in.threads = kThreads; in.grid = p->sm_count; in.data_bytes = data_words * 4;
   if (mode == kModeSliced) {  // report the plan of a chip-filling batch
     SlicedPlan pl;
-    sliced_plan(p, p->sm_count * 7 * 32, pl);
+    sliced_plan(p, p->sm_count * 7 * 32, pl, false, -1);
     in.threads = pl.ng * pl.split * 32; in.smem_bytes = pl.smem_bytes; in.resident = 0;
     p->n_stages = pl.n_stages; p->stage_words = p->s_stage_words;
   }
@@ -771,6 +805,7 @@ int tsb_program_destroy(tsb_program* p) {
   if (p->d_blob) cudaFree(p->d_blob);
   if (p->d_norm_dev) cudaFree(p->d_norm_dev);
   if (p->h_norm_dev) cudaFreeHost(p->h_norm_dev);
+  if (p->h_heavy_seen) cudaFreeHost(p->h_heavy_seen);
   if (p->d_subkeys) cudaFree(p->d_subkeys);
   if (p->d_cache) cudaFree(p->d_cache);
   if (p->d_cache_meta) cudaFree(p->d_cache_meta);
@@ -833,6 +868,7 @@ static int launch_light(tsb_program* p, const uint64_t* d_f, long long B, long l
   LightParams k;
   k.blob = p->d_blob; k.f = d_f; k.out = d_out; k.subkeys = d_subkeys; k.cache = p->d_cache; k.cache_meta = p->d_cache_meta;
   k.heavy_rows = heavy_rows; k.heavy_count = heavy_count; k.B = B; k.shot_offset = shot_offset;
+  k.shot0_heavy = p->is_sliced ? 0 : 1;
   const unsigned blocks = (unsigned)((B + 255) / 256);
   light_kernel<<<blocks, 256, 0, st>>>(k);
   CU(cudaGetLastError());
@@ -857,8 +893,10 @@ static CacheFn cache_fn_for(int W) {
 
 int tsb_program_set_pattern_cache(tsb_program* p, int max_weight, int64_t max_entries, int64_t* entries_out) {
   if (!p) return fail(TSB_ERR_INVALID, "null handle");
-  if (max_weight > 2) return fail(TSB_ERR_INVALID, "pattern cache supports weights 0, 1 and 2");
-  if (p->is_sliced && max_weight >= 0) return fail(TSB_ERR_UNSUPPORTED, "the pattern cache works with per-row (fast / faithful) programs");
+  if (max_weight > kCacheMaxWeight) return fail(TSB_ERR_INVALID, "pattern cache supports weights 0 to 3");
+  // a sliced program tabulates with its per-row companion's evaluator (bit-identical values, see sliced_kernels.cuh)
+  const tsb_program* ev = p->is_sliced ? p->aux : p;
+  if (max_weight >= 0 && !ev) return fail(TSB_ERR_UNSUPPORTED, "a sliced program builds its pattern cache with its companion program (tsb_program_set_aux)");
   CU(cudaSetDevice(p->device));
   CU(cudaDeviceSynchronize());
   if (p->d_cache) cudaFree(p->d_cache);
@@ -869,7 +907,7 @@ int tsb_program_set_pattern_cache(tsb_program* p, int max_weight, int64_t max_en
   const tsb_info& in = p->info;
   if (in.words_f64 > kCacheMaxWords64 || in.words_out64 > kCacheMaxWords64)
     return fail(TSB_ERR_UNSUPPORTED, "pattern cache needs num_f <= 512 and num_outputs <= 512");
-  if (max_entries <= 0) max_entries = 1ll << 24;
+  if (max_entries <= 0) max_entries = 1ll << 22;  // 16 MB of float32: stays L2-resident
   const uint32_t* b = p->host_blob.data();
   const int n_comp = in.n_components;
   std::vector<uint32_t> meta((size_t)std::max(1, n_comp) * kCacheMetaWords, 0);
@@ -882,7 +920,7 @@ int tsb_program_set_pattern_cache(tsb_program* p, int max_weight, int64_t max_en
     long long cnt = 0;
     if (n_c <= 20) {
       for (int cand = max_weight; cand >= 0; --cand) {
-        const long long pats = 1 + (cand >= 1 ? F : 0) + (cand >= 2 ? F * (F - 1) / 2 : 0);
+        const long long pats = cache_patterns(F, cand);
         if (pats * (1ll << n_c) <= max_entries - total) { w = cand; cnt = pats * (1ll << n_c); break; }
       }
     }
@@ -897,11 +935,11 @@ int tsb_program_set_pattern_cache(tsb_program* p, int max_weight, int64_t max_en
   CU(cudaMalloc(&p->d_cache, sizeof(float) * (size_t)std::max<long long>(1, total)));
   CU(cudaMalloc(&p->d_cache_meta, meta.size() * 4));
   CU(cudaMemcpy(p->d_cache_meta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
-  CacheFn fn = in.mode == kModeFast ? cache_fn_for<kModeFast>(in.words) : cache_fn_for<kModeFaithful>(in.words);
+  CacheFn fn = ev->info.mode == kModeFast ? cache_fn_for<kModeFast>(ev->info.words) : cache_fn_for<kModeFaithful>(ev->info.words);
   for (int c = 0; c < n_comp; ++c) {
     if (counts[c] == 0) continue;
     const unsigned blocks = (unsigned)((counts[c] + 255) / 256);
-    fn<<<blocks, 256, 0, p->stream>>>(p->d_blob, c, (int)meta[c * kCacheMetaWords + 3], p->d_cache + offs[c], counts[c]);
+    fn<<<blocks, 256, 0, p->stream>>>(ev->d_blob, c, (int)meta[c * kCacheMetaWords + 3], p->d_cache + offs[c], counts[c]);
     CU(cudaGetLastError());
   }
   CU(cudaStreamSynchronize(p->stream));
@@ -981,13 +1019,23 @@ static bool launch_norm_fast(const tsb_program* p, const tsb_program* a, float* 
 
 // Groups per CTA, split and ring depth for a batch of n_slabs slabs.  Few groups per SM -> 8 warps per group (so that a
 // thin slice still keeps 16+ warps on an SM), otherwise 4.
-static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl) {
-  const int n_groups = std::max(1, (n_slabs + 31) / 32);
+static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl, bool row_list, long long expect_rows) {
+  int n_groups = std::max(1, (n_slabs + 31) / 32);
   pl.grid = std::max(1, std::min(p->sm_count, n_groups));
-  const int gpc = (n_groups + pl.grid - 1) / pl.grid;  // groups per CTA
+  int gpc = (n_groups + pl.grid - 1) / pl.grid;  // groups per CTA
   // the smallest grid with that many groups per CTA: the kernel is no slower, and the SMs left over (8 of 148 for 10^6
   // shots) take the neighbouring kernels of the pipeline, the norm check and NCCL's all-gather instead of queueing them
   pl.grid = (n_groups + gpc - 1) / gpc;
+  if (row_list) {
+    // The live row count is only known on the device: the grid covers the worst case (CTAs beyond the live groups
+    // return at once, the kernel derives its rounds itself); the shape (split, groups per CTA) follows the count the
+    // previous call saw, which only affects speed.
+    pl.grid = std::max(1, std::min(p->sm_count, n_groups));
+    if (expect_rows >= 0) {
+      const int eg = std::max(1, (int)((expect_rows + 1023) / 1024));
+      gpc = (eg + pl.grid - 1) / pl.grid;
+    }
+  }
   int split = (p->s_has_exact || gpc < 4) ? 8 : 4;
   if (const char* e = getenv("TSIM_B200_SLICED_SPLIT")) {  // tuning knob
     const int v = atoi(e);
@@ -1002,6 +1050,7 @@ static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl) {
   pl.split = split;
   pl.rounds = (gpc + ng - 1) / ng;
   pl.ng = (gpc + pl.rounds - 1) / pl.rounds;
+  if (row_list) pl.ng = ng;  // rounds are derived on the device from the live count
   pl.xt_off = kBarWords;
   pl.pl_off = pl.xt_off + pl.ng * p->s_rows * 32;
   pl.data_off = pl.pl_off + pl.ng * 2 * split * kPlaneRows * 32;
@@ -1011,22 +1060,39 @@ static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl) {
   return true;
 }
 
-// K0t -> K1s -> K2a -> K1c on one stream
+// [light pass ->] K0t -> K1s -> K2a -> K1c on one stream.  With the pattern cache on (and a heavy buffer), shots whose
+// selected f pattern is tabulated are finished by light_kernel; K0t / K1s / K2a then run over the list of remaining rows.
 static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long long shot_offset, const uint32_t* d_subkeys,
                          uint64_t* d_out, float* d_norm_dev, cudaStream_t st, uint32_t* d_xt, uint32_t* d_ot, long long slab_cap,
-                         bool join = false, cudaEvent_t k1s_start = nullptr, cudaEvent_t k1s_stop = nullptr) {
+                         bool join = false, cudaEvent_t k1s_start = nullptr, cudaEvent_t k1s_stop = nullptr, uint32_t* d_heavy = nullptr) {
   if (B <= 0) return TSB_OK;
   const tsb_info& in = p->info;
   const int n_slabs = (int)((B + 31) / 32);
   if (n_slabs > slab_cap) return fail(TSB_ERR_INVALID, "internal: sliced scratch too small");
   const unsigned tblocks = (unsigned)(((long long)n_slabs * 32 + 255) / 256);
+  const bool memo = p->cache_wmax >= 0 && d_heavy && in.n_draws > 0;
+  const uint32_t* rows = memo ? d_heavy + kHeavyRows : nullptr;
+  const uint32_t* n_rows = memo ? d_heavy : nullptr;
+  // tsb_last_kernel_ms: the sampling kernel alone, or (memoised) light pass + K0t + K1s + K2a
+  if (memo && k1s_start) CU(cudaEventRecord(k1s_start, st));
+  if (memo) {
+    int rc = launch_light(p, d_f, B, shot_offset, d_subkeys, d_out, d_heavy + kHeavyRows, d_heavy, st);
+    if (rc) return rc;
+    if (p->h_heavy_seen) {  // remember the count for the next call's launch shape (read whenever it lands)
+      CU(cudaMemcpyAsync(p->h_heavy_seen, d_heavy, 4, cudaMemcpyDeviceToHost, st));
+      p->heavy_seen_B = B;
+    }
+  }
   if (p->total_F > 0) {
-    transpose_in_kernel<<<tblocks, 256, 0, st>>>(p->d_blob, d_f, B, n_slabs, (int)slab_cap, d_xt);
+    transpose_in_kernel<<<tblocks, 256, 0, st>>>(p->d_blob, d_f, B, n_slabs, (int)slab_cap, d_xt, rows, n_rows);
     CU(cudaGetLastError());
   }
   if (in.n_draws > 0) {
     SlicedPlan pl;
-    if (!sliced_plan(p, n_slabs, pl)) return fail(TSB_ERR_UNSUPPORTED, "internal: no sliced launch plan fits in shared memory");
+    long long expect = -1;
+    if (memo && p->h_heavy_seen && p->heavy_seen_B > 0)  // scale the last count to this batch size (+ 25 % headroom)
+      expect = std::min<long long>(B, (long long)((double)*p->h_heavy_seen * 1.25 * (double)B / (double)p->heavy_seen_B) + 1024);
+    if (!sliced_plan(p, n_slabs, pl, memo, expect)) return fail(TSB_ERR_UNSUPPORTED, "internal: no sliced launch plan fits in shared memory");
     SParams k;
     k.blob = p->d_blob; k.xt = d_xt; k.ot = d_ot; k.subkeys = d_subkeys; k.B = B; k.shot_offset = shot_offset;
     k.pv = reinterpret_cast<float*>(d_ot + (((size_t)slab_cap * std::max(1, in.n_draws) + 3) & ~(size_t)3));  // 16-byte aligned
@@ -1036,13 +1102,15 @@ static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long 
     k.smem_xt_off = pl.xt_off; k.smem_pl_off = pl.pl_off; k.smem_data_off = pl.data_off;
     k.rows = p->s_rows; k.sel = make_uint4(0x80u, 0x8000u, 0x800000u, 0x80000000u);
     k.sel_e = make_uint4(8u, 8u << 8, 8u << 16, 8u << 24);
-    if (k1s_start) CU(cudaEventRecord(k1s_start, st));  // tsb_last_kernel_ms reports the dominant kernel alone
-    sliced_fn(pl.split, p->s_has_exact)<<<pl.grid, pl.ng * pl.split * 32, pl.smem_bytes, st>>>(k);
+    k.row_list = rows; k.n_rows = n_rows;
+    if (!memo && k1s_start) CU(cudaEventRecord(k1s_start, st));
+    sliced_fn(pl.split, p->s_has_exact, memo)<<<pl.grid, pl.ng * pl.split * 32, pl.smem_bytes, st>>>(k);
     CU(cudaGetLastError());
-    if (k1s_stop) CU(cudaEventRecord(k1s_stop, st));
+    if (!memo && k1s_stop) CU(cudaEventRecord(k1s_stop, st));
   }
-  assemble_out_kernel<<<tblocks, 256, 0, st>>>(p->d_blob, d_f, d_ot, B, n_slabs, (int)slab_cap, d_out);
+  assemble_out_kernel<<<tblocks, 256, 0, st>>>(p->d_blob, d_f, d_ot, B, n_slabs, (int)slab_cap, d_out, rows, n_rows);
   CU(cudaGetLastError());
+  if (memo && k1s_stop) CU(cudaEventRecord(k1s_stop, st));
   if (shot_offset == 0 && in.n_components > 0 && p->aux) {
     // fork: the check works on copies of row 0, on a side stream, while st carries on with the next slice / step
     const tsb_program* a = p->aux;
@@ -1096,8 +1164,14 @@ int tsb_sample_device(tsb_program* p, const uint64_t* d_f, int64_t B, int64_t sh
       p->scratch_slabs = slabs;
     }
     // the stream only waits for the (overlapped) norm check when the caller wants the deviations in its own buffer
+    if (p->cache_wmax >= 0 && p->heavy_cap < B) {
+      if (p->d_heavy) cudaFree(p->d_heavy);
+      p->d_heavy = nullptr; p->heavy_cap = 0;
+      CU(cudaMalloc(&p->d_heavy, heavy_bytes(B)));
+      p->heavy_cap = B;
+    }
     int rc = launch_sliced(p, d_f, B, shot_offset, p->d_subkeys, d_out, d_norm_dev ? d_norm_dev : p->d_norm_dev, st, p->d_xt,
-                           p->d_ot, p->scratch_slabs, d_norm_dev != nullptr, p->ev_a, p->ev_b);
+                           p->d_ot, p->scratch_slabs, d_norm_dev != nullptr, p->ev_a, p->ev_b, p->cache_wmax >= 0 ? p->d_heavy : nullptr);
     if (rc) return rc;
     if (p->info.n_draws == 0) CU(cudaEventRecord(p->ev_b, st));  // no sampling kernel ran: empty interval
     p->last_launches = B > 0 ? 5 : 0;
@@ -1107,11 +1181,11 @@ int tsb_sample_device(tsb_program* p, const uint64_t* d_f, int64_t B, int64_t sh
   if (p->cache_wmax >= 0 && p->heavy_cap < B) {
     if (p->d_heavy) cudaFree(p->d_heavy);
     p->d_heavy = nullptr; p->heavy_cap = 0;
-    CU(cudaMalloc(&p->d_heavy, 4 * ((size_t)B + 1)));
+    CU(cudaMalloc(&p->d_heavy, heavy_bytes(B)));
     p->heavy_cap = B;
   }
   int rc = launch_sample(p, d_f, B, shot_offset, p->d_subkeys, d_out, d_norm_dev ? d_norm_dev : p->d_norm_dev, st,
-                         p->d_heavy ? p->d_heavy + 1 : nullptr, p->d_heavy);
+                         p->d_heavy ? p->d_heavy + kHeavyRows : nullptr, p->d_heavy);
   if (rc) return rc;
   CU(cudaEventRecord(p->ev_b, st));
   p->last_launches = B > 0 ? 2 : 0;
@@ -1157,7 +1231,7 @@ static int ensure_slot(tsb_program* p, Slot& s, long long cap) {
   CU(cudaMalloc(&s.d_f, (size_t)cap * in.words_f64 * 8));
   CU(cudaMalloc(&s.d_out, (size_t)cap * in.words_out64 * 8));
   CU(cudaMalloc(&s.d_out_bytes, (size_t)cap * std::max(1, in.num_outputs)));
-  CU(cudaMalloc(&s.d_heavy, 4 * ((size_t)cap + 1)));
+  CU(cudaMalloc(&s.d_heavy, heavy_bytes(cap)));
   if (p->is_sliced) {
     const size_t slabs = (size_t)((cap + 31) / 32);
     CU(cudaMalloc(&s.d_xt, 4 * slabs * (size_t)std::max(1, p->total_F)));
@@ -1251,8 +1325,8 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
     }
     if (trace) CU(cudaEventRecord(s.t_h1, s.stream));
     CU(cudaEventRecord(s.k_start, s.stream));
-    rc = p->is_sliced ? launch_sliced(p, s.d_f, n, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream, s.d_xt, s.d_ot, (s.cap + 31) / 32)
-                      : launch_sample(p, s.d_f, n, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream, s.d_heavy + 1, s.d_heavy);
+    rc = p->is_sliced ? launch_sliced(p, s.d_f, n, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream, s.d_xt, s.d_ot, (s.cap + 31) / 32, false, nullptr, nullptr, s.d_heavy)
+                      : launch_sample(p, s.d_f, n, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream, s.d_heavy + kHeavyRows, s.d_heavy);
     if (rc) return rc;
     CU(cudaEventRecord(s.k_stop, s.stream));
     s.timed = true;
@@ -1503,8 +1577,8 @@ int tsb_sample_noisy_host(tsb_program* p, tsb_noise* n, int64_t B, int64_t shot_
     derive_subkeys_kernel<<<1, 32, 0, s.stream>>>(k0, k1, in.n_draws, s.d_subkeys);
     CU(cudaGetLastError());
     CU(cudaEventRecord(s.k_start, s.stream));
-    rc = p->is_sliced ? launch_sliced(p, s.d_f, cnt, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream, s.d_xt, s.d_ot, (s.cap + 31) / 32)
-                      : launch_sample(p, s.d_f, cnt, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream, s.d_heavy + 1, s.d_heavy);
+    rc = p->is_sliced ? launch_sliced(p, s.d_f, cnt, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream, s.d_xt, s.d_ot, (s.cap + 31) / 32, false, nullptr, nullptr, s.d_heavy)
+                      : launch_sample(p, s.d_f, cnt, shot_offset + lo, s.d_subkeys, s.d_out, p->d_norm_dev, s.stream, s.d_heavy + kHeavyRows, s.d_heavy);
     if (rc) return rc;
     CU(cudaEventRecord(s.k_stop, s.stream));
     s.timed = true;

@@ -79,3 +79,32 @@ def test_program_stats_match_reference_repr_vocabulary():
     assert s["graphs"] == sum(G) == 148 and s["direct"] == 15 and s["max_outputs_per_component"] == 5
     assert s["A_terms"] == sum(G) * 8 and s["B_terms"] == sum(G) * 16 and s["C_terms"] == sum(G) * 24 and s["D_terms"] == sum(G) * 8
     assert s["max_params"] == 53
+
+
+def test_npz_carries_the_noise_tables(tmp_path):
+    from tsim_b200.program import load_npz_meta, load_npz_noise
+
+    prog = synthetic_program("cfg5_distill85")
+    nf = prog.infer_num_f()
+    # a two-outcome-per-channel sampler plus a multi-outcome channel (tables as channels.py:578-622 builds them)
+    rng = np.random.default_rng(3)
+    sparse = [(0.01 * (i + 1), np.array([1.0]), (rng.random((1, nf)) < 0.05).astype(np.uint8)) for i in range(5)]
+    sparse.append((0.2, np.array([0.25, 0.5, 1.0]), (rng.random((3, nf)) < 0.1).astype(np.uint8)))
+    cs = ChannelSampler.from_sparse(sparse, nf, seed=9)
+    path = str(tmp_path / "p.npz")
+    save_npz(path, prog, noise=cs, meta={"circuit": "unit"})
+    back, back_nf = load_npz_noise(path)
+    assert back_nf == nf and len(back) == len(sparse)
+    for (p0, c0, m0), (p1, c1, m1) in zip(sparse, back):
+        assert p0 == p1 and np.array_equal(c0, c1) and np.array_equal(m0, m1)
+    assert load_npz_meta(path) == {"circuit": "unit"}
+    # the same Generator stream from the reloaded tables
+    a = ChannelSampler.from_sparse(back, back_nf, seed=9).sample(500)
+    assert np.array_equal(a, ChannelSampler.from_sparse(sparse, nf, seed=9).sample(500))
+    assert load_npz_noise(str(_plain(tmp_path, prog))) is None
+
+
+def _plain(tmp_path, prog):
+    path = tmp_path / "plain.npz"
+    save_npz(str(path), prog)
+    return path

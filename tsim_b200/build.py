@@ -23,6 +23,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "--shared", "-Xcompiler", "-fPIC",
+    "-split-compile", "0",  # optimise the kernels of the translation unit on all host cores (90 s -> 30 s)
 ]
 
 

@@ -360,9 +360,26 @@ _LEVEL_FIELDS = (
 )
 
 
-def save_npz(path: str, program: CompiledProgram) -> None:
-    """Write a program as a flat ``.npz`` (mask tensors bit-packed along P)."""
+def save_npz(path: str, program: CompiledProgram, *, noise: Any = None, meta: dict | None = None) -> None:
+    """Write a program as a flat ``.npz`` (mask tensors bit-packed along P).
+
+    ``noise``: optional channel sampler (tsim's or ours) or its ``_sparse_data`` list of ``(p_fire, cond_cdf, xor_patterns)``
+    (reference ``noise/channels.py:578-622``); stored so that a benchmark can draw f vectors from the circuit's own noise
+    model.  ``meta``: free-form strings (circuit name, tsim version, ...)."""
     d: dict[str, np.ndarray] = {}
+    if noise is not None:
+        sparse = getattr(noise, "_sparse_data", noise)
+        d["noise.n"] = np.array([len(sparse)], dtype=np.int64)
+        d["noise.p_fire"] = np.array([float(t[0]) for t in sparse], dtype=np.float64)
+        d["noise.cdf_len"] = np.array([len(t[1]) for t in sparse], dtype=np.int64)
+        d["noise.cdf"] = np.concatenate([np.asarray(t[1], np.float64).reshape(-1) for t in sparse]) if sparse else np.zeros(0)
+        pats = [np.asarray(t[2], np.uint8).reshape(len(t[1]), -1) for t in sparse]
+        d["noise.num_f"] = np.array([pats[0].shape[1] if pats else (program.num_f or 0)], dtype=np.int64)
+        d["noise.patterns"] = (
+            np.packbits(np.concatenate(pats, axis=0), axis=1, bitorder="little") if pats else np.zeros((0, 0), np.uint8)
+        )
+    for k, v in (meta or {}).items():
+        d["meta." + str(k)] = np.array([str(v)])
     d["header"] = np.array(
         [
             program.num_outputs,
@@ -399,8 +416,29 @@ def save_npz(path: str, program: CompiledProgram) -> None:
     np.savez_compressed(path, **d)
 
 
+def load_npz_noise(path: str):
+    """The noise tables stored by :func:`save_npz` as ``(sparse_data, num_f)``, or ``None``."""
+    z = np.load(path)
+    if "noise.n" not in z.files:
+        return None
+    num_f = int(z["noise.num_f"][0])
+    lens = [int(v) for v in z["noise.cdf_len"]]
+    cdf, pats = z["noise.cdf"], z["noise.patterns"]
+    pats = np.unpackbits(pats, axis=1, bitorder="little", count=num_f) if pats.size else np.zeros((0, num_f), np.uint8)
+    out, pos = [], 0
+    for p_fire, n in zip(z["noise.p_fire"], lens):
+        out.append((float(p_fire), np.array(cdf[pos : pos + n], dtype=np.float64), np.ascontiguousarray(pats[pos : pos + n])))
+        pos += n
+    return out, num_f
+
+
+def load_npz_meta(path: str) -> dict:
+    z = np.load(path)
+    return {k[5:]: str(z[k][0]) for k in z.files if k.startswith("meta.")}
+
+
 def load_npz(path: str) -> CompiledProgram:
-    """Inverse of :func:`save_npz`."""
+    """Inverse of :func:`save_npz` (the program part)."""
     z = np.load(path)
     n_out, n_det, n_comp, num_f, has_reindex = (int(v) for v in z["header"])
     comps = []

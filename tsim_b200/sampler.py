@@ -286,7 +286,11 @@ class _CompiledSamplerBase:
                         packed: bool = False):
         """Reference ``_sample_batches`` (sampler.py:340-420).  ``packed=True`` (not in the reference) keeps the
         result as the device's ``uint64[shots, ceil(n_out/64)]`` rows; the reference row is still ``bool[n_out]``."""
-        if packed and (shots == 0 or not self._program.components):
+        # direct-only programs follow the reference's host shortcut (sampler.py:365-370) unless the noise itself lives on
+        # the device: then K5 -> direct gather -> packed rows never materialise the f matrix on the host
+        on_device = isinstance(self._channel_sampler, DeviceChannelSampler)
+        host_direct = not self._program.components and not on_device
+        if packed and (shots == 0 or host_direct):
             res = self._sample_batches(shots, batch_size, compute_reference=compute_reference)
             if compute_reference:
                 return pack_bool_rows(res[0]), res[1]
@@ -300,7 +304,7 @@ class _CompiledSamplerBase:
             if compute_reference:
                 return empty, np.zeros(self._program.num_outputs, dtype=np.bool_)
             return empty
-        if not self._program.components:
+        if host_direct:
             samples = self._sample_direct(shots)
             if compute_reference:
                 return samples, self._compute_reference_sample()
@@ -316,7 +320,6 @@ class _CompiledSamplerBase:
 
         batches = []
         reference = None
-        on_device = isinstance(self._channel_sampler, DeviceChannelSampler)
         packed_host = hasattr(self._channel_sampler, "sample_packed")
         for _ in range(num_batches):
             if on_device:
@@ -549,7 +552,7 @@ class CompiledDetectorSampler(_CompiledSamplerBase):
                     samples[~direct_discarded, nd:] ^= reference[nd:]
             else:
                 samples, _, _ = self._sample_batches_with_postselection(shots, batch_size, postselection_mask=postselection_mask)
-        elif bit_packed and self._program.components and shots > 0:
+        elif bit_packed and shots > 0 and (self._program.components or isinstance(self._channel_sampler, DeviceChannelSampler)):
             # packed end to end: the device's uint64 rows are sliced with word shifts, never expanded to bools
             n_out = self._program.num_outputs
             if compute_reference:

@@ -79,9 +79,10 @@ int tsb_program_info(const tsb_program* p, tsb_info* info);
 int tsb_program_set_aux(tsb_program* p, tsb_program* aux);
 
 /* Optional pattern cache (no reference counterpart): tabulate |E_k(pattern, prefix)| for every
- * selected-f pattern of weight <= max_weight (0, 1 or 2; -1 switches the cache off) with the sampling kernel's own
+ * selected-f pattern of weight <= max_weight (0..3; -1 switches the cache off) with the sampling kernel's own
  * evaluator, so that shots with such a pattern only walk the table.  Bits are identical with and without the cache.
- * max_entries <= 0: default budget (2^24 floats).  entries_out: table size actually built. */
+ * A bit-sliced program tabulates with its companion's evaluator and runs K0t / K1s / K2a over the remaining rows.
+ * max_entries <= 0: default budget (2^22 floats, L2-sized).  entries_out: table size actually built. */
 int tsb_program_set_pattern_cache(tsb_program* p, int max_weight, int64_t max_entries, int64_t* entries_out);
 
 /* (carry, sub) = jax.random.split(key): carry = out[0..1], sub = out[2..3] */
@@ -131,6 +132,26 @@ int tsb_noise_sample_host(tsb_noise* n, int64_t B, int64_t shot_offset, uint64_t
 int tsb_sample_noisy_host(tsb_program* p, tsb_noise* n, int64_t B, int64_t shot_offset, uint32_t k0, uint32_t k1,
                           uint64_t noise_seed, uint64_t noise_call, int skip_shot0, void* out, int out_format,
                           float* norm_dev, uint64_t* f_out);
+
+/* ---- post-selection session (reference src/tsim/sampler.py:422-545, _sample_batches_with_postselection) ----
+ * The host keeps the reference's control flow and key schedule; the data path stays on the GPU.  Per chunk of at most
+ * batch_size shots (push_host: packed f rows from the host; push_noise: rows generated by K5): the direct detector bits
+ * are computed, shots with (direct ^ ref_row) & mask_row != 0 are discarded (sampler.py:517-520), surviving f rows and
+ * their shot indices are appended IN SHOT ORDER to a pending buffer; *pending_out = survivors waiting.  dispatch samples
+ * exactly batch_size pending rows under the given batch key (RNG counter = position in that batch, as in the
+ * reference's _dispatch, :486-492) and scatters the rows to their shots; final_batch = 1 pads a partial batch with its
+ * first row (:499-505).  finish XORs xor_kept / xor_discarded into kept / discarded rows (reference-sample handling,
+ * :531-537; NULL = none) and copies out bool bytes or packed rows plus the discard flags.
+ * mask_row / ref_row / xor rows: uint64[words_out64] over output columns; num_detectors = columns [0, nd). */
+typedef struct tsb_postselect tsb_postselect;
+int tsb_postselect_create(tsb_program* p, int64_t shots, int64_t batch_size, const uint64_t* mask_row, const uint64_t* ref_row,
+                          int num_detectors, tsb_postselect** out);
+int tsb_postselect_push_host(tsb_postselect* s, const uint64_t* f_packed, int64_t n, int64_t* pending_out);
+int tsb_postselect_push_noise(tsb_postselect* s, tsb_noise* noise, int64_t n, uint64_t seed, uint64_t call, int64_t* pending_out);
+int tsb_postselect_dispatch(tsb_postselect* s, uint32_t k0, uint32_t k1, int final_batch, float* norm_dev, int64_t* pending_out);
+int tsb_postselect_finish(tsb_postselect* s, const uint64_t* xor_kept, const uint64_t* xor_discarded, void* out, int out_format,
+                          uint8_t* discarded_out);
+int tsb_postselect_destroy(tsb_postselect* s);
 
 void* tsb_host_alloc(size_t nbytes); /* page-locked host memory, NULL on failure */
 void tsb_host_free(void* ptr);

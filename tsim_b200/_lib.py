@@ -37,6 +37,12 @@ EXPORTS = (
     "tsb_sample_noisy_host",
     "tsb_program_set_pattern_cache",
     "tsb_program_set_aux",
+    "tsb_postselect_create",
+    "tsb_postselect_push_host",
+    "tsb_postselect_push_noise",
+    "tsb_postselect_dispatch",
+    "tsb_postselect_finish",
+    "tsb_postselect_destroy",
 )
 
 
@@ -121,6 +127,18 @@ def load() -> C.CDLL:
     lib.tsb_program_set_aux.argtypes = [vp, vp]
     lib.tsb_program_set_pattern_cache.restype = i32
     lib.tsb_program_set_pattern_cache.argtypes = [vp, i32, i64, C.POINTER(i64)]
+    lib.tsb_postselect_create.restype = i32
+    lib.tsb_postselect_create.argtypes = [vp, i64, i64, vp, vp, i32, C.POINTER(vp)]
+    lib.tsb_postselect_push_host.restype = i32
+    lib.tsb_postselect_push_host.argtypes = [vp, vp, i64, C.POINTER(i64)]
+    lib.tsb_postselect_push_noise.restype = i32
+    lib.tsb_postselect_push_noise.argtypes = [vp, vp, i64, u64, u64, C.POINTER(i64)]
+    lib.tsb_postselect_dispatch.restype = i32
+    lib.tsb_postselect_dispatch.argtypes = [vp, u32, u32, i32, vp, C.POINTER(i64)]
+    lib.tsb_postselect_finish.restype = i32
+    lib.tsb_postselect_finish.argtypes = [vp, vp, vp, vp, i32, vp]
+    lib.tsb_postselect_destroy.restype = i32
+    lib.tsb_postselect_destroy.argtypes = [vp]
     _lib = lib
     return lib
 

@@ -277,6 +277,10 @@ class DeviceProgram:
             )
         )
 
+    def postselect_session(self, shots: int, batch_size: int, mask: np.ndarray, ref: np.ndarray | None, num_detectors: int) -> "PostselectSession":
+        """Device-side survivor buffering for ``_sample_batches_with_postselection`` (reference sampler.py:422-545)."""
+        return PostselectSession(self, shots, batch_size, mask, ref, num_detectors)
+
     def level_params(self, component: int, level: int) -> int:
         """Number of parameters of ``components[component].compiled_scalar_graphs[level]``."""
         from . import pack as PK
@@ -304,3 +308,77 @@ class DeviceProgram:
             )
         )
         return amp.view(np.complex64).reshape(-1)
+
+
+def _pack_row(bits: np.ndarray, words: int) -> np.ndarray:
+    """``bool[n]`` -> ``uint64[words]`` (bit j = column j)."""
+    b = np.zeros(words * 64, dtype=np.uint8)
+    b[: len(bits)] = np.asarray(bits, dtype=np.uint8)
+    return np.packbits(b, bitorder="little").view(np.uint64).copy()
+
+
+class PostselectSession:
+    """``tsb_postselect``: direct-detector test, order-preserving survivor compaction, fixed-shape batches and the
+    scatter of sampled rows all stay on the GPU; the caller keeps the reference's loop and key schedule."""
+
+    def __init__(self, dp: DeviceProgram, shots: int, batch_size: int, mask: np.ndarray, ref: np.ndarray | None, num_detectors: int):
+        self.dp, self.shots, self.batch_size = dp, int(shots), int(batch_size)
+        self._lib = dp._lib
+        wo = dp.info["words_out64"]
+        n_out = dp.num_outputs
+        m = np.zeros(n_out, dtype=np.bool_)
+        m[: len(mask)] = mask
+        self._mask = _pack_row(m, wo)
+        self._ref = None
+        if ref is not None:
+            r = np.zeros(n_out, dtype=np.bool_)
+            r[: len(ref)] = ref
+            self._ref = _pack_row(r, wo)
+        h = C.c_void_p()
+        _lib.check(self._lib.tsb_postselect_create(
+            dp._h, self.shots, self.batch_size, self._mask.ctypes.data_as(C.c_void_p),
+            self._ref.ctypes.data_as(C.c_void_p) if self._ref is not None else None, int(num_detectors), C.byref(h)))
+        self._h = h
+        self._fin = weakref.finalize(self, self._lib.tsb_postselect_destroy, h)
+        self.dispatches = 0
+
+    def push_host(self, f: np.ndarray) -> int:
+        """A chunk of f rows (``uint8[n, num_f]`` or packed ``uint64``) -> number of survivors pending."""
+        f = np.asarray(f)
+        if f.dtype != np.uint64:
+            from .noise import pack_f_rows
+
+            f = pack_f_rows(f)
+        f = np.ascontiguousarray(f)
+        pending = C.c_int64(0)
+        _lib.check(self._lib.tsb_postselect_push_host(self._h, f.ctypes.data_as(C.c_void_p), f.shape[0], C.byref(pending)))
+        return int(pending.value)
+
+    def push_noise(self, noise, n: int) -> int:
+        pending = C.c_int64(0)
+        _lib.check(self._lib.tsb_postselect_push_noise(self._h, noise._h, int(n), int(noise.seed), int(noise.next_call()), C.byref(pending)))
+        return int(pending.value)
+
+    def dispatch(self, key, *, final: bool = False) -> tuple[int, np.ndarray]:
+        k0, k1 = key_words(key)
+        n_comp = self.dp.info["n_components"]
+        dev = np.zeros(max(1, n_comp), dtype=np.float32)
+        pending = C.c_int64(0)
+        _lib.check(self._lib.tsb_postselect_dispatch(self._h, k0, k1, int(final), dev.ctypes.data_as(C.c_void_p), C.byref(pending)))
+        self.dispatches += 1
+        return int(pending.value), dev[:n_comp]
+
+    def finish(self, xor_kept: np.ndarray | None = None, xor_discarded: np.ndarray | None = None) -> tuple[np.ndarray, np.ndarray]:
+        """-> ``(bool[shots, n_out], bool[shots] was_discarded)``; the two rows are XORed into kept / discarded shots."""
+        wo, n_out = self.dp.info["words_out64"], self.dp.num_outputs
+        out = _result_pool.take((self.shots, n_out), np.bool_) if self.shots else np.empty((0, n_out), np.bool_)
+        disc = np.zeros(self.shots, dtype=np.bool_)
+        xk = xd = None
+        if xor_kept is not None or xor_discarded is not None:
+            xk = _pack_row(xor_kept if xor_kept is not None else np.zeros(n_out, bool), wo)
+            xd = _pack_row(xor_discarded if xor_discarded is not None else np.zeros(n_out, bool), wo)
+        _lib.check(self._lib.tsb_postselect_finish(
+            self._h, xk.ctypes.data_as(C.c_void_p) if xk is not None else None, xd.ctypes.data_as(C.c_void_p) if xd is not None else None,
+            out.ctypes.data_as(C.c_void_p), _lib.TSB_OUT_BYTES, disc.ctypes.data_as(C.c_void_p)))
+        self._fin()
+        return out, disc

@@ -16,6 +16,7 @@ DEPS = [
     os.path.join(HERE, "csrc", "blob.h"),
     os.path.join(HERE, "csrc", "sliced_kernels.cuh"),
     os.path.join(HERE, "csrc", "noise_kernels.cuh"),
+    os.path.join(HERE, "csrc", "postselect.cuh"),
     os.path.join(os.path.dirname(HERE), "include", "tsim_b200.h"),
 ]
 

@@ -12,6 +12,7 @@
 #include "../../include/tsim_b200.h"
 #include "blob.h"
 #include "noise_kernels.cuh"
+#include "postselect.cuh"
 #include "sampler_kernels.cuh"
 #include "sliced_kernels.cuh"
 
@@ -1609,5 +1610,205 @@ int tsb_sample_noisy_host(tsb_program* p, tsb_noise* n, int64_t B, int64_t shot_
   if (p->side) CU(cudaStreamSynchronize(p->side));
   if (norm_dev && in.n_components > 0)
     CU(cudaMemcpy(norm_dev, p->d_norm_dev, sizeof(float) * in.n_components, cudaMemcpyDeviceToHost));
+  return TSB_OK;
+}
+
+// =============================================================================================
+// Post-selection session (row f3): survivors are compacted, batched, sampled and scattered on the device
+// =============================================================================================
+struct tsb_postselect {
+  tsb_program* p = nullptr;
+  long long shots = 0, batch = 0, pushed = 0, pending = 0;
+  int wf = 0, wo = 0;
+  cudaStream_t stream = nullptr;
+  uint64_t* d_rows = nullptr;       // [wo] x 5: mask | ref | detmask | xor_kept | xor_discarded
+  uint64_t* d_result = nullptr;     // [shots][wo]
+  uint8_t* d_discarded = nullptr;   // [shots]
+  uint64_t* d_chunk_f = nullptr;    // [batch][wf]
+  uint64_t* d_surv_f = nullptr;     // [2 batch][wf]
+  uint32_t* d_surv_idx = nullptr;   // [2 batch]
+  uint64_t* d_out = nullptr;        // [batch][wo]
+  uint32_t* d_counts = nullptr;     // block counts | block offsets | total
+  uint8_t* d_bytes = nullptr;       // [shots][n_out] (finish with byte output)
+  float* d_norm = nullptr;
+  uint32_t* h_total = nullptr;      // pinned
+  float* h_norm = nullptr;          // pinned
+  int n_blocks_cap = 0;
+  long long dispatches = 0;
+};
+
+int tsb_postselect_destroy(tsb_postselect* s) {
+  if (!s) return TSB_OK;
+  cudaSetDevice(s->p->device);
+  if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
+  cudaFree(s->d_rows); cudaFree(s->d_result); cudaFree(s->d_discarded); cudaFree(s->d_chunk_f); cudaFree(s->d_surv_f);
+  cudaFree(s->d_surv_idx); cudaFree(s->d_out); cudaFree(s->d_counts); cudaFree(s->d_bytes); cudaFree(s->d_norm);
+  if (s->h_total) cudaFreeHost(s->h_total);
+  if (s->h_norm) cudaFreeHost(s->h_norm);
+  delete s;
+  return TSB_OK;
+}
+
+int tsb_postselect_create(tsb_program* p, int64_t shots, int64_t batch_size, const uint64_t* mask_row, const uint64_t* ref_row,
+                          int num_detectors, tsb_postselect** out) {
+  if (!p || !out || !mask_row) return fail(TSB_ERR_INVALID, "null argument");
+  if (shots < 0 || batch_size < 1) return fail(TSB_ERR_INVALID, "bad shots / batch_size");
+  if (shots >= (1ll << 32)) return fail(TSB_ERR_UNSUPPORTED, "post-selection sessions index shots with 32 bits");
+  const tsb_info& in = p->info;
+  if (num_detectors < 0 || num_detectors > in.num_outputs) return fail(TSB_ERR_INVALID, "num_detectors out of range");
+  CU(cudaSetDevice(p->device));
+  tsb_postselect* s = new tsb_postselect();
+  s->p = p; s->shots = shots; s->batch = batch_size; s->wf = in.words_f64; s->wo = in.words_out64;
+  const int wo = s->wo;
+  std::vector<uint64_t> rows(5 * (size_t)wo, 0ull);
+  for (int w = 0; w < wo; ++w) {
+    rows[w] = mask_row[w];
+    rows[wo + w] = ref_row ? ref_row[w] : 0ull;
+    const int lo = 64 * w;
+    rows[2 * wo + w] = num_detectors >= lo + 64 ? ~0ull : (num_detectors > lo ? ((1ull << (num_detectors - lo)) - 1ull) : 0ull);
+  }
+  s->n_blocks_cap = (int)((batch_size + kPsThreads - 1) / kPsThreads);
+  cudaError_t e = cudaSuccess;
+  auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  chk(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  chk(cudaMalloc(&s->d_rows, rows.size() * 8));
+  chk(cudaMalloc(&s->d_result, std::max<size_t>(8, (size_t)shots * wo * 8)));
+  chk(cudaMalloc(&s->d_discarded, std::max<size_t>(1, (size_t)shots)));
+  chk(cudaMalloc(&s->d_chunk_f, (size_t)batch_size * s->wf * 8));
+  chk(cudaMalloc(&s->d_surv_f, 2 * (size_t)batch_size * s->wf * 8));
+  chk(cudaMalloc(&s->d_surv_idx, 2 * (size_t)batch_size * 4));
+  chk(cudaMalloc(&s->d_out, (size_t)batch_size * wo * 8));
+  chk(cudaMalloc(&s->d_counts, 4 * (2 * (size_t)s->n_blocks_cap + 4)));
+  chk(cudaMalloc(&s->d_norm, sizeof(float) * std::max(1, in.n_components)));
+  chk(cudaHostAlloc(&s->h_total, 4, cudaHostAllocDefault));
+  chk(cudaHostAlloc(&s->h_norm, sizeof(float) * std::max(1, in.n_components), cudaHostAllocDefault));
+  if (e == cudaSuccess) chk(cudaMemcpy(s->d_rows, rows.data(), rows.size() * 8, cudaMemcpyHostToDevice));
+  if (e != cudaSuccess) {
+    fail(TSB_ERR_CUDA, std::string("tsb_postselect_create: ") + cudaGetErrorString(e));
+    tsb_postselect_destroy(s);
+    return TSB_ERR_CUDA;
+  }
+  *out = s;
+  return TSB_OK;
+}
+
+// the chunk sits in s->d_chunk_f: flag, scan, scatter; returns the pending survivor count
+static int postselect_ingest(tsb_postselect* s, long long n, int64_t* pending_out) {
+  const tsb_info& in = s->p->info;
+  const int wo = s->wo;
+  PsParams k;
+  k.blob = s->p->d_blob; k.f = s->d_chunk_f; k.B = n;
+  k.mask = s->d_rows; k.ref = s->d_rows + wo; k.detmask = s->d_rows + 2 * wo;
+  k.result = s->d_result + (size_t)s->pushed * wo; k.discarded = s->d_discarded + s->pushed; k.block_counts = s->d_counts;
+  const int nb = (int)((n + kPsThreads - 1) / kPsThreads);
+  uint32_t* offsets = s->d_counts + s->n_blocks_cap;
+  uint32_t* total = s->d_counts + 2 * s->n_blocks_cap;
+  postselect_flag_kernel<<<nb, kPsThreads, 0, s->stream>>>(k);
+  postselect_scan_kernel<<<1, 1024, 0, s->stream>>>(s->d_counts, nb, (uint32_t)s->pending, offsets, total);
+  postselect_scatter_kernel<<<nb, kPsThreads, 0, s->stream>>>(k, offsets, s->pushed, s->d_surv_f, s->d_surv_idx);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(s->h_total, total, 4, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  s->pending = (long long)*s->h_total;
+  s->pushed += n;
+  (void)in;
+  if (pending_out) *pending_out = s->pending;
+  return TSB_OK;
+}
+
+static int postselect_check_push(tsb_postselect* s, int64_t n) {
+  if (!s) return fail(TSB_ERR_INVALID, "null session");
+  if (n < 0 || n > s->batch) return fail(TSB_ERR_INVALID, "a chunk holds at most batch_size shots");
+  if (s->pushed + n > s->shots) return fail(TSB_ERR_INVALID, "more shots pushed than the session was created for");
+  if (s->pending >= s->batch) return fail(TSB_ERR_INVALID, "dispatch the pending full batch before pushing more shots");
+  return TSB_OK;
+}
+
+int tsb_postselect_push_host(tsb_postselect* s, const uint64_t* f_packed, int64_t n, int64_t* pending_out) {
+  int rc = postselect_check_push(s, n);
+  if (rc) return rc;
+  if (n == 0) { if (pending_out) *pending_out = s->pending; return TSB_OK; }
+  if (!f_packed) return fail(TSB_ERR_INVALID, "null f rows");
+  CU(cudaSetDevice(s->p->device));
+  CU(cudaMemcpyAsync(s->d_chunk_f, f_packed, (size_t)n * s->wf * 8, cudaMemcpyHostToDevice, s->stream));
+  return postselect_ingest(s, n, pending_out);
+}
+
+int tsb_postselect_push_noise(tsb_postselect* s, tsb_noise* noise, int64_t n, uint64_t seed, uint64_t call, int64_t* pending_out) {
+  int rc = postselect_check_push(s, n);
+  if (rc) return rc;
+  if (n == 0) { if (pending_out) *pending_out = s->pending; return TSB_OK; }
+  if (!noise || noise->device != s->p->device || noise->words != s->wf) return fail(TSB_ERR_INVALID, "noise sampler does not match the program");
+  CU(cudaSetDevice(s->p->device));
+  rc = tsb_noise_sample_device(noise, n, 0, seed, call, 0, s->d_chunk_f, s->stream);
+  if (rc) return rc;
+  return postselect_ingest(s, n, pending_out);
+}
+
+int tsb_postselect_dispatch(tsb_postselect* s, uint32_t k0, uint32_t k1, int final_batch, float* norm_dev, int64_t* pending_out) {
+  if (!s) return fail(TSB_ERR_INVALID, "null session");
+  const tsb_info& in = s->p->info;
+  if (s->pending == 0) return fail(TSB_ERR_INVALID, "no pending survivors");
+  if (s->pending < s->batch && !final_batch) return fail(TSB_ERR_INVALID, "a partial batch is only dispatched at the end");
+  CU(cudaSetDevice(s->p->device));
+  const long long n_valid = std::min(s->pending, s->batch);
+  if (n_valid < s->batch) {  // fixed batch shape: pad with copies of the first pending row (sampler.py:499-505)
+    const long long n = (s->batch - n_valid) * s->wf;
+    pad_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->d_surv_f, s->wf, n_valid, s->batch);
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemsetAsync(s->d_norm, 0, sizeof(float) * std::max(1, in.n_components), s->stream));
+  int rc = tsb_sample_device(s->p, s->d_surv_f, s->batch, 0, k0, k1, s->d_out, s->d_norm, s->stream);
+  if (rc) return rc;
+  {
+    const long long n = n_valid * s->wo;
+    scatter_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->d_out, s->d_surv_idx, n_valid, s->wo, s->d_result);
+    CU(cudaGetLastError());
+  }
+  const long long left = s->pending - n_valid;
+  if (left > 0) {  // left < batch: source [batch, batch + left) and destination [0, left) do not overlap
+    CU(cudaMemcpyAsync(s->d_surv_f, s->d_surv_f + (size_t)s->batch * s->wf, (size_t)left * s->wf * 8, cudaMemcpyDeviceToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d_surv_idx, s->d_surv_idx + s->batch, (size_t)left * 4, cudaMemcpyDeviceToDevice, s->stream));
+  }
+  if (in.n_components > 0)
+    CU(cudaMemcpyAsync(s->h_norm, s->d_norm, sizeof(float) * in.n_components, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  if (norm_dev)
+    for (int i = 0; i < in.n_components; ++i) norm_dev[i] = s->h_norm[i];
+  s->pending = left;
+  s->dispatches += 1;
+  if (pending_out) *pending_out = left;
+  return TSB_OK;
+}
+
+int tsb_postselect_finish(tsb_postselect* s, const uint64_t* xor_kept, const uint64_t* xor_discarded, void* out, int out_format,
+                          uint8_t* discarded_out) {
+  if (!s) return fail(TSB_ERR_INVALID, "null session");
+  if (s->pushed != s->shots) return fail(TSB_ERR_INVALID, "not every shot of the session was pushed");
+  if (s->pending != 0) return fail(TSB_ERR_INVALID, "pending survivors were not dispatched");
+  if (out_format != TSB_OUT_BYTES && out_format != TSB_OUT_PACKED) return fail(TSB_ERR_INVALID, "bad out_format");
+  if (s->shots == 0) return TSB_OK;
+  const tsb_info& in = s->p->info;
+  CU(cudaSetDevice(s->p->device));
+  const int wo = s->wo;
+  if (xor_kept && xor_discarded) {
+    CU(cudaMemcpyAsync(s->d_rows + 3 * wo, xor_kept, 8 * (size_t)wo, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d_rows + 4 * wo, xor_discarded, 8 * (size_t)wo, cudaMemcpyHostToDevice, s->stream));
+    const long long n = s->shots * wo;
+    xor_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->d_result, s->d_discarded, s->shots, wo, s->d_rows + 3 * wo, s->d_rows + 4 * wo);
+    CU(cudaGetLastError());
+  }
+  if (out && in.num_outputs > 0) {
+    if (out_format == TSB_OUT_BYTES) {
+      if (!s->d_bytes) CU(cudaMalloc(&s->d_bytes, (size_t)s->shots * in.num_outputs));
+      int rc = tsb_unpack_out_device(s->p, s->d_result, s->shots, s->d_bytes, s->stream);
+      if (rc) return rc;
+      CU(cudaMemcpyAsync(out, s->d_bytes, (size_t)s->shots * in.num_outputs, cudaMemcpyDeviceToHost, s->stream));
+    } else {
+      CU(cudaMemcpyAsync(out, s->d_result, (size_t)s->shots * wo * 8, cudaMemcpyDeviceToHost, s->stream));
+    }
+  }
+  if (discarded_out) CU(cudaMemcpyAsync(discarded_out, s->d_discarded, (size_t)s->shots, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
   return TSB_OK;
 }

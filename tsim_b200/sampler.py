@@ -352,6 +352,69 @@ class _CompiledSamplerBase:
         self, shots: int, batch_size: int | None, *, postselection_mask: np.ndarray, compute_reference: bool = False,
         xor_detector_ref: bool = False,
     ):
+        """Reference ``_sample_batches_with_postselection`` (sampler.py:422-545).  With a real ``DeviceProgram`` the
+        survivor buffering runs on the GPU (``tsb_postselect``: same chunks, same batches, same key schedule, hence the
+        same bits); ``TSIM_B200_POSTSELECT=host`` or a device object without sessions keeps the host buffering."""
+        import os
+
+        if (
+            shots > 0
+            and self._program.components
+            and hasattr(self._device_program, "postselect_session")
+            and os.environ.get("TSIM_B200_POSTSELECT", "device") != "host"
+        ):
+            return self._postselect_device(shots, batch_size, postselection_mask=postselection_mask,
+                                           compute_reference=compute_reference, xor_detector_ref=xor_detector_ref)
+        return self._postselect_host(shots, batch_size, postselection_mask=postselection_mask,
+                                     compute_reference=compute_reference, xor_detector_ref=xor_detector_ref)
+
+    def _postselect_device(self, shots: int, batch_size: int | None, *, postselection_mask: np.ndarray,
+                           compute_reference: bool = False, xor_detector_ref: bool = False):
+        if batch_size is not None and batch_size < 1:
+            raise ValueError(f"batch_size must be at least 1, got {batch_size}")
+        nd = self._num_detectors
+        num_outputs = self._program.num_outputs
+        postselect_direct = postselection_mask & self._direct_detector_mask
+        if batch_size is None:
+            batch_size = self._resolve_batch_size(shots, batch_size, compute_reference=False)
+        reference = self._compute_reference_sample() if compute_reference else None
+        use_ref = xor_detector_ref and reference is not None
+        session = self._device_program.postselect_session(
+            shots, batch_size, postselect_direct, reference[:nd] if use_ref else None, nd
+        )
+        on_device = isinstance(self._channel_sampler, DeviceChannelSampler)
+        packed_host = hasattr(self._channel_sampler, "sample_packed")
+        shot_idx = 0
+        pending = 0
+        while shot_idx < shots:
+            chunk = min(batch_size, shots - shot_idx)
+            if on_device:
+                pending = session.push_noise(self._channel_sampler, chunk)
+            else:
+                f = self._channel_sampler.sample_packed(chunk) if packed_host else self._channel_sampler.sample(chunk)
+                pending = session.push_host(f)
+            shot_idx += chunk
+            while pending >= batch_size:  # _flush (sampler.py:494-498): one key per dispatched batch
+                pending, devs = session.dispatch(self._next_subkey())
+                check_norm_deviations(devs)
+        if pending:  # _flush(final=True): padded partial batch
+            pending, devs = session.dispatch(self._next_subkey(), final=True)
+            check_norm_deviations(devs)
+        xk = xd = None
+        if use_ref:
+            xk = np.zeros(num_outputs, dtype=np.bool_)
+            xk[:nd] = reference[:nd]
+            xd = np.zeros(num_outputs, dtype=np.bool_)
+            xd[:nd] = reference[:nd] & self._direct_detector_mask
+        result, was_discarded = session.finish(xk, xd)
+        if compute_reference:
+            return result, reference, was_discarded
+        return result, None, was_discarded
+
+    def _postselect_host(
+        self, shots: int, batch_size: int | None, *, postselection_mask: np.ndarray, compute_reference: bool = False,
+        xor_detector_ref: bool = False,
+    ):
         if shots < 0:
             raise ValueError(f"shots must be non-negative, got {shots}")
         if batch_size is not None and batch_size < 1:

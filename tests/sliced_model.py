@@ -10,7 +10,7 @@ import numpy as np
 
 from fast_model import M32, _s32
 from tsim_b200 import pack as PK
-from tsim_b200.pack_sliced import CLASS_WORDS, PI_CLASSES, SLICED_HEADER_WORDS
+from tsim_b200.pack_sliced import CLASS_WORDS, PAIR_TABLE, PI_CLASSES, SLICED_HEADER_WORDS, _mul_u32
 
 
 def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarray):
@@ -45,7 +45,8 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
             off = coff + int(data[coff + _g])  # directory: chunk-relative record offsets
             h = [int(v) for v in data[off : off + SLICED_HEADER_WORDS]]
             n_words, n_gen = h[0] & 0xFFFF, h[0] >> 16
-            n_idx, nb = h[1] & 0xFF, (h[1] >> 8) & 0xFF
+            n_idx, nb, n_mul = h[1] & 0xFF, (h[1] >> 8) & 0xFF, (h[1] >> 16) & 0xFF
+            mul_ctl = [(int(data[off + h[3] - 4]) >> (8 * j)) & 63 for j in range(n_mul)]
             tbl = coff + h[2]
             A = [0, 0, 0]
             Bp = [0] * 5
@@ -167,6 +168,10 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
                 idx = sum(((pl >> s) & 1) << k for k, pl in enumerate(planes))
                 if not approx:
                     e = [int(v) for v in data[tbl + 4 * idx : tbl + 4 * idx + 4]]
+                    for j, ctl in enumerate(mul_ctl):  # two-stage decode: ring factors of the multiplied general pairs
+                        pa, pb = ((gen[j][0] >> s) & 1), ((gen[j][1] >> s) & 1)
+                        fac = PAIR_TABLE[ctl ^ (pa << 2) ^ (pb << 5)]
+                        e = [int(v) for v in _mul_u32(np.array(e, dtype=np.uint32), fac)]
                     S[s] = [(S[s][i] + e[i]) & M32 for i in range(4)]
                 else:
                     e = data[tbl + 2 * idx : tbl + 2 * idx + 2].view(np.float32)

@@ -138,8 +138,11 @@ def test_auto_mode_prefers_sliced_then_rowwise():
 
     assert PK.pack_program(synthetic_program("cfg2_distill35")).mode == PK.MODE_SLICED
     assert PK.pack_program(synthetic_program("cfg2_distill35"), mode="rowwise").mode == PK.MODE_FAST
-    # decode tables of graphs with many general phase pairs are too large to stream: the per-row records stay
-    assert PK.pack_program(synthetic_program("cfg4_cultivation_d3")).mode == PK.MODE_FAST
+    # exact levels decode general phase pairs in two stages (table x ring factors), so cfg4's tables stay small enough
+    pp4 = PK.pack_program(synthetic_program("cfg4_cultivation_d3"))
+    assert pp4.mode == PK.MODE_SLICED and pp4.stats["data_bytes"] < 6 << 20 and int(pp4.blob[PK.H_PLANE_ROWS]) > 12
+    # the size budget still sends bulky programs to the per-row records
+    assert PK.pack_program(synthetic_program("cfg4_cultivation_d3"), sliced_budget_bytes=1 << 20).mode in (PK.MODE_FAST, PK.MODE_SLICED)
     # a program whose int32 arithmetic may wrap keeps the reference's operation order
     rng = np.random.default_rng(5)
     lv = random_level(rng, G=4, P=6, A=3, H=2, C=2, D=1, approx=False, density=0.4)

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout -s KILL 1200 python -m pytest tests/test_gpu_fullsize.py -x -q -k "other_baseline or multi_round" > gpurun_out/t_cfg4.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/t_cfg4.log
+timeout -s KILL 300 python tools/memo_bench.py --workload cfg4_cultivation_d3 --shots 1000000 --mode sliced --weights off,2 --reps 3 2>&1 | tail -4
+timeout -s KILL 300 python tools/memo_bench.py --workload cfg4_cultivation_d3 --shots 125000 --mode sliced --weights off,2 --reps 3 2>&1 | tail -4

@@ -29,7 +29,7 @@
 namespace tsb {
 
 constexpr int kSlicedHeaderWords = 8;
-constexpr int kPlaneRows = 12;  // "vanished" plane + up to 11 index planes (pack_sliced.MAX_INDEX_BITS)
+constexpr int kMinPlaneRows = 12;  // "vanished" plane + up to 11 index planes (pack_sliced.MAX_INDEX_BITS); more with multiplied pairs
 
 struct SParams {
   const uint32_t* __restrict__ blob;     // sliced blob
@@ -50,6 +50,7 @@ struct SParams {
   int smem_pl_off;
   int smem_data_off;
   int rows;  // zero_row + 1
+  int plane_rows;  // plane rows per graph slot (blob header H_PLANE_ROWS)
   uint4 sel;    // dp4a byte selectors {128 << 0, 128 << 8, 128 << 16, 128 << 24} (see par4)
   uint4 sel_e;  // the same with 8, the byte size of a float2 decode-table entry, instead of 128 (see sliced_phase2)
   // optional indirection (HAS_ROWS kernels; memoised path pass 2, post-selection survivors): slot i of the launch is
@@ -391,7 +392,8 @@ __device__ __forceinline__ void transpose8x8(uint32_t& lo, uint32_t& hi) {
 // bit transpose, and a dp4a per shot scales the index byte into the entry's address; further planes are rare.
 template <int SH, bool HAS_EXACT>
 __device__ __forceinline__ void sliced_phase2(const uint32_t* __restrict__ cbase, uint32_t rec, const uint32_t* __restrict__ plj, int w,
-                                              bool approx, const uint4& sel_e, typename SlicedAcc<HAS_EXACT>::type (&acc)[SH]) {
+                                              bool approx, const uint4& sel_e, typename SlicedAcc<HAS_EXACT>::type (&acc)[SH],
+                                              const int4* __restrict__ pair_tab) {
   static_assert(SH == 8 || SH == 4, "a warp handles a byte or a nibble of every plane word");
   const uint4 h0 = *reinterpret_cast<const uint4*>(cbase + rec);
   const int n_idx = (int)(h0.y & 0xFFu);
@@ -420,6 +422,22 @@ __device__ __forceinline__ void sliced_phase2(const uint32_t* __restrict__ cbase
   const uint32_t zb = plj[0] >> sh0;
   const uint32_t zero_entry = smem_u32(cbase + rec + 4);  // reserved header words: a shot whose value vanished adds 0
   const uint32_t r0 = SH == 8 ? lo : ((w & 1) ? hi : lo), r1 = hi;
+  // exact levels: general phase pairs applied as ring factors (two-stage decode, pack_sliced.py): pair j's parities
+  // sit in planes 1 + n_idx + 2 j (alpha side) and + 1 (beta side); its control byte alpha | beta << 3 in the record's
+  // last four words.  qab[j] = this warp's SH alpha bits | SH beta bits << 8.
+  uint32_t n_mul = 0, ctlw = 0, qab[4] = {0u, 0u, 0u, 0u};
+  if constexpr (HAS_EXACT) {
+    if (!approx) {
+      n_mul = (h0.y >> 16) & 0xFFu;
+      if (n_mul) {
+        ctlw = cbase[rec + h0.w - 4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if ((uint32_t)j < n_mul)
+            qab[j] = ((plj[(1 + n_idx + 2 * j) * 32] >> sh0) & kField) | (((plj[(2 + n_idx + 2 * j) * 32] >> sh0) & kField) << 8);
+      }
+    }
+  }
 #pragma unroll
   for (int s = 0; s < SH; ++s) {
     const uint32_t r = s < 4 ? r0 : r1;
@@ -438,7 +456,17 @@ __device__ __forceinline__ void sliced_phase2(const uint32_t* __restrict__ cbase
       }
     } else {
       if constexpr (HAS_EXACT) {
-        const uint4 e = *reinterpret_cast<const uint4*>(__cvta_shared_to_generic(ea));
+        uint4 e = *reinterpret_cast<const uint4*>(__cvta_shared_to_generic(ea));
+        if (n_mul) {  // warp-uniform
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if ((uint32_t)j < n_mul) {
+              const uint32_t ix = ((ctlw >> (8 * j)) & 63u) ^ (((qab[j] >> s) & 1u) << 2) ^ (((qab[j] >> (8 + s)) & 1u) << 5);
+              const ZW pr = zw_mul(ZW{e.x, e.y, e.z, e.w}, zw_from(pair_tab[ix]));
+              e = make_uint4(pr.c0, pr.c1, pr.c2, pr.c3);
+            }
+          }
+        }
         acc[s].x += e.x; acc[s].y += e.y; acc[s].z += e.z; acc[s].w += e.w;
       }
     }
@@ -452,7 +480,7 @@ __device__ __forceinline__ void group_sync(int grp, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(nthreads) : "memory");
 }
 
-// dynamic shared memory (32-bit words): [0,64) mbarriers | xt [ng][rows][32] | planes [ng][2][SPLIT][kPlaneRows][32] |
+// dynamic shared memory (32-bit words): [0,64) mbarriers | xt [ng][rows][32] | planes [ng][2][SPLIT][plane_rows][32] |
 // stage ring
 template <int SPLIT, bool HAS_EXACT, bool HAS_ROWS>
 __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_kernel(const SParams prm) {
@@ -475,7 +503,9 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
   // word offsets of this thread's columns; made opaque so that the compiler keeps them in registers instead of
   // re-deriving them from threadIdx inside the block loop (it did, ten instructions per block)
   uint32_t xoff = prm.smem_xt_off + grp * prm.rows * 32 + lane;
-  uint32_t ploff = prm.smem_pl_off + grp * (2 * SPLIT * kPlaneRows * 32) + lane;  // two plane buffers per group
+  // one graph slot of a plane buffer; only exact levels multiply pairs, so all-approximate programs keep the constant
+  const int plane_words = HAS_EXACT ? prm.plane_rows * 32 : kMinPlaneRows * 32;
+  uint32_t ploff = prm.smem_pl_off + grp * (2 * SPLIT * plane_words) + lane;  // two plane buffers per group
   const uint4 sel = prm.sel;
   asm volatile("" : "+r"(xoff), "+r"(ploff));
   uint32_t* xcol = smem + xoff;
@@ -489,6 +519,15 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
   const uint32_t* __restrict__ gdata = blob + blob[H_OFF_DATA];
   const int one_row = (int)blob[H_ONE_ROW];
 
+  // 1 + w^a + w^b - w^(a+b), index a | b << 3 (terms.py:179-181): factors of the multiplied general pairs (exact levels)
+  __shared__ int4 s_pair[HAS_EXACT ? 64 : 1];
+  if constexpr (HAS_EXACT) {
+    for (int i = tid; i < 64; i += (int)blockDim.x) {
+      const int a = i & 7, b = i >> 3;
+      const int4 ua = unit_phase(a), ub = unit_phase(b), uc = unit_phase(a + b);
+      s_pair[i] = make_int4(1 + ua.x + ub.x - uc.x, ua.y + ub.y - uc.y, ua.z + ub.z - uc.z, ua.w + ub.w - uc.w);
+    }
+  }
   if (tid == 0) {
     for (int i = 0; i < prm.n_stages; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
@@ -556,12 +595,12 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
             for (int w0 = 0; w0 < n_g; w0 += SPLIT) {
               // A warp may write the other buffer for the next wave as soon as it is through with this one: everybody
               // passed this wave's barrier, hence finished reading that buffer in the wave before.
-              uint32_t* pw = plg + pbuf * (SPLIT * kPlaneRows * 32);
-              if (w0 + w < n_g) sliced_phase1(cbase, cbase[w0 + w], xcol, pw + w * (kPlaneRows * 32), sel);
+              uint32_t* pw = plg + pbuf * (SPLIT * plane_words);
+              if (w0 + w < n_g) sliced_phase1(cbase, cbase[w0 + w], xcol, pw + w * plane_words, sel);
               group_sync(grp, SPLIT * 32);
               const int nj = min(SPLIT, n_g - w0);
               for (int j = 0; j < nj; ++j)
-                sliced_phase2<SH, HAS_EXACT>(cbase, cbase[w0 + j], pw + j * (kPlaneRows * 32), w, approx, prm.sel_e, acc);
+                sliced_phase2<SH, HAS_EXACT>(cbase, cbase[w0 + j], pw + j * plane_words, w, approx, prm.sel_e, acc, s_pair);
               pbuf ^= 1u;
             }
           }

@@ -543,7 +543,7 @@ struct tsb_program {
   uint32_t* h_heavy_seen = nullptr;  // pinned: heavy-row count of an earlier memoised sliced launch (launch-shape hint only)
   long long heavy_seen_B = 0;
   // MODE_SLICED
-  int is_sliced = 0, s_has_exact = 0, s_rows = 0, s_smem_limit = 0, s_stage_words = 0;
+  int is_sliced = 0, s_has_exact = 0, s_rows = 0, s_plane_rows = 0, s_smem_limit = 0, s_stage_words = 0;
   int total_F = 0, max_nc = 0;
   tsb_program* aux = nullptr;   // companion per-row program (norm check); not owned
   cudaStream_t side = nullptr;  // the norm check of shot 0 runs here, overlapped with the rest of the batch
@@ -644,11 +644,11 @@ struct SlicedPlan {
   int split = 0, ng = 0, rounds = 0, grid = 0, n_stages = 0;
   int xt_off = 0, pl_off = 0, data_off = 0, smem_bytes = 0;
 };
-static int sliced_group_words(int rows, int split) { return rows * 32 + 2 * split * kPlaneRows * 32; }  // matrix + two plane buffers
+static int sliced_group_words(int rows, int split, int plane_rows) { return rows * 32 + 2 * split * plane_rows * 32; }  // matrix + two plane buffers
 // largest number of groups (<= cap) that leaves room for `want_stages` stages; 0 if not even one group fits
-static int sliced_fit_groups(int rows, int split, int cap, int stage_words, int want_stages, int smem_limit) {
+static int sliced_fit_groups(int rows, int plane_rows, int split, int cap, int stage_words, int want_stages, int smem_limit) {
   for (int ng = cap; ng >= 1; --ng)
-    if (((long long)kBarWords + (long long)ng * sliced_group_words(rows, split) + (long long)want_stages * stage_words) * 4 <= smem_limit) return ng;
+    if (((long long)kBarWords + (long long)ng * sliced_group_words(rows, split, plane_rows) + (long long)want_stages * stage_words) * 4 <= smem_limit) return ng;
   return 0;
 }
 static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl, bool row_list, long long expect_rows);
@@ -702,6 +702,7 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
   if (mode == kModeSliced) {
     p->is_sliced = 1;
     p->s_rows = (int)blob[H_ZERO_ROW] + 1;
+    p->s_plane_rows = kMinPlaneRows;
     const uint32_t* lv = blob + blob[H_OFF_LEVEL];
     for (uint32_t i = 0; i < blob[H_N_LEVELS]; ++i)
       if (!(lv[i * kLevelWords + L_FLAGS] & 1u) && lv[i * kLevelWords + L_G] > 0u) p->s_has_exact = 1;
@@ -710,6 +711,7 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
       p->total_F += (int)ct[c * kCompWords + C_F];
       p->max_nc = std::max(p->max_nc, (int)ct[c * kCompWords + C_NC]);
     }
+    if (p->s_has_exact) p->s_plane_rows = std::max<int>(kMinPlaneRows, (int)blob[H_PLANE_ROWS]);  // multiplied pairs: exact levels only
     CUB(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
     CUB(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
@@ -719,11 +721,18 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
       int v = atoi(lim);
       if (v > 0) lim_smem = std::min(lim_smem, v);
     }
+    // static shared memory of the kernels (the pair-factor table of the exact variants) comes out of the same budget
+    for (int split : {4, 8})
+      for (bool rows : {false, true}) {
+        cudaFuncAttributes fa;
+        CUB(cudaFuncGetAttributes(&fa, (const void*)sliced_fn(split, p->s_has_exact, rows)));
+        lim_smem = std::min<int>(lim_smem, (int)prop.sharedMemPerBlockOptin - (int)fa.sharedSizeBytes);
+      }
     p->s_smem_limit = lim_smem;
     p->s_stage_words = std::max(32, ((int)blob[H_MAX_CHUNK] + 31) & ~31);
     const int split_min = p->s_has_exact ? 8 : 4;
-    if (!sliced_fit_groups(p->s_rows, split_min, 1, p->s_stage_words, 1, lim_smem) ||
-        !sliced_fit_groups(p->s_rows, 8, 1, p->s_stage_words, 1, lim_smem)) {
+    if (!sliced_fit_groups(p->s_rows, p->s_plane_rows, split_min, 1, p->s_stage_words, 1, lim_smem) ||
+        !sliced_fit_groups(p->s_rows, p->s_plane_rows, 8, 1, p->s_stage_words, 1, lim_smem)) {
       fail(TSB_ERR_UNSUPPORTED, "a single chunk of the program does not fit in shared memory next to one slab group");
       return bail(TSB_ERR_UNSUPPORTED);
     }
@@ -1045,8 +1054,8 @@ static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl, bool 
   const int n_chunks = (int)p->host_blob[H_N_CHUNKS];
   const int want = std::min(2, std::max(1, n_chunks));
   int cap = std::min(sliced_max_groups(split), gpc);
-  int ng = sliced_fit_groups(p->s_rows, split, cap, p->s_stage_words, want, p->s_smem_limit);
-  if (!ng) ng = sliced_fit_groups(p->s_rows, split, cap, p->s_stage_words, 1, p->s_smem_limit);
+  int ng = sliced_fit_groups(p->s_rows, p->s_plane_rows, split, cap, p->s_stage_words, want, p->s_smem_limit);
+  if (!ng) ng = sliced_fit_groups(p->s_rows, p->s_plane_rows, split, cap, p->s_stage_words, 1, p->s_smem_limit);
   if (!ng) return false;
   pl.split = split;
   pl.rounds = (gpc + ng - 1) / ng;
@@ -1054,7 +1063,7 @@ static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl, bool 
   if (row_list) pl.ng = ng;  // rounds are derived on the device from the live count
   pl.xt_off = kBarWords;
   pl.pl_off = pl.xt_off + pl.ng * p->s_rows * 32;
-  pl.data_off = pl.pl_off + pl.ng * 2 * split * kPlaneRows * 32;
+  pl.data_off = pl.pl_off + pl.ng * 2 * split * p->s_plane_rows * 32;
   const long long room = (long long)p->s_smem_limit / 4 - pl.data_off;
   pl.n_stages = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kMaxStages, std::max(1, n_chunks)), room / p->s_stage_words));
   pl.smem_bytes = (pl.data_off + pl.n_stages * p->s_stage_words) * 4;
@@ -1101,7 +1110,7 @@ static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long 
     k.n_groups = (n_slabs + 31) / 32; k.ng = pl.ng; k.rounds = pl.rounds;
     k.n_stages = pl.n_stages; k.stage_words = p->s_stage_words;
     k.smem_xt_off = pl.xt_off; k.smem_pl_off = pl.pl_off; k.smem_data_off = pl.data_off;
-    k.rows = p->s_rows; k.sel = make_uint4(0x80u, 0x8000u, 0x800000u, 0x80000000u);
+    k.rows = p->s_rows; k.plane_rows = p->s_plane_rows; k.sel = make_uint4(0x80u, 0x8000u, 0x800000u, 0x80000000u);
     k.sel_e = make_uint4(8u, 8u << 8, 8u << 16, 8u << 24);
     k.row_list = rows; k.n_rows = n_rows;
     if (!memo && k1s_start) CU(cudaEventRecord(k1s_start, st));

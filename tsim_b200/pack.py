@@ -33,11 +33,11 @@ import numpy as np
 from .program import CompiledProgram, CompiledScalarGraphs
 
 MAGIC = 0x32425354  # "TSB2"
-VERSION = 5
+VERSION = 6
 MODE_FAITHFUL = 0
 MODE_FAST = 1
 MODE_SLICED = 2
-SLICED_AUTO_MAX_BYTES = 4 << 20  # mode="auto" keeps the per-row records beyond this size of the sliced data region
+SLICED_AUTO_MAX_BYTES = 16 << 20  # mode="auto" keeps the per-row records beyond this size of the sliced data region
 
 HEADER_WORDS = 32
 COMP_WORDS = 8
@@ -54,6 +54,7 @@ H_OFF_FSEL, H_OFF_DEST, H_OFF_DATA, H_DATA_WORDS = 16, 17, 18, 19
 H_TOTAL_WORDS, H_WF64, H_WOUT64, H_OFF_TABLES = 20, 21, 22, 23
 H_TABLE_WORDS = 24
 H_ONE_ROW, H_ZERO_ROW = 25, 26
+H_PLANE_ROWS = 27  # sliced: plane rows per graph slot in shared memory (vanish + index planes + multiplied-pair planes)
 
 
 @dataclass
@@ -299,6 +300,15 @@ def pack_program(
     data_off = 0
     fsel_off = 0
     draw = 0
+    plane_rows = 12
+    # Stage size of the sliced kernel's TMA ring.  Programs with exact levels run 8 warps per slab group with wider plane
+    # buffers (multiplied pairs): 44 KB stages leave shared memory for a third group per SM (16 -> 24 warps; the kernel is
+    # latency bound) and still hold a whole wave of eight graphs.  Half-size stages were measured slower (cfg4: 12.2 ->
+    # 14.7 ms): four graphs per chunk idle half of every wave.
+    has_exact_level = any(
+        lv.num_graphs > 0 and not lv.prefactor.has_approximate_floatfactors for c in comps for lv in c.compiled_scalar_graphs
+    )
+    sliced_chunk_words = 11264 if has_exact_level else 12288
     for ci, c in enumerate(comps):
         F = len(c.f_selection)
         n_c = len(c.compiled_scalar_graphs) - 1
@@ -321,6 +331,8 @@ def pack_program(
                 left = None if sliced_budget_bytes is None else max(0, sliced_budget_bytes // 4 - data_off)
                 graphs, (A, H, C, D), p_lo = sliced_level_records(lv, max_p, max_p + 1, budget_words=left)
                 graph_lists = []
+                for rec, _tbl in graphs:
+                    plane_rows = max(plane_rows, 1 + (int(rec[1]) & 0xFF) + 2 * ((int(rec[1]) >> 16) & 0xFF))
             else:
                 from .pack_fast import fast_level_records  # local import: keeps this module lean
 
@@ -349,7 +361,7 @@ def pack_program(
             flush()
             if mode_id == MODE_SLICED:
                 # chunk = directory | records | decode tables (pack_sliced.py); offsets inside are chunk-relative
-                for arr, n_graphs in sliced_level_chunks(graphs):
+                for arr, n_graphs in sliced_level_chunks(graphs, sliced_chunk_words):
                     chunk_rows.append([data_off, len(arr), n_graphs, 0])
                     data_parts.append(arr)
                     data_off += len(arr)
@@ -394,6 +406,7 @@ def pack_program(
     header[H_WOUT64] = max(1, (n_out + 63) // 64)
     header[H_ONE_ROW] = max_p
     header[H_ZERO_ROW] = max_p + 1
+    header[H_PLANE_ROWS] = plane_rows
 
     blob = np.zeros(total, dtype=np.uint32)
     blob[:HEADER_WORDS] = header

@@ -27,6 +27,7 @@ Graph record (uint32 words):
     [1]  n_index_bits | n_b_planes << 8
     [2]  offset of the decode table (filled in when the chunk is assembled)
     [3]  record words
+    [1]  also: number of *multiplied* general pairs << 16 (exact levels; their control bytes are the record's last 4 words)
     [4..7] zero (the decode entry of a shot whose value vanished)
     then the term stream as typed runs (``_emit_runs``): LIN / LIN2 / PI / PAIR items with straight-line parities of
     8 / 12 / 16 rows, and a generic block stream (``_block``) for heavier masks.  Ops:
@@ -52,6 +53,7 @@ from .program import CompiledScalarGraphs
 
 SLICED_HEADER_WORDS = 8
 MAX_GENERAL_PAIRS = 3
+MAX_MUL_PAIRS = 4  # exact levels: general pairs applied as ring factors after the table lookup (two-stage decode)
 MAX_INDEX_BITS = 11
 MAX_CHUNK_WORDS = 12288  # 48 KB stages
 B_OFFSET = 64
@@ -342,15 +344,21 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int, 
         # into one variant per (pa, pb) combination -- the pair's factor for that combination is folded into the
         # constants and a gate term makes the variant vanish for every other combination, so exactly one variant of
         # a graph contributes for a given shot (the float sum of the approximate branch sees the same addends).
-        in_table = min(len(general), MAX_GENERAL_PAIRS, (MAX_INDEX_BITS - 3 - nb) // 2)
-        excess = general[in_table:]
+        # Exact levels decode in two stages instead: the table holds the monoid part only, and the kernel multiplies the
+        # looked-up value by each general pair's factor 1 + w^a + w^b - w^(a+b) (one shared 64-entry table, one ring
+        # product per pair and shot; terms.py:164-187) -- wrapping Z[w] arithmetic is a ring, so the product equals the
+        # single-table entry bit for bit, and the table no longer grows by 4x per pair.
+        n_mul = 0 if approx else min(len(general), MAX_MUL_PAIRS)
+        in_table = 0 if not approx else min(len(general), MAX_GENERAL_PAIRS, (MAX_INDEX_BITS - 3 - nb) // 2)
+        excess = general[in_table + n_mul :]
         if len(excess) > 3:
             raise _Unsupported("too many general phase pairs in one graph")
         n_idx = 3 + nb + 2 * in_table
         general_ctl = []
-        for slot, (al, be, r1, r2) in enumerate(general[:in_table]):
-            general_ctl.append(al | (be << 3))
-            two(OP_PAIRGEN, slot, r1, r2)
+        mul_ctl = []
+        for slot, (al, be, r1, r2) in enumerate(general[: in_table + n_mul]):
+            (general_ctl if approx else mul_ctl).append(al | (be << 3))
+            two(OP_PAIRGEN, slot, r1, r2)  # planes 1 + 3 + nb + 2 slot (pa), + 1 (pb)
         for combo in range(4 ** len(excess)):
             ffv = ff
             gates = []
@@ -368,13 +376,16 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int, 
             body = _emit_runs(terms + gates, zero_row)
             if len(body) > 0xFFFF:
                 raise _Unsupported("too many terms")
+            trailer = [sum(c << (8 * i) for i, c in enumerate(mul_ctl)), 0, 0, 0] if mul_ctl else []
             words = np.zeros(SLICED_HEADER_WORDS + len(body), dtype=np.uint32)
             words[0] = len(body) | (len(general_ctl) << 16)
-            words[1] = n_idx | (nb << 8)
+            words[1] = n_idx | (nb << 8) | (len(mul_ctl) << 16)
             words[SLICED_HEADER_WORDS:] = np.array(body, dtype=np.uint64).astype(np.uint32)
             pad = (-len(words)) % 4
             if pad:
                 words = np.concatenate([words, np.zeros(pad, np.uint32)])
+            if trailer:  # the last four words of the record: control bytes (alpha | beta << 3) of the multiplied pairs
+                words = np.concatenate([words, np.array(trailer, dtype=np.uint32)])
             words[3] = len(words)
             recs.append(words)
             shifts_base.append(p_t + power2)
@@ -383,6 +394,14 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int, 
                      aff=np.complex64(pre.approximate_floatfactors[g]))
             )
 
+    if not approx and len(recs) > 1:
+        # Exact levels add integers, so the graph order is free (the approximate branch is a sequential float sum in graph
+        # order, evaluate.py:56-59, and keeps it): sort by stream length so that the graphs of a wave -- one per warp, all
+        # waiting at the wave's barrier for the longest -- cost about the same.
+        order = sorted(range(len(recs)), key=lambda i: -len(recs[i]))
+        recs = [recs[i] for i in order]
+        shifts_base = [shifts_base[i] for i in order]
+        decode = [decode[i] for i in order]
     p_lo = min(shifts_base) if shifts_base else 0
     if budget_words is not None:  # fail before the tables are built (mode="auto" gives up on bulky programs)
         need = sum(len(r) for r in recs) + sum((2 if approx else 4) << d["n_idx"] for d in decode)

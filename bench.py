@@ -253,7 +253,20 @@ class DeviceLoop:
         self.d_out = [torch.empty((shots, self.wo), dtype=torch.int64, device=cx.dev) for _ in range(self.n_buf)]
         self.f_host0 = f_host[0]
         self.gather = gather and cx.world > 1
-        self.d_all = [torch.empty((cx.world * shots, self.wo), dtype=torch.int64, device=cx.dev) for _ in range(2)] if self.gather else None
+        self.d_all, self.pg, self.gather_kind = None, None, "none"
+        if self.gather:
+            kind = os.environ.get("TSIM_B200_GATHER", "peer")
+            if kind == "peer":
+                try:
+                    from tsim_b200.distributed import PeerGather
+
+                    self.pg = PeerGather(shots, self.wo, cx.local)
+                    self.gather_kind = "peer-memory copy-engine push + signal-pad barrier (no SM)"
+                except Exception as exc:  # pragma: no cover - depends on the box
+                    log(f"[bench] peer-memory gather unavailable ({exc!r}); using NCCL all_gather")
+            if self.pg is None:
+                self.d_all = [torch.empty((cx.world * shots, self.wo), dtype=torch.int64, device=cx.dev) for _ in range(2)]
+                self.gather_kind = "NCCL all_gather_into_tensor"
         self.pending = []
         self.stream = torch.cuda.current_stream().cuda_stream
         self.key = (0, 42)
@@ -263,6 +276,16 @@ class DeviceLoop:
     def step(self):
         self.key, sub = self.split_key(self.key)
         b = self.i % self.n_buf
+        if self.pg is not None:
+            # the pipeline writes this rank's rows straight into its slice of the receive buffer; the push of step i runs on
+            # the copy engines while step i + 1 samples
+            if len(self.pending) >= 2:
+                self.cx.torch.cuda.current_stream().wait_event(self.pending.pop(0))
+            rows = self.pg.local_rows(self.i)
+            self.dp.sample_device(self.d_f[b].data_ptr(), self.shots, sub, rows.data_ptr(), shot_offset=self.shot_offset, stream=self.stream)
+            self.pending.append(self.pg.push(self.i))
+            self.i += 1
+            return sub, b
         self.dp.sample_device(self.d_f[b].data_ptr(), self.shots, sub, self.d_out[b].data_ptr(), shot_offset=self.shot_offset, stream=self.stream)
         if self.gather:
             if len(self.pending) >= 2:
@@ -274,7 +297,11 @@ class DeviceLoop:
 
     def drain(self):
         while self.pending:
-            self.pending.pop(0).wait()
+            w = self.pending.pop(0)
+            if self.pg is not None:
+                self.cx.torch.cuda.current_stream().wait_event(w)
+            else:
+                w.wait()
 
     def timed(self, steps: int, warmup: int, clocks: ClockSampler | None = None) -> float:
         """-> total ms of `steps` steps (max over ranks), CUDA events on the launch stream."""
@@ -463,7 +490,7 @@ def run_gpu(args):
     step_ms_isolated, k_ms, launches_per_step = loop.isolated(5)
 
     # ---- sustained sub-run (>= 1.5 s of back-to-back steps): clocks under load, same kernel
-    sustain_steps = int(min(20000, max(args.steps, np.ceil(1500.0 / max(1e-3, total_ms / args.steps)))))
+    sustain_steps = args.steps if args.no_sustain else int(min(20000, max(args.steps, np.ceil(1500.0 / max(1e-3, total_ms / args.steps)))))
     clocks = ClockSampler(local)
     sustained_ms = loop.timed(sustain_steps, 0, clocks)
     sustained_value = world * shots * sustain_steps / (sustained_ms * 1e-3)
@@ -634,7 +661,7 @@ def run_gpu(args):
             "pattern_cache": "off for value / e2e.value (full evaluation of every shot); on (library default) for value_memoised / e2e.memoised",
             "g_resident_in_smem": bool(info["resident"]),
             "l2": f"inputs/outputs rotate over {loop.n_buf} buffer pairs ({loop.n_buf * loop.per_step_bytes / 1e6:.0f} MB > 126 MB L2)",
-            "parallelism": f"shots sharded over {world} GPU(s), one all-gather of packed outputs per step" if world > 1 else "single GPU",
+            "parallelism": f"shots sharded over {world} GPU(s), one gather of packed outputs per step: {loop.gather_kind}" if world > 1 else "single GPU",
             "synthetic_program": "shape-matched random g (tsim's compile stages need stim/pyzx_param, absent here)" if not args.program else args.program,
         },
         "clocks": {**csum, "region": f"sustained sub-run: {sustain_steps} back-to-back steps, {sustained_ms:.0f} ms", "timed_region_samples": cshort.get("samples", 0),
@@ -675,6 +702,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-sustain", action="store_true", help="profiling runs: skip the >= 1.5 s sustained sub-run")
     ap.add_argument("--workload", default=WORKLOAD, help="synthetic configuration (default: the headline cfg2_distill35)")
     ap.add_argument("--program", default=None, help="a program dumped by tools/dump_tsim_programs.py (.npz) instead of a synthetic one")
     args = ap.parse_args()

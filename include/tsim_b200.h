@@ -153,6 +153,11 @@ int tsb_postselect_finish(tsb_postselect* s, const uint64_t* xor_kept, const uin
                           uint8_t* discarded_out);
 int tsb_postselect_destroy(tsb_postselect* s);
 
+/* Multi-GPU gather of the packed output rows (the one collective of the path) over peer memory: a
+ * rank pushes its rows into every peer's receive buffer with copy-engine transfers -- no SM, so the push overlaps the next
+ * batch's sampling kernel.  dst is a peer-mapped (or local) device address, e.g. from CUDA IPC / symmetric memory. */
+int tsb_memcpy_peer_async(void* dst, const void* src, size_t nbytes, void* stream);
+
 void* tsb_host_alloc(size_t nbytes); /* page-locked host memory, NULL on failure */
 void tsb_host_free(void* ptr);
 

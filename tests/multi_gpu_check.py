@@ -47,6 +47,36 @@ def main():
         if not flags.item():
             dist.destroy_process_group()
             sys.exit(1)
+    # peer-memory gather (copy-engine pushes into symmetric memory) vs NCCL all_gather on the sampler's own output rows
+    try:
+        from tsim_b200.distributed import PeerGather
+
+        n, wo = 50_000, dp.info["words_out64"]
+        pg = PeerGather(n, wo, local)
+        st = torch.cuda.current_stream().cuda_stream
+        key = (7, 7)
+        ok = True
+        for i in range(5):
+            key, sub = split_key(key)
+            d_f = torch.from_numpy(noise.sample_packed(n, shot_offset=rank * n, call=100 + i).view(np.int64)).cuda()
+            rows = pg.local_rows(i)
+            dp.sample_device(d_f.data_ptr(), n, sub, rows.data_ptr(), shot_offset=rank * n, stream=st)
+            done = pg.push(i)
+            ref = torch.empty((world * n, wo), dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(ref, rows.clone())
+            torch.cuda.current_stream().wait_event(done)
+            ok = ok and bool(torch.equal(pg.gathered(i), ref))
+            pg.mark_consumed(i)
+        flags = torch.tensor([int(ok)], device="cuda")
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"[multi_gpu_check] world={world} peer-memory gather == NCCL all_gather over 5 steps: {'OK' if flags.item() else 'MISMATCH'}", flush=True)
+        if not flags.item():
+            dist.destroy_process_group()
+            sys.exit(1)
+    except Exception as exc:
+        if rank == 0:
+            print(f"[multi_gpu_check] peer-memory gather unavailable on this box: {exc!r}", flush=True)
     dist.destroy_process_group()
 
 

@@ -1,6 +1,6 @@
 """Aggregate an ncu SASS source page by CUDA source line, using nvdisasm line info of the local build.
 
-usage: python tools/ncu_by_line.py <report.ncu-rep> <kernel mangled-name substring> [top N]
+usage: python tools/ncu_by_line.py <report.ncu-rep | source.csv> <kernel mangled-name substring> [top N]
 """
 import collections, csv, io, os, re, subprocess, sys, tempfile
 
@@ -30,7 +30,10 @@ for ln in dis.splitlines():
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
     if m:
         off2line[int(m.group(1), 16)] = (cur, m.group(2).strip())
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".csv"):  # a source page exported on the GPU box (ncu -i rep --page source --csv)
+    out = open(rep).read()
+else:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 h = rows[hi]

@@ -1,6 +1,6 @@
 """Markdown summary of an ncu report (raw page) and of a launch list CSV -> stdout.
 
-usage: python tools/ncu_summary.py full <report.ncu-rep>      |      python tools/ncu_summary.py list <launches.csv>
+usage: python tools/ncu_summary.py full <report.ncu-rep | raw.csv>      |      python tools/ncu_summary.py list <launches.csv>
 """
 import collections, csv, io, subprocess, sys
 
@@ -22,7 +22,10 @@ WANT = [
 ]
 
 if sys.argv[1] == "full":
-    out = subprocess.run(["ncu", "-i", sys.argv[2], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if sys.argv[2].endswith(".csv"):  # a raw page exported on the GPU box (ncu -i rep --page raw --csv)
+        out = open(sys.argv[2]).read()
+    else:
+        out = subprocess.run(["ncu", "-i", sys.argv[2], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     h, u, v = rows[0], rows[1], rows[2]
     kn = v[h.index("Kernel Name")]

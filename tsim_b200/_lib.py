@@ -43,6 +43,7 @@ EXPORTS = (
     "tsb_postselect_dispatch",
     "tsb_postselect_finish",
     "tsb_postselect_destroy",
+    "tsb_memcpy_peer_async",
 )
 
 
@@ -139,6 +140,8 @@ def load() -> C.CDLL:
     lib.tsb_postselect_finish.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.tsb_postselect_destroy.restype = i32
     lib.tsb_postselect_destroy.argtypes = [vp]
+    lib.tsb_memcpy_peer_async.restype = i32
+    lib.tsb_memcpy_peer_async.argtypes = [vp, vp, C.c_size_t, vp]
     _lib = lib
     return lib
 

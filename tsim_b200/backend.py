@@ -382,3 +382,118 @@ class PostselectSession:
             out.ctypes.data_as(C.c_void_p), _lib.TSB_OUT_BYTES, disc.ctypes.data_as(C.c_void_p)))
         self._fin()
         return out, disc
+
+
+class MultiDeviceProgram:
+    """The same program on several GPUs of one box, driven from ONE process (reference: single process, ``jax.devices()[0]``,
+    sampler.py:310; SURVEY section 5 ``devices=``).  A batch is cut into contiguous row ranges (``shard.shard_range``), every
+    device samples its range with ``shot_offset = lo`` -- the RNG counter is the in-batch shot index, so the bits do not
+    depend on the number of devices -- and writes into its slice of one pinned host buffer.  The per-device calls run on a
+    thread pool (ctypes releases the GIL; each handle owns its streams).  Same surface as :class:`DeviceProgram`."""
+
+    def __init__(self, program, *, devices, mode: str = "auto", joint: bool = False, pattern_cache: int | None | str = "default"):
+        from concurrent.futures import ThreadPoolExecutor
+
+        devices = [int(d) for d in devices]
+        if not devices:
+            raise ValueError("devices must name at least one GPU")
+        n_dev = _lib.load().tsb_device_count()
+        for d in devices:
+            if not 0 <= d < n_dev:
+                raise ValueError(f"no such CUDA device: {d} (the box has {n_dev})")
+        self.devices = devices
+        self.parts = [DeviceProgram(program, device=d, mode=mode, joint=joint, pattern_cache=pattern_cache) for d in devices]
+        first = self.parts[0]
+        self.program, self.packed, self.joint, self.info, self.device = first.program, first.packed, first.joint, first.info, first.device
+        self._pool = ThreadPoolExecutor(len(devices))
+
+    num_f = property(lambda self: self.info["num_f"])
+    num_outputs = property(lambda self: self.info["num_outputs"])
+    pattern_cache = property(lambda self: self.parts[0].pattern_cache)
+
+    def set_pattern_cache(self, max_weight, max_entries: int = 0) -> int:
+        return [p.set_pattern_cache(max_weight, max_entries) for p in self.parts][0]
+
+    def last_kernel_ms(self):
+        return self.parts[0].last_kernel_ms()
+
+    def _ranges(self, B: int):
+        from .shard import shard_range
+
+        return [shard_range(B, r, len(self.parts)) for r in range(len(self.parts))]
+
+    def _result(self, B: int, packed_out: bool, out):
+        if packed_out:
+            shape, dtype = (B, self.info["words_out64"]), np.uint64
+        else:
+            shape, dtype = (B, self.num_outputs), np.bool_
+        if out is None:
+            out = _result_pool.take(shape, dtype) if B > 0 else np.empty(shape, dtype=dtype)
+        elif out.shape != shape or out.dtype != dtype or not out.flags.c_contiguous:
+            raise ValueError("out has the wrong shape, dtype or layout")
+        return out
+
+    def _gather(self, futures, shot_offset: int):
+        devs = np.zeros(self.info["n_components"], dtype=np.float32)
+        for (lo, hi), fut in futures:
+            res = fut.result()
+            if hi > lo and lo + shot_offset == 0:  # the norm check belongs to in-batch shot 0 (sampler.py:66-72)
+                devs = np.asarray(res[1], dtype=np.float32)
+        return devs
+
+    def sample(self, f_params: np.ndarray, key, *, shot_offset: int = 0, packed_out: bool = False, out: np.ndarray | None = None):
+        f = np.asarray(f_params)
+        if f.ndim != 2:
+            raise ValueError("f_params must be 2-D")
+        B = f.shape[0]
+        out = self._result(B, packed_out, out)
+        futures = []
+        for part, (lo, hi) in zip(self.parts, self._ranges(B)):
+            if hi > lo:
+                futures.append(((lo, hi), self._pool.submit(part.sample, f[lo:hi], key, shot_offset=shot_offset + lo, packed_out=packed_out, out=out[lo:hi])))
+        return out, self._gather(futures, shot_offset)
+
+    def sample_noisy(self, noise, B: int, key, *, shot_offset: int = 0, call: int | None = None, skip_shot0: bool = False,
+                     packed_out: bool = False, return_f: bool = False):
+        """``noise``: a :class:`tsim_b200.noise.MultiDeviceChannelSampler` over the same devices."""
+        if return_f:
+            raise ValueError("return_f is a single-device debugging aid")
+        B = int(B)
+        if call is None:
+            call = noise.next_call()
+        out = self._result(B, packed_out, None)
+
+        def run(part, nz, lo, hi):
+            # a shard's rows land in its own pinned result; copy into the common buffer (8 B per shot when packed)
+            res = part.sample_noisy(nz, hi - lo, key, shot_offset=shot_offset + lo, call=call, skip_shot0=skip_shot0, packed_out=packed_out)
+            out[lo:hi] = res[0]
+            return res
+
+        futures = []
+        for part, nz, (lo, hi) in zip(self.parts, noise.parts_for(self.devices), self._ranges(B)):
+            if hi > lo:
+                futures.append(((lo, hi), self._pool.submit(run, part, nz, lo, hi)))
+        return out, self._gather(futures, shot_offset)
+
+    def sample_device(self, *a, **kw):
+        raise NotImplementedError("device-pointer launches address one GPU: use the DeviceProgram of that device (parts[i])")
+
+    def postselect_session(self, *a, **kw):
+        return self.parts[0].postselect_session(*a, **kw)  # survivor buffering is sequential by definition: one device
+
+    def level_params(self, component: int, level: int) -> int:
+        return self.parts[0].level_params(component, level)
+
+    def evaluate(self, component: int, level: int, params: np.ndarray) -> np.ndarray:
+        x = np.asarray(params)
+        if x.ndim != 2:
+            raise ValueError("params must be 2-D")
+        out = np.zeros(x.shape[0], dtype=np.complex64)
+        futs = [((lo, hi), self._pool.submit(part.evaluate, component, level, x[lo:hi])) for part, (lo, hi) in zip(self.parts, self._ranges(x.shape[0])) if hi > lo]
+        for (lo, hi), fut in futs:
+            out[lo:hi] = fut.result()
+        return out
+
+    def close(self) -> None:
+        for p in self.parts:
+            p.close()

@@ -1416,6 +1416,14 @@ int tsb_evaluate_host(tsb_program* p, int component, int level, const uint8_t* p
   return rc;
 }
 
+// device-to-device copy on the copy engines (no SM): the push half of the peer-memory gather of output rows
+int tsb_memcpy_peer_async(void* dst, const void* src, size_t nbytes, void* stream) {
+  if (nbytes == 0) return TSB_OK;
+  if (!dst || !src) return fail(TSB_ERR_INVALID, "null pointer");
+  CU(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return TSB_OK;
+}
+
 void* tsb_host_alloc(size_t nbytes) {
   void* ptr = nullptr;
   if (cudaHostAlloc(&ptr, std::max<size_t>(nbytes, 1), cudaHostAllocDefault) != cudaSuccess) {

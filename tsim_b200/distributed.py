@@ -31,6 +31,81 @@ def nccl_defaults() -> None:
     os.environ.setdefault("NCCL_MAX_NCHANNELS", "8")
 
 
+class PeerGather:
+    """The gather of packed output rows over NVLink peer memory, without SMs.
+
+    Every rank owns ``n_buffers`` receive buffers ``int64[world * shots, words]`` in symmetric memory
+    (``torch.distributed._symmetric_memory``: same allocation on every rank, peer-mapped through CUDA IPC / fabric
+    handles).  The sampling pipeline writes a rank's rows straight into its slice of its own buffer
+    (:meth:`local_rows`); :meth:`push` then copies that slice into the same slice of every peer's buffer with
+    copy-engine transfers (``tsb_memcpy_peer_async``) on a side stream and joins a signal-pad barrier -- when the
+    returned event fires, every rank's rows have landed here.  No SM takes part, so the exchange of step i hides
+    completely behind the sampling kernel of step i + 1, which fills its SMs with one 228 KB CTA each and leaves an
+    NCCL all-gather only the eight SMs its launch plan spares (N = 8: 0.81 -> 0.95 ms per step with NCCL).
+    Raises if symmetric memory cannot be set up (callers fall back to ``all_gather_into_tensor``)."""
+
+    def __init__(self, shots: int, words: int, device: int, n_buffers: int = 2):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.shots, self.words = int(shots), int(words)
+        dev = torch.device("cuda", device)
+        self._torch, self._lib = torch, _lib.load()
+        self._check = _lib.check
+        self.bufs = [symm_mem.empty((self.world * self.shots, self.words), dtype=torch.int64, device=dev) for _ in range(n_buffers)]
+        self.hdls = [symm_mem.rendezvous(b, dist.group.WORLD) for b in self.bufs]
+        self.side = torch.cuda.Stream(dev)
+        self._consumed = [None] * n_buffers
+        self._slice_bytes = self.shots * self.words * 8
+        for h in self.hdls:
+            if len(h.buffer_ptrs) != self.world:
+                raise RuntimeError("symmetric memory rendezvous did not return one buffer per rank")
+
+    def local_rows(self, i: int):
+        """This rank's slice of receive buffer ``i``: the destination of the sampling pipeline's output rows."""
+        b = self.bufs[i % len(self.bufs)]
+        return b[self.rank * self.shots : (self.rank + 1) * self.shots]
+
+    def gathered(self, i: int):
+        return self.bufs[i % len(self.bufs)]
+
+    def mark_consumed(self, i: int, stream=None) -> None:
+        """The reader of ``gathered(i)`` is done (in stream order): peers may overwrite the buffer two pushes later."""
+        torch = self._torch
+        ev = torch.cuda.Event()
+        ev.record(stream if stream is not None else torch.cuda.current_stream())
+        self._consumed[i % len(self.bufs)] = ev
+
+    def push(self, i: int, stream=None):
+        """After the producer of ``local_rows(i)`` on ``stream`` (default: current): push to all peers, barrier.
+        Returns the event that marks ``gathered(i)`` complete on this rank."""
+        torch = self._torch
+        k = i % len(self.bufs)
+        hdl = self.hdls[k]
+        ready = torch.cuda.Event()
+        ready.record(stream if stream is not None else torch.cuda.current_stream())
+        self.side.wait_event(ready)
+        # Before this rank joins barrier i, its reader of the OTHER buffer (push i - 1) must be done: peers overwrite that
+        # buffer in push i + 1, which they start only after barrier i.
+        prev = self._consumed[(i - 1) % len(self.bufs)] if len(self.bufs) > 1 else self._consumed[k]
+        if prev is not None:
+            self.side.wait_event(prev)
+        src = self.bufs[k].data_ptr() + self.rank * self._slice_bytes
+        with torch.cuda.stream(self.side):
+            for d in range(1, self.world):
+                peer = (self.rank + d) % self.world  # staggered: every link carries one transfer at a time
+                dst = int(hdl.buffer_ptrs[peer]) + self.rank * self._slice_bytes
+                self._check(self._lib.tsb_memcpy_peer_async(dst, src, self._slice_bytes, self.side.cuda_stream))
+            hdl.barrier(channel=0)
+            done = torch.cuda.Event()
+            done.record(self.side)
+        return done
+
+
 class ShardedDetectorSampler:
     """Packed detector/observable samples from all ranks of the default process group."""
 

@@ -125,6 +125,16 @@ class ChannelSampler:
     def words_per_row(self) -> int:
         return self._words
 
+    def clone_to(self, device: int) -> "DeviceChannelSampler":
+        """The same tables, seed and call counter on another GPU."""
+        if int(device) == self.device:
+            return self
+        c = DeviceChannelSampler.__new__(DeviceChannelSampler)
+        c.__dict__.update({k: v for k, v in self.__dict__.items() if k not in ("_h", "_fin")})
+        c.device = int(device)
+        c._create()
+        return c
+
 
 def pack_f_rows(f_params: np.ndarray) -> np.ndarray:
     """``uint8/bool[B, num_f]`` -> ``uint64[B, ceil(num_f/64)]`` (bit i of the row = f_i)."""
@@ -171,11 +181,18 @@ class DeviceChannelSampler:
         self._n_out = np.asarray(n_out, dtype=np.int32)
         self._thr = np.asarray(thr, dtype=np.uint64)
         self._pat = np.concatenate(pats, axis=0) if pats else np.zeros((0, self._words), np.uint64)
-        lib = _lib.load()
-        self._lib = lib
+        self._lib = _lib.load()
+        self._create()
+
+    def _create(self) -> None:
+        import ctypes as C
+        import weakref
+
+        from . import _lib
+
         h = C.c_void_p()
         _lib.check(
-            lib.tsb_noise_create(
+            self._lib.tsb_noise_create(
                 self.n_channels,
                 self._n_out.ctypes.data_as(C.c_void_p),
                 self._thr.ctypes.data_as(C.c_void_p),
@@ -186,9 +203,7 @@ class DeviceChannelSampler:
             )
         )
         self._h = h
-        import weakref
-
-        self._fin = weakref.finalize(self, lib.tsb_noise_destroy, h)
+        self._fin = weakref.finalize(self, self._lib.tsb_noise_destroy, h)
 
     @classmethod
     def from_bit_probs(cls, probs, seed: int | None = None, *, device: int = 0) -> "DeviceChannelSampler":
@@ -204,6 +219,16 @@ class DeviceChannelSampler:
     @property
     def words_per_row(self) -> int:
         return self._words
+
+    def clone_to(self, device: int) -> "DeviceChannelSampler":
+        """The same tables, seed and call counter on another GPU."""
+        if int(device) == self.device:
+            return self
+        c = DeviceChannelSampler.__new__(DeviceChannelSampler)
+        c.__dict__.update({k: v for k, v in self.__dict__.items() if k not in ("_h", "_fin")})
+        c.device = int(device)
+        c._create()
+        return c
 
     def next_call(self) -> int:
         c = self.calls
@@ -247,3 +272,44 @@ class DeviceChannelSampler:
         """Dense ``uint8[num_samples, num_f]`` (the reference's format)."""
         packed = self.sample_packed(num_samples, **kw)
         return np.unpackbits(packed.view(np.uint8), axis=1, bitorder="little", count=self.num_f) if self.num_f else np.zeros((num_samples, 0), np.uint8)
+
+
+class MultiDeviceChannelSampler:
+    """One :class:`DeviceChannelSampler` per GPU with a common seed and call counter.  K5's rows are a pure function of
+    (seed, call, in-batch shot index, channel), so the shards of a batch drawn on different devices are the rows a
+    single device would have drawn."""
+
+    def __init__(self, sparse_data, num_f: int, seed: int | None = None, *, devices):
+        self.seed = int(seed if seed is not None else np.random.default_rng().integers(0, 2**30))
+        self.devices = [int(d) for d in devices]
+        self.parts = [DeviceChannelSampler(sparse_data, num_f, self.seed, device=d) for d in self.devices]
+        self.num_f = int(num_f)
+        self.calls = 0
+
+    @classmethod
+    def from_bit_probs(cls, probs, seed: int | None = None, *, devices) -> "MultiDeviceChannelSampler":
+        host = ChannelSampler.from_bit_probs(probs, seed=0)
+        return cls(host._sparse_data, host.num_f, seed, devices=devices)
+
+    @classmethod
+    def from_host(cls, sampler, seed: int | None = None, *, devices) -> "MultiDeviceChannelSampler":
+        num_f = int(getattr(sampler, "num_f", None) or sampler.signature_matrix.shape[1])
+        return cls(sampler._sparse_data, num_f, seed, devices=devices)
+
+    def next_call(self) -> int:
+        c = self.calls
+        self.calls += 1
+        return c
+
+    def parts_for(self, devices):
+        if [int(d) for d in devices] != self.devices:
+            raise ValueError(f"noise sampler lives on devices {self.devices}, the program on {list(devices)}")
+        return self.parts
+
+    def sample_packed(self, num_samples: int = 1, **kw) -> np.ndarray:
+        kw.setdefault("call", self.next_call())
+        return self.parts[0].sample_packed(num_samples, **kw)
+
+    def sample(self, num_samples: int = 1, **kw) -> np.ndarray:
+        kw.setdefault("call", self.next_call())
+        return self.parts[0].sample(num_samples, **kw)

@@ -23,8 +23,8 @@ from typing import Any
 
 import numpy as np
 
-from .backend import DeviceProgram, key_words, split_key
-from .noise import ChannelSampler, DeviceChannelSampler
+from .backend import DeviceProgram, MultiDeviceProgram, key_words, split_key
+from .noise import ChannelSampler, DeviceChannelSampler, MultiDeviceChannelSampler
 from .program import CompiledProgram, from_tsim, program_stats
 from .shard import pack_bool_rows
 
@@ -34,7 +34,7 @@ _VANISHING = (
     "as a bug at https://github.com/QuEraComputing/tsim/issues/new."
 )
 
-_device_cache: dict[tuple[int, int, str], tuple[Any, DeviceProgram]] = {}
+_device_cache: dict[tuple, tuple[Any, Any]] = {}
 _DEVICE_CACHE_MAX = 16
 
 
@@ -42,19 +42,40 @@ def _cache_evict(key) -> None:
     _device_cache.pop(key, None)
 
 
-def device_program_for(program: Any, *, device: int = 0, mode: str = "auto", num_f: int | None = None) -> DeviceProgram:
-    """Upload ``program`` once per (object, device, mode) and reuse the handle on later calls.
+def default_devices() -> list[int] | None:
+    """``TSIM_B200_DEVICES``: ``"all"`` or a comma-separated list of GPU indices for every handle this module creates
+    (``sample_program`` / ``install()`` included), so that a tsim user reaches all GPUs of the box without code changes."""
+    import os
+
+    env = os.environ.get("TSIM_B200_DEVICES", "").strip().lower()
+    if not env:
+        return None
+    if env == "all":
+        from . import _lib
+
+        return list(range(_lib.load().tsb_device_count()))
+    return [int(v) for v in env.split(",") if v.strip()]
+
+
+def device_program_for(program: Any, *, device: int = 0, devices: Any = None, mode: str = "auto", num_f: int | None = None):
+    """Upload ``program`` once per (object, device(s), mode) and reuse the handle on later calls.
 
     tsim's programs are equinox modules (unhashable), so the cache is keyed on ``id`` and an entry dies with its
     program (``weakref.finalize``) or, for objects that cannot be weakly referenced, when the cache exceeds
     ``_DEVICE_CACHE_MAX`` entries (oldest first)."""
-    if isinstance(program, DeviceProgram):
+    if isinstance(program, (DeviceProgram, MultiDeviceProgram)):
         return program
-    key = (id(program), int(device), str(mode))
+    if devices is None:
+        devices = default_devices()
+    devs = tuple(int(d) for d in devices) if devices is not None else (int(device),)
+    key = (id(program), devs, str(mode))
     hit = _device_cache.get(key)
     if hit is not None and (hit[0] is None or hit[0]() is program):
         return hit[1]
-    dp = DeviceProgram(from_tsim(program, num_f=num_f), device=device, mode=mode)
+    if len(devs) > 1:
+        dp = MultiDeviceProgram(from_tsim(program, num_f=num_f), devices=devs, mode=mode)
+    else:
+        dp = DeviceProgram(from_tsim(program, num_f=num_f), device=devs[0], mode=mode)
     try:
         ref = weakref.ref(program)
         weakref.finalize(program, _cache_evict, key)
@@ -189,15 +210,30 @@ class _CompiledSamplerBase:
         seed: int | None = None,
         key: tuple[int, int] | None = None,
         device: int = 0,
+        devices: Any = None,
         mode: str = "auto",
         joint: bool = False,
     ):
+        """``devices``: GPUs of this box to shard every batch over, from this one process (default: ``device`` alone).  The
+        sampled bits do not depend on it (RNG counters are in-batch shot indices)."""
         if seed is None and key is None:
             seed = int(np.random.default_rng().integers(0, 2**30))
         # jax.random.key(seed) (sampler.py:198)
         self._key = key_words(key) if key is not None else ((int(seed) >> 32) & 0xFFFFFFFF, int(seed) & 0xFFFFFFFF)
         self._program: CompiledProgram = from_tsim(program, num_f=getattr(channel_sampler, "num_f", None))
-        self._device_program = DeviceProgram(self._program, device=device, mode=mode, joint=joint)
+        if devices is None:
+            devices = default_devices()
+        if devices is not None and len(list(devices)) > 1:
+            self._device_program = MultiDeviceProgram(self._program, devices=list(devices), mode=mode, joint=joint)
+            if isinstance(channel_sampler, DeviceChannelSampler):  # the same tables and seed on every device
+                ds = channel_sampler
+                channel_sampler = MultiDeviceChannelSampler.__new__(MultiDeviceChannelSampler)
+                channel_sampler.seed, channel_sampler.devices, channel_sampler.num_f, channel_sampler.calls = ds.seed, [int(d) for d in devices], ds.num_f, ds.calls
+                channel_sampler.parts = [ds.clone_to(d) for d in channel_sampler.devices]
+        else:
+            if devices is not None and len(list(devices)) == 1:
+                device = int(list(devices)[0])
+            self._device_program = DeviceProgram(self._program, device=device, mode=mode, joint=joint)
         self._channel_sampler = channel_sampler
         self._num_detectors = int(self._program.num_detectors if num_detectors is None else num_detectors)
 
@@ -288,7 +324,7 @@ class _CompiledSamplerBase:
         result as the device's ``uint64[shots, ceil(n_out/64)]`` rows; the reference row is still ``bool[n_out]``."""
         # direct-only programs follow the reference's host shortcut (sampler.py:365-370) unless the noise itself lives on
         # the device: then K5 -> direct gather -> packed rows never materialise the f matrix on the host
-        on_device = isinstance(self._channel_sampler, DeviceChannelSampler)
+        on_device = isinstance(self._channel_sampler, (DeviceChannelSampler, MultiDeviceChannelSampler))
         host_direct = not self._program.components and not on_device
         if packed and (shots == 0 or host_direct):
             res = self._sample_batches(shots, batch_size, compute_reference=compute_reference)
@@ -382,7 +418,7 @@ class _CompiledSamplerBase:
         session = self._device_program.postselect_session(
             shots, batch_size, postselect_direct, reference[:nd] if use_ref else None, nd
         )
-        on_device = isinstance(self._channel_sampler, DeviceChannelSampler)
+        on_device = isinstance(self._channel_sampler, DeviceChannelSampler)  # multi-device noise: rows come back through the host
         packed_host = hasattr(self._channel_sampler, "sample_packed")
         shot_idx = 0
         pending = 0
@@ -615,7 +651,7 @@ class CompiledDetectorSampler(_CompiledSamplerBase):
                     samples[~direct_discarded, nd:] ^= reference[nd:]
             else:
                 samples, _, _ = self._sample_batches_with_postselection(shots, batch_size, postselection_mask=postselection_mask)
-        elif bit_packed and shots > 0 and (self._program.components or isinstance(self._channel_sampler, DeviceChannelSampler)):
+        elif bit_packed and shots > 0 and (self._program.components or isinstance(self._channel_sampler, (DeviceChannelSampler, MultiDeviceChannelSampler))):
             # packed end to end: the device's uint64 rows are sliced with word shifts, never expanded to bools
             n_out = self._program.num_outputs
             if compute_reference:

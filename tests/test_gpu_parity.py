@@ -396,3 +396,21 @@ def test_reordered_modes_agree_with_faithful_near_the_bound(mode):
     want, want_dev = _oracle(prog, f, (2, 9))
     got, dev = _device_program(prog, mode).sample(f, (2, 9))
     assert np.array_equal(got, want) and _dev_equal(dev, want_dev)
+
+
+@pytest.mark.parametrize("host_pack", ["0", "1"])
+@pytest.mark.parametrize("name,B", [("cfg2_distill35", 600_001), ("cfg5_distill85", 70_000), ("cfg3_surface_d5", 300_000)])
+def test_byte_rows_host_packed_or_dma(name, B, host_pack, monkeypatch):
+    """The reference's uint8[B, num_f] rows reach the device either packed by host threads (1/8 of the PCIe bytes) or
+    as bytes packed by K0; same bits either way (several pipeline slices, ragged tail, 1..3 words per row)."""
+    monkeypatch.setenv("TSIM_B200_HOST_PACK", host_pack)
+    prog = synthetic_program(name)
+    nf = prog.infer_num_f()
+    f = ChannelSampler.from_bit_probs(noise_probs(nf, 5e-3), seed=9).sample(B)
+    f[-1, :] = 1
+    dp = _device_program(prog, "auto")
+    got, dev = dp.sample(f, (2, 3))
+    packed, dev2 = dp.sample(pack_f_rows(f), (2, 3), packed_out=True)
+    assert np.array_equal(np.packbits(got, axis=1, bitorder="little"), packed.view(np.uint8)[:, : (prog.num_outputs + 7) // 8])
+    want = oracle.sample_program(prog, f[-1024:], (2, 3), shot_offset=B - 1024, check_norm=False)
+    assert np.array_equal(got[-1024:], want)

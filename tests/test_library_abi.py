@@ -50,3 +50,29 @@ def test_no_device_fails_loudly(lib):
     with pytest.raises(RuntimeError):
         DeviceProgram(K.hm_program())
     assert lib.tsb_host_alloc(16) is None
+
+
+def test_host_side_bit_packers_agree_with_numpy():
+    """The SIMD row packers of the end-to-end input path (csrc/host_pack.cpp; CPU code, no device needed): every ISA
+    variant this host supports against np.packbits, ragged row widths and the over-read guard at the end of the array."""
+    import ctypes as C
+
+    import numpy as np
+
+    from tsim_b200 import _lib
+    from tsim_b200.noise import pack_f_rows
+
+    lib = C.CDLL(_lib.LIB_PATH)
+    lib.tsb_host_pack_rows.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_int]
+    best = lib.tsb_host_pack_isa()
+    rng = np.random.default_rng(0)
+    for nf in (1, 7, 63, 64, 65, 121, 128, 160, 200):
+        n = 777
+        f = (rng.random((n, nf)) < 0.3).astype(np.uint8)
+        f[rng.integers(0, n, 50), rng.integers(0, nf, 50)] = 255  # only the low bit counts, like the device's K0
+        wf = max(1, (nf + 63) // 64)
+        want = pack_f_rows(f & 1)
+        for isa in range(best + 1):
+            out = np.zeros((n, wf), np.uint64)
+            lib.tsb_host_pack_rows(f.ctypes.data, n, nf, wf, out.ctypes.data, f.size, isa)
+            assert np.array_equal(out, want), (nf, isa)

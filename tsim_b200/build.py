@@ -8,9 +8,11 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "tsim_b200.cu")
+HOST_SRC = os.path.join(HERE, "csrc", "host_pack.cpp")  # plain C++ (SIMD bit packing with run-time dispatch), g++
 LIB = os.path.join(HERE, "libtsim_b200.so")
 DEPS = [
     SRC,
+    HOST_SRC,
     os.path.join(HERE, "csrc", "sampler_kernels.cuh"),
     os.path.join(HERE, "csrc", "zomega.cuh"),
     os.path.join(HERE, "csrc", "blob.h"),
@@ -44,7 +46,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libtsim_b200.so")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, SRC]
+    gxx = shutil.which("g++") or "g++"
+    host_obj = os.path.join(HERE, "csrc", "host_pack.o")
+    res = subprocess.run([gxx, "-O3", "-fPIC", "-std=c++17", "-c", HOST_SRC, "-o", host_obj], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, SRC, host_obj]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

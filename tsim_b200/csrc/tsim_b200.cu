@@ -6,7 +6,13 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/tsim_b200.h"
@@ -486,6 +492,127 @@ static int fail(int code, const std::string& msg) {
       return fail(TSB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
   } while (0)
 
+// ---------------------------------------------------------------------------------------------
+// Host-side bit packing of the reference's f matrix (uint8[B, num_f], 0/1) into the device's row words.
+// The byte matrix is 8x the packed rows: on the 63-byte rows of cfg2 the PCIe copy of the bytes (63 MB per 10^6 shots,
+// 1.3 ms at 49 GB/s; 6 ms from pageable memory) is the critical path of the end-to-end call, while a handful of host
+// threads pack them at memory speed; only the packed rows then cross the bus.
+// ---------------------------------------------------------------------------------------------
+class HostPool {
+ public:
+  explicit HostPool(int n) {
+    for (int i = 0; i < n; ++i) workers_.emplace_back([this] { loop(); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  int size() const { return (int)workers_.size(); }
+  // try_begin: the workers start on fn(i), i in [0, n), and the caller carries on; finish: the caller joins in and
+  // returns when all are done.  The pool runs one task at a time: try_begin returns false while another thread's task
+  // is in flight (several handles driven from several threads, e.g. MultiDeviceProgram) and the caller does its work itself.
+  bool try_begin(int n, std::function<void(int)> fn) {
+    if (n <= 0 || !busy_.try_lock()) return false;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      task_ = std::move(fn);
+      fn_ = &task_; next_ = 0; total_ = n; done_ = 0; ++epoch_;
+    }
+    cv_.notify_all();
+    return true;
+  }
+  void finish() {  // only after a successful try_begin, from the same thread
+    work();
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      done_cv_.wait(lk, [this] { return done_ == total_; });
+      fn_ = nullptr;
+    }
+    busy_.unlock();
+  }
+
+ private:
+  void work() {
+    for (;;) {
+      int i;
+      const std::function<void(int)>* fn;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!fn_ || next_ >= total_) return;
+        i = next_++;
+        fn = fn_;
+      }
+      (*fn)(i);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (++done_ == total_) done_cv_.notify_all();
+      }
+    }
+  }
+  void loop() {
+    unsigned long long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || epoch_ != seen; });
+        if (stop_) return;
+        seen = epoch_;
+      }
+      work();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_, busy_;
+  std::condition_variable cv_, done_cv_;
+  std::function<void(int)> task_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int next_ = 0, total_ = 0, done_ = 0;
+  unsigned long long epoch_ = 0;
+  bool stop_ = false;
+};
+
+// threads for host-side packing: TSIM_B200_HOST_THREADS, else the host's cores divided by the ranks sharing them
+// (LOCAL_WORLD_SIZE under torchrun), at most 16.  0 or 1 disables the host path.
+static int host_threads() {
+  static int v = [] {
+    if (const char* e = getenv("TSIM_B200_HOST_THREADS")) return std::max(0, atoi(e));
+    int hw = (int)std::thread::hardware_concurrency();
+    int ranks = 1;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+    return std::max(1, std::min(16, hw / ranks));
+  }();
+  return v;
+}
+static HostPool* host_pool() {
+  static HostPool* pool = new HostPool(std::max(0, host_threads() - 1));  // the caller works too; leaked on purpose (process lifetime)
+  return pool;
+}
+
+// SIMD packers with run-time dispatch (host_pack.cpp, plain C++)
+extern "C" void tsb_host_pack_rows(const uint8_t* src, long long n, int num_f, int wf, uint64_t* dst, long long avail, int isa);
+extern "C" int tsb_host_pack_isa(void);
+
+// rows [0, n) of a uint8[., num_f] matrix -> uint64[., wf] (bit i of a row = f_i & 1), on the pool
+// Asynchronous on the pool's workers when the pool is free (returns true: the caller joins with host_pool()->finish());
+// otherwise packed right here by the calling thread (returns false).
+static bool pack_rows_host_begin(const uint8_t* src, long long n, int num_f, int wf, uint64_t* dst) {
+  HostPool* pool = host_pool();
+  static const int isa = [] { const char* e = getenv("TSIM_B200_HOST_PACK_ISA"); return e ? atoi(e) : -1; }();
+  const int parts = (int)std::min<long long>((pool->size() + 1) * 4, std::max<long long>(1, n / 4096));
+  const long long per = (n + parts - 1) / parts;
+  if (pool->try_begin(parts, [=](int i) {
+        const long long lo = i * per, hi = std::min(n, lo + per);
+        if (hi > lo) tsb_host_pack_rows(src + lo * num_f, hi - lo, num_f, wf, dst + lo * wf, (n - lo) * num_f, isa);
+      }))
+    return true;
+  tsb_host_pack_rows(src, n, num_f, wf, dst, n * num_f, isa);
+  return false;
+}
+
 constexpr int kSlots = 3;            // pipeline depth of tsb_sample_host
 constexpr int kHeavyRows = 4;        // word offset of the row list inside a heavy buffer (the count sits at word 0)
 static size_t heavy_bytes(long long cap) { return 4 * ((size_t)cap + kHeavyRows + 64); }
@@ -505,6 +632,8 @@ struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t k_start = nullptr, k_stop = nullptr;
   cudaEvent_t t_h0 = nullptr, t_h1 = nullptr, t_d1 = nullptr;  // TSIM_B200_TRACE: copy-in start / end, copy-out end
+  cudaEvent_t e_h2d = nullptr;  // the staging buffer has been copied to the device
+  uint64_t* h_stage = nullptr;     // pinned: f rows of the slice packed on the host (host-pack path)
   uint8_t* d_in_bytes = nullptr;   // raw host rows (bytes format) or packed rows
   uint64_t* d_f = nullptr;
   uint64_t* d_out = nullptr;
@@ -790,6 +919,7 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
 }
 
 static void free_slot(Slot& s) {
+  if (s.h_stage) cudaFreeHost(s.h_stage);
   if (s.d_in_bytes) cudaFree(s.d_in_bytes);
   if (s.d_f) cudaFree(s.d_f);
   if (s.d_out) cudaFree(s.d_out);
@@ -802,6 +932,7 @@ static void free_slot(Slot& s) {
   if (s.t_h0) cudaEventDestroy(s.t_h0);
   if (s.t_h1) cudaEventDestroy(s.t_h1);
   if (s.t_d1) cudaEventDestroy(s.t_d1);
+  if (s.e_h2d) cudaEventDestroy(s.e_h2d);
   if (s.k_stop) cudaEventDestroy(s.k_stop);
   if (s.stream) cudaStreamDestroy(s.stream);
   s = Slot();
@@ -1225,9 +1356,12 @@ static int ensure_slot(tsb_program* p, Slot& s, long long cap) {
     CU(cudaEventCreate(&s.t_h0));
     CU(cudaEventCreate(&s.t_h1));
     CU(cudaEventCreate(&s.t_d1));
+    CU(cudaEventCreateWithFlags(&s.e_h2d, cudaEventDisableTiming));
     CU(cudaMalloc(&s.d_subkeys, 8 * (size_t)std::max(1, in.n_draws)));
   }
   if (s.cap >= cap) return TSB_OK;
+  if (s.h_stage) cudaFreeHost(s.h_stage);
+  s.h_stage = nullptr;
   if (s.d_in_bytes) cudaFree(s.d_in_bytes);
   if (s.d_f) cudaFree(s.d_f);
   if (s.d_out) cudaFree(s.d_out);
@@ -1237,6 +1371,7 @@ static int ensure_slot(tsb_program* p, Slot& s, long long cap) {
   if (s.d_ot) cudaFree(s.d_ot);
   s.d_in_bytes = nullptr; s.d_f = nullptr; s.d_out = nullptr; s.d_out_bytes = nullptr; s.d_heavy = nullptr;
   s.d_xt = nullptr; s.d_ot = nullptr; s.cap = 0;
+  CU(cudaHostAlloc(&s.h_stage, (size_t)cap * in.words_f64 * 8, cudaHostAllocDefault));
   CU(cudaMalloc(&s.d_in_bytes, (size_t)cap * std::max(1, in.num_f)));
   CU(cudaMalloc(&s.d_f, (size_t)cap * in.words_f64 * 8));
   CU(cudaMalloc(&s.d_out, (size_t)cap * in.words_out64 * 8));
@@ -1293,6 +1428,7 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
   if (B == 0) return TSB_OK;
   CU(cudaMemsetAsync(p->d_norm_dev, 0, sizeof(float) * std::max(1, in.n_components), p->stream));
   static const bool trace = getenv("TSIM_B200_TRACE") != nullptr;  // per-slice timeline on stderr
+  const auto t_call = std::chrono::steady_clock::now();
   if (trace) CU(cudaEventRecord(p->ev_a, p->stream));
   CU(cudaStreamSynchronize(p->stream));
   auto dump = [&](const Slot& s, int idx) {
@@ -1306,14 +1442,23 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
   const long long slice = std::min<long long>(pipeline_slice(p), B);
   const size_t in_row = f_format == TSB_F_BYTES ? (size_t)in.num_f : (size_t)in.words_f64 * 8;
   const size_t out_row = out_format == TSB_OUT_BYTES ? (size_t)in.num_outputs : (size_t)in.words_out64 * 8;
+  // byte rows: pack on the host when enough threads are free for this rank (TSIM_B200_HOST_PACK=0/1 overrides)
+  const char* host_pack_env = getenv("TSIM_B200_HOST_PACK");
+  const bool host_pack = host_pack_env ? atoi(host_pack_env) != 0 : host_threads() >= 6;
   int n_slices = (int)((B + slice - 1) / slice);
-  for (int i = 0; i < n_slices; ++i) {
-    Slot& s = p->slots[i % kSlots];
-    int rc = ensure_slot(p, s, slice);
-    if (rc) return rc;
-    if (i >= kSlots) {
-      CU(cudaStreamSynchronize(s.stream));  // slot reuse: previous slice in this slot has fully drained
-      if (trace) dump(s, i - kSlots);
+  const bool pack_here = f_format == TSB_F_BYTES && host_pack && in.num_f > 0;
+  std::chrono::steady_clock::time_point tp0;
+  bool pack_async = false;  // the pool's workers are on the current slice (else the calling thread packed it itself)
+  struct PoolGuard {  // an error return between begin and join must not leave the pool locked
+    bool& on;
+    ~PoolGuard() { if (on) host_pool()->finish(); }
+  } pool_guard{pack_async};
+  // drain(j): the slot of slice j is free again (its previous slice has left the device, results copied out).
+  auto drain = [&](int j) -> int {
+    Slot& s = p->slots[j % kSlots];
+    if (j >= kSlots) {
+      CU(cudaStreamSynchronize(s.stream));
+      if (trace) dump(s, j - kSlots);
       if (s.timed) {
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, s.k_start, s.k_stop));
@@ -1321,12 +1466,53 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
         s.timed = false;
       }
     }
+    return TSB_OK;
+  };
+  // stage(j), host packing: as soon as the slot's staging buffer has been copied out, the pool's workers pack slice j
+  // into it -- while this thread enqueues the GPU work of slice j - 1
+  auto stage = [&](int j) -> int {
+    Slot& s = p->slots[j % kSlots];
+    int rc = ensure_slot(p, s, slice);
+    if (rc) return rc;
+    if (!pack_here) return TSB_OK;
+    if (j >= kSlots) CU(cudaEventSynchronize(s.e_h2d));
+    const long long lo = (long long)j * slice, n = std::min<long long>(slice, B - lo);
+    tp0 = std::chrono::steady_clock::now();
+    pack_async = pack_rows_host_begin((const uint8_t*)f + (size_t)lo * in_row, n, in.num_f, in.words_f64, s.h_stage);
+    return TSB_OK;
+  };
+  auto pack_join = [&](int j) {
+    if (!pack_here) return;
+    if (pack_async) host_pool()->finish();
+    pack_async = false;
+    if (trace)
+      fprintf(stderr, "[tsb trace] slice %d: host pack %.3f-%.3f ms (host clock since call start)\n", j,
+              std::chrono::duration<double, std::milli>(tp0 - t_call).count(),
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count());
+  };
+  {
+    int rc = stage(0);
+    if (rc) return rc;
+    pack_join(0);
+  }
+  for (int i = 0; i < n_slices; ++i) {
+    Slot& s = p->slots[i % kSlots];
+    int rc = drain(i);
+    if (rc) return rc;
     const long long lo = (long long)i * slice, n = std::min<long long>(slice, B - lo);
     derive_subkeys_kernel<<<1, 32, 0, s.stream>>>(k0, k1, in.n_draws, s.d_subkeys);
     CU(cudaGetLastError());
     const uint8_t* src = (const uint8_t*)f + (size_t)lo * in_row;
     if (trace) CU(cudaEventRecord(s.t_h0, s.stream));
-    if (f_format == TSB_F_BYTES) {
+    if (pack_here) {
+      // packed on the host (pool threads), 1/8 of the bytes cross the bus
+      CU(cudaMemcpyAsync(s.d_f, s.h_stage, (size_t)n * in.words_f64 * 8, cudaMemcpyHostToDevice, s.stream));
+      CU(cudaEventRecord(s.e_h2d, s.stream));
+      if (i + 1 < n_slices) {
+        rc = stage(i + 1);
+        if (rc) return rc;
+      }
+    } else if (f_format == TSB_F_BYTES) {
       if (in.num_f > 0) CU(cudaMemcpyAsync(s.d_in_bytes, src, (size_t)n * in_row, cudaMemcpyHostToDevice, s.stream));
       rc = tsb_pack_f_device(p, s.d_in_bytes, n, s.d_f, s.stream);
       if (rc) return rc;
@@ -1352,6 +1538,14 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
       }
     }
     if (trace) CU(cudaEventRecord(s.t_d1, s.stream));
+    if (i + 1 < n_slices) {
+      if (pack_here) {
+        pack_join(i + 1);
+      } else {
+        rc = stage(i + 1);
+        if (rc) return rc;
+      }
+    }
   }
   for (int i = 0; i < kSlots; ++i) {
     Slot& s = p->slots[i];
@@ -1368,6 +1562,8 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
   if (p->side) CU(cudaStreamSynchronize(p->side));
   if (norm_dev && in.n_components > 0)
     CU(cudaMemcpy(norm_dev, p->d_norm_dev, sizeof(float) * in.n_components, cudaMemcpyDeviceToHost));
+  if (trace)
+    fprintf(stderr, "[tsb trace] call returns at %.3f ms (host clock)\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count());
   return TSB_OK;
 }
 

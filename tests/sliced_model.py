@@ -36,8 +36,15 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
     if int(lvl[0]) == 0:
         return [("approx", np.float32(0), np.float32(0))] * N
 
+    scale = int(blob[PK.H_INDEX_SCALE])  # index bytes hold row * scale
+    assert scale in (1, 2)
+
+    def row(byte):
+        assert byte % scale == 0
+        return rows.get(byte // scale, 0)
+
     def par4(w):
-        return rows.get(w & 255, 0) ^ rows.get((w >> 8) & 255, 0) ^ rows.get((w >> 16) & 255, 0) ^ rows.get(w >> 24, 0)
+        return row(w & 255) ^ row((w >> 8) & 255) ^ row((w >> 16) & 255) ^ row(w >> 24)
 
     for c in range(int(lvl[7]), int(lvl[7]) + int(lvl[8])):
         coff, _, ng, _ = (int(v) for v in chunks[c])

@@ -116,7 +116,7 @@ def test_sliced_chunk_layout_invariants():
             off, words, ng = int(off), int(words), int(ng)
             assert off % 4 == 0 and words % 4 == 0 and words <= MAX_CHUNK_WORDS
             if ci + 1 < n:
-                assert ng % 8 == 0  # only the last chunk of a level may end with a partial wave
+                assert ng % 4 == 0  # only the last chunk of a level may end with a partial wave (waves of 4; of 8 on thin slices)
             chunk = data[off : off + words]
             end_of_records = None
             for g in range(ng):

@@ -10,7 +10,7 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(root, "tsim_b200", "libtsim_b200.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
-cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+cubin = max((os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")), key=os.path.getsize)  # the host-only object has an (empty) cubin too
 dis = subprocess.run(["nvdisasm", "-g", cubin], capture_output=True, text=True).stdout
 # find the text section of the kernel
 sec = None

@@ -5,7 +5,7 @@
 namespace tsb {
 
 constexpr uint32_t kMagic = 0x32425354u;  // "TSB2"
-constexpr uint32_t kVersion = 6;
+constexpr uint32_t kVersion = 7;
 constexpr int kModeFaithful = 0;
 constexpr int kModeFast = 1;
 constexpr int kModeSliced = 2;
@@ -23,7 +23,8 @@ enum HeaderSlot {
   H_OFF_DIRECT, H_OFF_COMP, H_OFF_LEVEL, H_OFF_CHUNK,
   H_OFF_FSEL, H_OFF_DEST, H_OFF_DATA, H_DATA_WORDS,
   H_TOTAL_WORDS, H_WF64, H_WOUT64, H_OFF_TABLES,
-  H_TABLE_WORDS, H_ONE_ROW, H_ZERO_ROW, H_PLANE_ROWS
+  H_TABLE_WORDS, H_ONE_ROW, H_ZERO_ROW, H_PLANE_ROWS,
+  H_INDEX_SCALE  // sliced records: row index bytes are stored times this (2 when rows <= 127, so that 64-bit lanes can address them)
 };
 
 // component table row

@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "blob.h"
 #include "sampler_kernels.cuh"
 #include "zomega.cuh"
@@ -41,8 +43,8 @@ struct SParams {
   long long shot_offset;
   int n_slabs;
   int slab_cap;
-  int n_groups;  // groups of 32 slabs
-  int ng;        // groups per CTA per round
+  int n_groups;  // units of 32 slabs (1024 shots): narrow groups, or half the lanes of a wide group
+  int ng;        // units per CTA per round
   int rounds;
   int n_stages;
   int stage_words;
@@ -51,7 +53,7 @@ struct SParams {
   int smem_data_off;
   int rows;  // zero_row + 1
   int plane_rows;  // plane rows per graph slot (blob header H_PLANE_ROWS)
-  uint4 sel;    // dp4a byte selectors {128 << 0, 128 << 8, 128 << 16, 128 << 24} (see par4)
+  uint4 sel;    // dp4a byte selectors {s << 0, s << 8, s << 16, s << 24}, s = row stride in bytes / H_INDEX_SCALE (see par4)
   uint4 sel_e;  // the same with 8, the byte size of a float2 decode-table entry, instead of 128 (see sliced_phase2)
   // optional indirection (HAS_ROWS kernels; memoised path pass 2, post-selection survivors): slot i of the launch is
   // batch row rows[i], i < *n_rows -- the count is only known on the device, so the kernel derives n_slabs, n_groups and
@@ -146,52 +148,95 @@ __global__ void __launch_bounds__(256) assemble_out_kernel(const uint32_t* __res
 // ---------------------------------------------------------------------------------------------
 // K1s
 // ---------------------------------------------------------------------------------------------
-// A *group* of SPLIT warps owns 32 slabs (lane = slab, 1024 shots).  The group's transposed parameter matrix sits in
-// shared memory ([row][lane], one conflict-free wavefront per access).  The graphs of a chunk are handed out in waves
+// A *group* of SPLIT warps owns 32 lanes of slabs.  In the narrow layout a lane is one slab (32 shots, one 32-bit word
+// per parameter row; the group holds 1024 shots); in the wide layout a lane is two consecutive slabs (64 shots, one
+// 64-bit word per row, LDS.64; 2048 shots per group), which halves the instructions per shot of phase 1 -- the row
+// address, the record fetch and the loop control are shared by twice as many shots.  The group's transposed parameter
+// matrix sits in shared memory ([row][lane], conflict-free wavefronts).  The graphs of a chunk are handed out in waves
 // of SPLIT: warp w of the group runs phase 1 (bit-sliced term stream -> planes) for graph wave + w and parks the
 // planes in shared memory; after a group barrier every warp runs phase 2 for ITS 32 / SPLIT shots of each slab over
 // the wave's graphs in order (the approximate branch is a sequential float sum over graphs): gather the plane bits
 // into the index, add the decode-table entry.  Level accumulators stay in registers.
-__device__ __forceinline__ void add_a3(uint32_t& A0, uint32_t& A1, uint32_t& A2, uint32_t da, uint32_t p) {
+//
+// Wide groups are filled in *units* of 16 lanes (32 slabs = 1024 shots, the same granularity as a narrow group): when
+// a CTA holds an odd number of units, lanes 16..31 of its last group sit out: 64-bit shared-memory accesses are served
+// per half-warp, so an idle half costs no wavefront and shared-memory traffic stays proportional to the shots.
+struct U2 {
+  uint32_t x, y;
+};
+__device__ __forceinline__ U2 operator^(U2 a, U2 b) { return U2{a.x ^ b.x, a.y ^ b.y}; }
+__device__ __forceinline__ U2 operator&(U2 a, U2 b) { return U2{a.x & b.x, a.y & b.y}; }
+__device__ __forceinline__ U2 operator|(U2 a, U2 b) { return U2{a.x | b.x, a.y | b.y}; }
+__device__ __forceinline__ U2 operator~(U2 a) { return U2{~a.x, ~a.y}; }
+__device__ __forceinline__ U2& operator^=(U2& a, U2 b) { a.x ^= b.x; a.y ^= b.y; return a; }
+__device__ __forceinline__ U2& operator|=(U2& a, U2 b) { a.x |= b.x; a.y |= b.y; return a; }
+
+template <class LW>
+struct LaneWord;
+template <>
+struct LaneWord<uint32_t> {
+  static constexpr int kWords = 1;
+  static constexpr bool kPrefetch = false;  // item records of phase 1 (run_items)
+  static __device__ __forceinline__ uint32_t zero() { return 0u; }
+  static __device__ __forceinline__ uint32_t ones() { return 0xFFFFFFFFu; }
+  static __device__ __forceinline__ uint32_t ld(uint32_t saddr) {
+    return *reinterpret_cast<const uint32_t*>(__cvta_shared_to_generic(saddr));
+  }
+};
+template <>
+struct LaneWord<U2> {
+  static constexpr int kWords = 2;
+  static constexpr bool kPrefetch = false;  // measured: no gain at 16 warps of 128 registers (0.727 -> 0.738 ms)
+  static __device__ __forceinline__ U2 zero() { return U2{0u, 0u}; }
+  static __device__ __forceinline__ U2 ones() { return U2{0xFFFFFFFFu, 0xFFFFFFFFu}; }
+  static __device__ __forceinline__ U2 ld(uint32_t saddr) {
+    const uint2 v = *reinterpret_cast<const uint2*>(__cvta_shared_to_generic(saddr));
+    return U2{v.x, v.y};
+  }
+};
+
+template <class LW>
+__device__ __forceinline__ void add_a3(LW& A0, LW& A1, LW& A2, uint32_t da, LW p) {
   if (da & 1u) {
-    const uint32_t c0 = A0 & p;
+    const LW c0 = A0 & p;
     A0 ^= p;
-    const uint32_t c1 = A1 & c0;
+    const LW c1 = A1 & c0;
     A1 ^= c0;
     A2 ^= c1;
   }
   if (da & 2u) {
-    const uint32_t c1 = A1 & p;
+    const LW c1 = A1 & p;
     A1 ^= p;
     A2 ^= c1;
   }
   if (da & 4u) A2 ^= p;
 }
 
-__device__ __forceinline__ void add_cnt5(uint32_t (&Bp)[5], uint32_t w) {
+template <class LW>
+__device__ __forceinline__ void add_cnt5(LW (&Bp)[5], LW w) {
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
-    const uint32_t t = Bp[k] & w;
+    const LW t = Bp[k] & w;
     Bp[k] ^= w;
     w = t;
   }
 }
 
 // Row indices in the term stream are bytes, four per word.  xs = 32-bit shared-memory address of this lane's column of
-// the group's matrix (row r at xs + 128 r).  One dp4a with a selector word (128 in byte k, 0 elsewhere) turns byte k
-// into the row's address on the FMA pipe, which leaves the ALU pipe to the XORs.  The selectors arrive as kernel
-// parameters so that they stay constant-bank operands.
-__device__ __forceinline__ uint32_t ld_sh(uint32_t saddr) {
-  return *reinterpret_cast<const uint32_t*>(__cvta_shared_to_generic(saddr));
+// the group's matrix (row r at xs + stride r; stride = 128 bytes narrow, 256 wide).  One dp4a with a selector word
+// (s in byte k, 0 elsewhere) turns byte k into the row's address on the FMA pipe, which leaves the ALU pipe to the
+// XORs.  The selectors arrive as kernel parameters so that they stay constant-bank operands; index bytes are stored
+// times H_INDEX_SCALE (2 when the program has at most 127 rows: s = 64 narrow, 128 wide; else 1: s = 128, narrow only).
+template <class LW>
+__device__ __forceinline__ LW par4(uint32_t xs, uint32_t w, const uint4& sel) {
+  typedef LaneWord<LW> L;
+  return (L::ld(__dp4a(w, sel.x, xs)) ^ L::ld(__dp4a(w, sel.y, xs))) ^ (L::ld(__dp4a(w, sel.z, xs)) ^ L::ld(__dp4a(w, sel.w, xs)));
 }
-__device__ __forceinline__ uint32_t par4(uint32_t xs, uint32_t w, const uint4& sel) {
-  return (ld_sh(__dp4a(w, sel.x, xs)) ^ ld_sh(__dp4a(w, sel.y, xs))) ^ (ld_sh(__dp4a(w, sel.z, xs)) ^ ld_sh(__dp4a(w, sel.w, xs)));
-}
-template <int N>
-__device__ __forceinline__ uint32_t par_words(uint32_t xs, const uint32_t* w, const uint4& sel) {
-  uint32_t p = par4(xs, w[0], sel);
+template <class LW, int N>
+__device__ __forceinline__ LW par_words(uint32_t xs, const uint32_t* w, const uint4& sel) {
+  LW p = par4<LW>(xs, w[0], sel);
 #pragma unroll
-  for (int i = 1; i < N; ++i) p ^= par4(xs, w[i], sel);
+  for (int i = 1; i < N; ++i) p ^= par4<LW>(xs, w[i], sel);
   return p;
 }
 // N words (multiple of 4) from a 16-byte aligned, warp-uniform address
@@ -208,57 +253,81 @@ __device__ __forceinline__ void ld_words(const uint32_t* __restrict__ b, uint32_
 enum SlicedOp { OP_FIRST = 0, OP_LIN = 1, OP_PI = 2, OP_PAIRGEN = 3, OP_PAIRMON = 4 };
 enum SlicedRun { RUN_LIN = 0, RUN_PI = 3, RUN_LIN2 = 9, RUN_PAIR = 12, RUN_GENERIC = 15 };
 
+template <class LW>
 struct Planes {
-  uint32_t A0, A1, A2, Z;
-  uint32_t Bp[5];
+  LW A0, A1, A2, Z;
+  LW Bp[5];
 };
 
-__device__ __forceinline__ void lin_op(Planes& P, uint32_t prm, uint32_t p) {
+template <class LW>
+__device__ __forceinline__ void lin_op(Planes<LW>& P, uint32_t prm, LW p) {
   add_a3(P.A0, P.A1, P.A2, prm & 7u, p);
   const uint32_t bm = (prm >> 3) & 3u, zm = (prm >> 5) & 3u;
   if (bm) add_cnt5(P.Bp, bm == 1u ? p : ~p);
   if (zm) P.Z |= (zm == 1u ? p : ~p);
 }
 
-// LIN run: item = [params, index words]; NW = index words used, item = 4 words (NW <= 3) or 8 words
-template <int NW>
-__device__ __forceinline__ const uint32_t* lin_run(const uint32_t* __restrict__ b, uint32_t count, uint32_t xs, const uint4& sel, Planes& P) {
-  constexpr int IW = NW <= 3 ? 4 : 8;
+// The items of a run, IW words each, with the record words of the next item fetched while the current one waits for
+// its rows (PF: two item buffers in ping-pong; one shared-memory round trip per item instead of two).  The fetch past
+// the last item reads whatever follows the run inside the stage (the chunk ends with the decode tables) and is dropped.
+// The narrow layout runs at 72 registers per thread and keeps the plain loop.
+template <int IW, bool PF, class F>
+__device__ __forceinline__ const uint32_t* run_items(const uint32_t* __restrict__ b, uint32_t count, F&& body) {
+  if constexpr (PF) {
+    uint32_t wa[IW], wb[IW];
+    ld_words<IW>(b, wa);
+    uint32_t i = 0;
 #pragma unroll 1
-  for (uint32_t i = 0; i < count; ++i, b += IW) {
-    uint32_t w[IW];
-    ld_words<IW>(b, w);
-    lin_op(P, w[0], par_words<NW>(xs, w + 1, sel));
+    for (;;) {
+      ld_words<IW>(b + IW, wb);
+      body(wa);
+      b += IW;
+      if (++i == count) break;
+      ld_words<IW>(b + IW, wa);
+      body(wb);
+      b += IW;
+      if (++i == count) break;
+    }
+  } else {
+#pragma unroll 1
+    for (uint32_t i = 0; i < count; ++i, b += IW) {
+      uint32_t w[IW];
+      ld_words<IW>(b, w);
+      body(w);
+    }
   }
   return b;
+}
+
+// LIN run: item = [params, index words]; NW = index words used, item = 4 words (NW <= 3) or 8 words
+template <class LW, int NW>
+__device__ __forceinline__ const uint32_t* lin_run(const uint32_t* __restrict__ b, uint32_t count, uint32_t xs, const uint4& sel, Planes<LW>& P) {
+  constexpr int IW = NW <= 3 ? 4 : 8;
+  return run_items<IW, LaneWord<LW>::kPrefetch>(b, count, [&](const uint32_t(&w)[IW]) { lin_op(P, w[0], par_words<LW, NW>(xs, w + 1, sel)); });
 }
 
 // PI run: item = [4 index words psi, 4 index words phi], N1 / N2 of them used
-template <int N1, int N2>
-__device__ __forceinline__ const uint32_t* pi_run(const uint32_t* __restrict__ b, uint32_t count, uint32_t xs, const uint4& sel, Planes& P) {
-#pragma unroll 1
-  for (uint32_t i = 0; i < count; ++i, b += 8) {
-    uint32_t w[8];
-    ld_words<8>(b, w);
-    P.A2 ^= par_words<N1>(xs, w, sel) & par_words<N2>(xs, w + 4, sel);
-  }
-  return b;
+template <class LW, int N1, int N2>
+__device__ __forceinline__ const uint32_t* pi_run(const uint32_t* __restrict__ b, uint32_t count, uint32_t xs, const uint4& sel, Planes<LW>& P) {
+  return run_items<8, LaneWord<LW>::kPrefetch>(
+      b, count, [&](const uint32_t(&w)[8]) { P.A2 ^= par_words<LW, N1>(xs, w, sel) & par_words<LW, N2>(xs, w + 4, sel); });
 }
 
 // two-parity ops of the phase-pair family
-__device__ __forceinline__ void pair_op(Planes& P, uint32_t op, uint32_t prm, uint32_t q, uint32_t p, uint32_t nb, uint32_t* __restrict__ plw) {
+template <class LW>
+__device__ __forceinline__ void pair_op(Planes<LW>& P, uint32_t op, uint32_t prm, LW q, LW p, uint32_t nb, LW* __restrict__ plw) {
   if (op == OP_PAIRGEN) {
     const uint32_t r0 = 4u + nb + 2u * (prm & 15u);
     plw[r0 * 32u] = q;
     plw[(r0 + 1u) * 32u] = p;
     return;
   }
-  const uint32_t wd[3] = {q, p, q & p};
+  const LW wd[3] = {q, p, q & p};
 #pragma unroll
   for (int v = 0; v < 3; ++v) {
     add_a3(P.A0, P.A1, P.A2, (prm >> (6 * v)) & 7u, wd[v]);
     const int db = (int)((prm >> (6 * v + 3)) & 7u) - 3;
-    const uint32_t w = db > 0 ? wd[v] : ~wd[v];
+    const LW w = db > 0 ? wd[v] : ~wd[v];
     for (int r = 0; r < (db < 0 ? -db : db); ++r) add_cnt5(P.Bp, w);
   }
   const uint32_t ztt = (prm >> 18) & 15u;
@@ -269,47 +338,39 @@ __device__ __forceinline__ void pair_op(Planes& P, uint32_t op, uint32_t prm, ui
 }
 
 // LIN2 run: a += 2 p and nothing else
-template <int NW>
-__device__ __forceinline__ const uint32_t* lin2_run(const uint32_t* __restrict__ b, uint32_t count, uint32_t xs, const uint4& sel, Planes& P) {
+template <class LW, int NW>
+__device__ __forceinline__ const uint32_t* lin2_run(const uint32_t* __restrict__ b, uint32_t count, uint32_t xs, const uint4& sel, Planes<LW>& P) {
   constexpr int IW = NW <= 3 ? 4 : 8;
-#pragma unroll 1
-  for (uint32_t i = 0; i < count; ++i, b += IW) {
-    uint32_t w[IW];
-    ld_words<IW>(b, w);
-    const uint32_t p = par_words<NW>(xs, w + 1, sel);
+  return run_items<IW, LaneWord<LW>::kPrefetch>(b, count, [&](const uint32_t(&w)[IW]) {
+    const LW p = par_words<LW, NW>(xs, w + 1, sel);
     P.A2 ^= P.A1 & p;
     P.A1 ^= p;
-  }
-  return b;
+  });
 }
 
 // PAIR run: item = [op | params << 3, -, -, -, 4 index words, 4 index words], NW of each used
-template <int NW>
-__device__ __forceinline__ const uint32_t* pair_run(const uint32_t* __restrict__ b, uint32_t count, uint32_t xs, const uint4& sel, Planes& P,
-                                                     uint32_t nb, uint32_t* __restrict__ plw) {
-#pragma unroll 1
-  for (uint32_t i = 0; i < count; ++i, b += 12) {
-    const uint32_t hdr = *b;
-    uint32_t w[8];
-    ld_words<8>(b + 4, w);
-    const uint32_t q = par_words<NW>(xs, w, sel), p = par_words<NW>(xs, w + 4, sel);
-    pair_op(P, hdr & 7u, hdr >> 3, q, p, nb, plw);
-  }
-  return b;
+template <class LW, int NW>
+__device__ __forceinline__ const uint32_t* pair_run(const uint32_t* __restrict__ b, uint32_t count, uint32_t xs, const uint4& sel, Planes<LW>& P,
+                                                     uint32_t nb, LW* __restrict__ plw) {
+  return run_items<12, false>(b, count, [&](const uint32_t(&w)[12]) {
+    const LW q = par_words<LW, NW>(xs, w + 4, sel), p = par_words<LW, NW>(xs, w + 8, sel);
+    pair_op(P, w[0] & 7u, w[0] >> 3, q, p, nb, plw);
+  });
 }
 
 // generic run: a stream of parity blocks (pack_sliced.py::_block) with a per-block dispatch
-__device__ __forceinline__ const uint32_t* generic_run(const uint32_t* __restrict__ b, uint32_t words, uint32_t xs, const uint4& sel, Planes& P,
-                                                        uint32_t nb, uint32_t* __restrict__ plw) {
+template <class LW>
+__device__ __forceinline__ const uint32_t* generic_run(const uint32_t* __restrict__ b, uint32_t words, uint32_t xs, const uint4& sel, Planes<LW>& P,
+                                                        uint32_t nb, LW* __restrict__ plw) {
   const uint32_t* __restrict__ end = b + words;
-  uint32_t q = 0;
+  LW q = LaneWord<LW>::zero();
   while (b < end) {
     const uint2 h = *reinterpret_cast<const uint2*>(b);
     const uint32_t hdr = h.x, n = h.y;
-    uint32_t p = 0u;
+    LW p = LaneWord<LW>::zero();
     for (uint32_t i = 0; i < n; i += 2) {
       const uint2 w = *reinterpret_cast<const uint2*>(b + 2 + i);
-      p ^= par4(xs, w.x, sel) ^ par4(xs, w.y, sel);
+      p ^= par4<LW>(xs, w.x, sel) ^ par4<LW>(xs, w.y, sel);
     }
     b += 2 + n;
     const uint32_t op = hdr & 7u, prm = hdr >> 3;
@@ -326,18 +387,19 @@ __device__ __forceinline__ const uint32_t* generic_run(const uint32_t* __restric
   return b;
 }
 
-// phase 1: the term stream of one graph (typed runs, pack_sliced.py::_emit_runs) for the 32 slabs of the group ->
+// phase 1: the term stream of one graph (typed runs, pack_sliced.py::_emit_runs) for the lanes of the group ->
 // plane rows plw[r * 32]: r = 0 "some factor vanished", 1..3 a, 4..4+nb-1 the b counter, then (pa, pb) of every
 // in-table general pair.
-__device__ __forceinline__ void sliced_phase1(const uint32_t* __restrict__ cbase, uint32_t rec, const uint32_t* __restrict__ xcol,
-                                              uint32_t* __restrict__ plw, const uint4& sel) {
+template <class LW>
+__device__ __forceinline__ void sliced_phase1(const uint32_t* __restrict__ cbase, uint32_t rec, const LW* __restrict__ xcol,
+                                              LW* __restrict__ plw, const uint4& sel) {
   const uint32_t xs = smem_u32(xcol);
   const uint2 h0 = *reinterpret_cast<const uint2*>(cbase + rec);
   const uint32_t nb = (h0.y >> 8) & 0xFFu;
-  Planes P;
-  P.A0 = P.A1 = P.A2 = P.Z = 0u;
+  Planes<LW> P;
+  P.A0 = P.A1 = P.A2 = P.Z = LaneWord<LW>::zero();
 #pragma unroll
-  for (int i = 0; i < 5; ++i) P.Bp[i] = 0u;
+  for (int i = 0; i < 5; ++i) P.Bp[i] = LaneWord<LW>::zero();
   const uint32_t* __restrict__ b = cbase + rec + kSlicedHeaderWords;
   const uint32_t* __restrict__ end = b + (h0.x & 0xFFFFu);
   while (b < end) {
@@ -345,22 +407,22 @@ __device__ __forceinline__ void sliced_phase1(const uint32_t* __restrict__ cbase
     const uint32_t kind = rh & 0xFFFFu, count = rh >> 16;
     b += 4;
     switch (kind) {
-      case RUN_LIN + 0: b = lin_run<2>(b, count, xs, sel, P); break;
-      case RUN_LIN + 1: b = lin_run<3>(b, count, xs, sel, P); break;
-      case RUN_LIN + 2: b = lin_run<4>(b, count, xs, sel, P); break;
-      case RUN_PI + 0: b = pi_run<2, 2>(b, count, xs, sel, P); break;
-      case RUN_PI + 1: b = pi_run<2, 3>(b, count, xs, sel, P); break;
-      case RUN_PI + 2: b = pi_run<2, 4>(b, count, xs, sel, P); break;
-      case RUN_PI + 3: b = pi_run<3, 3>(b, count, xs, sel, P); break;
-      case RUN_PI + 4: b = pi_run<3, 4>(b, count, xs, sel, P); break;
-      case RUN_PI + 5: b = pi_run<4, 4>(b, count, xs, sel, P); break;
-      case RUN_LIN2 + 0: b = lin2_run<2>(b, count, xs, sel, P); break;
-      case RUN_LIN2 + 1: b = lin2_run<3>(b, count, xs, sel, P); break;
-      case RUN_LIN2 + 2: b = lin2_run<4>(b, count, xs, sel, P); break;
-      case RUN_PAIR + 0: b = pair_run<2>(b, count, xs, sel, P, nb, plw); break;
-      case RUN_PAIR + 1: b = pair_run<3>(b, count, xs, sel, P, nb, plw); break;
-      case RUN_PAIR + 2: b = pair_run<4>(b, count, xs, sel, P, nb, plw); break;
-      default: b = generic_run(b, count, xs, sel, P, nb, plw); break;
+      case RUN_LIN + 0: b = lin_run<LW, 2>(b, count, xs, sel, P); break;
+      case RUN_LIN + 1: b = lin_run<LW, 3>(b, count, xs, sel, P); break;
+      case RUN_LIN + 2: b = lin_run<LW, 4>(b, count, xs, sel, P); break;
+      case RUN_PI + 0: b = pi_run<LW, 2, 2>(b, count, xs, sel, P); break;
+      case RUN_PI + 1: b = pi_run<LW, 2, 3>(b, count, xs, sel, P); break;
+      case RUN_PI + 2: b = pi_run<LW, 2, 4>(b, count, xs, sel, P); break;
+      case RUN_PI + 3: b = pi_run<LW, 3, 3>(b, count, xs, sel, P); break;
+      case RUN_PI + 4: b = pi_run<LW, 3, 4>(b, count, xs, sel, P); break;
+      case RUN_PI + 5: b = pi_run<LW, 4, 4>(b, count, xs, sel, P); break;
+      case RUN_LIN2 + 0: b = lin2_run<LW, 2>(b, count, xs, sel, P); break;
+      case RUN_LIN2 + 1: b = lin2_run<LW, 3>(b, count, xs, sel, P); break;
+      case RUN_LIN2 + 2: b = lin2_run<LW, 4>(b, count, xs, sel, P); break;
+      case RUN_PAIR + 0: b = pair_run<LW, 2>(b, count, xs, sel, P, nb, plw); break;
+      case RUN_PAIR + 1: b = pair_run<LW, 3>(b, count, xs, sel, P, nb, plw); break;
+      case RUN_PAIR + 2: b = pair_run<LW, 4>(b, count, xs, sel, P, nb, plw); break;
+      default: b = generic_run<LW>(b, count, xs, sel, P, nb, plw); break;
     }
   }
   plw[0] = P.Z;
@@ -390,11 +452,16 @@ __device__ __forceinline__ void transpose8x8(uint32_t& lo, uint32_t& hi) {
 // phase 2: this warp's SH shots of every slab (warp w of the group: shots w * SH ...): the plane bits of a shot form
 // the index of its decode-table entry.  The first eight index planes are gathered with byte permutes and one 8 x 8
 // bit transpose, and a dp4a per shot scales the index byte into the entry's address; further planes are rare.
-template <int SH, bool HAS_EXACT>
-__device__ __forceinline__ void sliced_phase2(const uint32_t* __restrict__ cbase, uint32_t rec, const uint32_t* __restrict__ plj, int w,
-                                              bool approx, const uint4& sel_e, typename SlicedAcc<HAS_EXACT>::type (&acc)[SH],
+// plj: this lane's word of plane row 0 (rows are 32 lane words apart); a wide lane word is read once for both slabs.
+__device__ __forceinline__ uint32_t lw_half(uint32_t v, int) { return v; }
+__device__ __forceinline__ uint32_t lw_half(const U2& v, int h) { return h ? v.y : v.x; }
+
+template <int SH, bool HAS_EXACT, class LW>
+__device__ __forceinline__ void sliced_phase2(const uint32_t* __restrict__ cbase, uint32_t rec, const LW* __restrict__ plj, int w,
+                                              bool approx, const uint4& sel_e, typename SlicedAcc<HAS_EXACT>::type* __restrict__ acc_all,
                                               const int4* __restrict__ pair_tab) {
   static_assert(SH == 8 || SH == 4, "a warp handles a byte or a nibble of every plane word");
+  constexpr int NH = LaneWord<LW>::kWords;
   const uint4 h0 = *reinterpret_cast<const uint4*>(cbase + rec);
   const int n_idx = (int)(h0.y & 0xFFu);
   const uint32_t tbl = smem_u32(cbase + h0.z);
@@ -403,96 +470,119 @@ __device__ __forceinline__ void sliced_phase2(const uint32_t* __restrict__ cbase
   const uint32_t kEntryShift = (HAS_EXACT && !approx) ? 4u : 3u;
   const int sh0 = w * SH;
   const uint32_t bsel = (uint32_t)(SH == 8 ? w : (w >> 1));  // byte of the plane words that holds this warp's shots
-  uint32_t pb[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) pb[k] = k < n_idx ? plj[(1 + k) * 32] : 0u;
   const uint32_t ps = bsel | ((4u + bsel) << 4);
-  uint32_t lo = __byte_perm(__byte_perm(pb[0], pb[1], ps), __byte_perm(pb[2], pb[3], ps), 0x5410);
-  uint32_t hi = __byte_perm(__byte_perm(pb[4], pb[5], ps), __byte_perm(pb[6], pb[7], ps), 0x5410);
-  transpose8x8(lo, hi);
-  uint32_t base[SH];
-#pragma unroll
-  for (int s = 0; s < SH; ++s) base[s] = tbl;
-  for (int k = 8; k < n_idx; ++k) {
-    const uint32_t pk = ((plj[(1 + k) * 32] >> sh0) & kField) << (k + kEntryShift);
-    const uint32_t m = 1u << (k + kEntryShift);
-#pragma unroll
-    for (int s = 0; s < SH; ++s) base[s] += (pk >> s) & m;
-  }
-  const uint32_t zb = plj[0] >> sh0;
   const uint32_t zero_entry = smem_u32(cbase + rec + 4);  // reserved header words: a shot whose value vanished adds 0
-  const uint32_t r0 = SH == 8 ? lo : ((w & 1) ? hi : lo), r1 = hi;
-  // exact levels: general phase pairs applied as ring factors (two-stage decode, pack_sliced.py): pair j's parities
-  // sit in planes 1 + n_idx + 2 j (alpha side) and + 1 (beta side); its control byte alpha | beta << 3 in the record's
-  // last four words.  qab[j] = this warp's SH alpha bits | SH beta bits << 8.
-  uint32_t n_mul = 0, ctlw = 0, qab[4] = {0u, 0u, 0u, 0u};
-  if constexpr (HAS_EXACT) {
-    if (!approx) {
-      n_mul = (h0.y >> 16) & 0xFFu;
-      if (n_mul) {
-        ctlw = cbase[rec + h0.w - 4];
+  LW pbw[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if ((uint32_t)j < n_mul)
-            qab[j] = ((plj[(1 + n_idx + 2 * j) * 32] >> sh0) & kField) | (((plj[(2 + n_idx + 2 * j) * 32] >> sh0) & kField) << 8);
+  for (int k = 0; k < 8; ++k) pbw[k] = k < n_idx ? plj[(1 + k) * 32] : LaneWord<LW>::zero();
+  const LW zw = plj[0];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    typename SlicedAcc<HAS_EXACT>::type* __restrict__ acc = acc_all + h * SH;
+    uint32_t pb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pb[k] = lw_half(pbw[k], h);
+    uint32_t lo = __byte_perm(__byte_perm(pb[0], pb[1], ps), __byte_perm(pb[2], pb[3], ps), 0x5410);
+    uint32_t hi = __byte_perm(__byte_perm(pb[4], pb[5], ps), __byte_perm(pb[6], pb[7], ps), 0x5410);
+    transpose8x8(lo, hi);
+    uint32_t base[SH];
+#pragma unroll
+    for (int s = 0; s < SH; ++s) base[s] = tbl;
+    for (int k = 8; k < n_idx; ++k) {
+      const uint32_t pk = ((lw_half(plj[(1 + k) * 32], h) >> sh0) & kField) << (k + kEntryShift);
+      const uint32_t m = 1u << (k + kEntryShift);
+#pragma unroll
+      for (int s = 0; s < SH; ++s) base[s] += (pk >> s) & m;
+    }
+    const uint32_t zb = lw_half(zw, h) >> sh0;
+    const uint32_t r0 = SH == 8 ? lo : ((w & 1) ? hi : lo), r1 = hi;
+    // exact levels: general phase pairs applied as ring factors (two-stage decode, pack_sliced.py): pair j's parities
+    // sit in planes 1 + n_idx + 2 j (alpha side) and + 1 (beta side); its control byte alpha | beta << 3 in the record's
+    // last four words.  qab[j] = this warp's SH alpha bits | SH beta bits << 8.
+    uint32_t n_mul = 0, ctlw = 0, qab[4] = {0u, 0u, 0u, 0u};
+    if constexpr (HAS_EXACT) {
+      if (!approx) {
+        n_mul = (h0.y >> 16) & 0xFFu;
+        if (n_mul) {
+          ctlw = cbase[rec + h0.w - 4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if ((uint32_t)j < n_mul)
+              qab[j] = ((lw_half(plj[(1 + n_idx + 2 * j) * 32], h) >> sh0) & kField) |
+                       (((lw_half(plj[(2 + n_idx + 2 * j) * 32], h) >> sh0) & kField) << 8);
+        }
       }
     }
-  }
 #pragma unroll
-  for (int s = 0; s < SH; ++s) {
-    const uint32_t r = s < 4 ? r0 : r1;
-    uint32_t sl = (s & 3) == 0 ? sel_e.x : (s & 3) == 1 ? sel_e.y : (s & 3) == 2 ? sel_e.z : sel_e.w;
-    if (HAS_EXACT && !approx) sl <<= 1;
-    uint32_t ea = __dp4a(r, sl, base[s]);
-    ea = ((zb >> s) & 1u) ? zero_entry : ea;
-    if (approx) {
-      const float2 e = *reinterpret_cast<const float2*>(__cvta_shared_to_generic(ea));
-      if constexpr (HAS_EXACT) {
-        acc[s].x = __float_as_uint(__fadd_rn(__uint_as_float(acc[s].x), e.x));
-        acc[s].y = __float_as_uint(__fadd_rn(__uint_as_float(acc[s].y), e.y));
+    for (int s = 0; s < SH; ++s) {
+      const uint32_t r = s < 4 ? r0 : r1;
+      uint32_t sl = (s & 3) == 0 ? sel_e.x : (s & 3) == 1 ? sel_e.y : (s & 3) == 2 ? sel_e.z : sel_e.w;
+      if (HAS_EXACT && !approx) sl <<= 1;
+      uint32_t ea = __dp4a(r, sl, base[s]);
+      ea = ((zb >> s) & 1u) ? zero_entry : ea;
+      if (approx) {
+        const float2 e = *reinterpret_cast<const float2*>(__cvta_shared_to_generic(ea));
+        if constexpr (HAS_EXACT) {
+          acc[s].x = __float_as_uint(__fadd_rn(__uint_as_float(acc[s].x), e.x));
+          acc[s].y = __float_as_uint(__fadd_rn(__uint_as_float(acc[s].y), e.y));
+        } else {
+          acc[s].x = __fadd_rn(acc[s].x, e.x);
+          acc[s].y = __fadd_rn(acc[s].y, e.y);
+        }
       } else {
-        acc[s].x = __fadd_rn(acc[s].x, e.x);
-        acc[s].y = __fadd_rn(acc[s].y, e.y);
-      }
-    } else {
-      if constexpr (HAS_EXACT) {
-        uint4 e = *reinterpret_cast<const uint4*>(__cvta_shared_to_generic(ea));
-        if (n_mul) {  // warp-uniform
+        if constexpr (HAS_EXACT) {
+          uint4 e = *reinterpret_cast<const uint4*>(__cvta_shared_to_generic(ea));
+          if (n_mul) {  // warp-uniform
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if ((uint32_t)j < n_mul) {
-              const uint32_t ix = ((ctlw >> (8 * j)) & 63u) ^ (((qab[j] >> s) & 1u) << 2) ^ (((qab[j] >> (8 + s)) & 1u) << 5);
-              const ZW pr = zw_mul(ZW{e.x, e.y, e.z, e.w}, zw_from(pair_tab[ix]));
-              e = make_uint4(pr.c0, pr.c1, pr.c2, pr.c3);
+            for (int j = 0; j < 4; ++j) {
+              if ((uint32_t)j < n_mul) {
+                const uint32_t ix = ((ctlw >> (8 * j)) & 63u) ^ (((qab[j] >> s) & 1u) << 2) ^ (((qab[j] >> (8 + s)) & 1u) << 5);
+                const ZW pr = zw_mul(ZW{e.x, e.y, e.z, e.w}, zw_from(pair_tab[ix]));
+                e = make_uint4(pr.c0, pr.c1, pr.c2, pr.c3);
+              }
             }
           }
+          acc[s].x += e.x; acc[s].y += e.y; acc[s].z += e.z; acc[s].w += e.w;
         }
-        acc[s].x += e.x; acc[s].y += e.y; acc[s].z += e.z; acc[s].w += e.w;
       }
     }
   }
 }
 
 __host__ __device__ constexpr int sliced_max_groups(int split) { return split == 4 ? 7 : 3; }
-__host__ __device__ constexpr int sliced_max_threads(int split) { return sliced_max_groups(split) * split * 32; }
+constexpr int kWideMaxGroups = 4;  // wide layout: 4 warps per group, up to 8 units of 1024 shots per CTA
+__host__ __device__ constexpr int sliced_max_threads(int split, bool wide = false) {
+  return (wide ? kWideMaxGroups : sliced_max_groups(split)) * split * 32;
+}
 
 __device__ __forceinline__ void group_sync(int grp, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ uint32_t atom_add_acq_rel_shared(uint32_t* p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+  return old;
+}
+constexpr int kSlicedMaxStages = 16;  // full barriers in the first half of the barrier words, release counters in the second
 
-// dynamic shared memory (32-bit words): [0,64) mbarriers | xt [ng][rows][32] | planes [ng][2][SPLIT][plane_rows][32] |
-// stage ring
-template <int SPLIT, bool HAS_EXACT, bool HAS_ROWS>
-__global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_kernel(const SParams prm) {
+// dynamic shared memory (32-bit words): [0,64) mbarriers | xt [groups][rows][32 lanes] | planes
+// [groups][2][SPLIT][plane_rows][32 lanes] | stage ring; a lane is one word (narrow) or two (wide)
+template <int SPLIT, bool HAS_EXACT, bool HAS_ROWS, bool WIDE>
+__global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sliced_kernel(const SParams prm) {
+  static_assert(!WIDE || (SPLIT == 4 && !HAS_EXACT), "the wide layout is built for the 4-way split of approximate programs");
   constexpr int SH = 32 / SPLIT;
-  int n_slabs = prm.n_slabs, n_groups = prm.n_groups, rounds = prm.rounds;
+  constexpr int NH = WIDE ? 2 : 1;  // slabs per lane
+  typedef typename std::conditional<WIDE, U2, uint32_t>::type LW;
+  typedef LaneWord<LW> L;
+  // a *unit* is 32 slabs (1024 shots): a narrow group, or half the lanes of a wide group
+  int n_slabs = prm.n_slabs, n_units = prm.n_groups, rounds = prm.rounds;
   if constexpr (HAS_ROWS) {
     const long long nr = (long long)*prm.n_rows;
     n_slabs = (int)((nr + 31) / 32);
-    n_groups = (n_slabs + 31) / 32;
-    if ((int)blockIdx.x >= n_groups) return;  // this CTA owns no group in any round
-    const int gpc = (n_groups + (int)gridDim.x - 1) / (int)gridDim.x;
-    rounds = (gpc + prm.ng - 1) / prm.ng;
+    n_units = (n_slabs + 31) / 32;
+    if ((int)blockIdx.x >= n_units) return;  // this CTA owns no unit in any round
+    const int upc = (n_units + (int)gridDim.x - 1) / (int)gridDim.x;
+    rounds = (upc + prm.ng - 1) / prm.ng;
   }
   typedef typename SlicedAcc<HAS_EXACT>::type Acc;
   extern __shared__ __align__(128) uint32_t smem[];
@@ -500,16 +590,9 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int grp = wid / SPLIT, w = wid % SPLIT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  // word offsets of this thread's columns; made opaque so that the compiler keeps them in registers instead of
-  // re-deriving them from threadIdx inside the block loop (it did, ten instructions per block)
-  uint32_t xoff = prm.smem_xt_off + grp * prm.rows * 32 + lane;
-  // one graph slot of a plane buffer; only exact levels multiply pairs, so all-approximate programs keep the constant
+  // one graph slot of a plane buffer (lane words); only exact levels multiply pairs, so all-approximate programs keep the constant
   const int plane_words = HAS_EXACT ? prm.plane_rows * 32 : kMinPlaneRows * 32;
-  uint32_t ploff = prm.smem_pl_off + grp * (2 * SPLIT * plane_words) + lane;  // two plane buffers per group
   const uint4 sel = prm.sel;
-  asm volatile("" : "+r"(xoff), "+r"(ploff));
-  uint32_t* xcol = smem + xoff;
-  uint32_t* plg = smem + ploff;
   uint32_t* sdata = smem + prm.smem_data_off;
 
   const int n_comp = (int)blob[H_N_COMP], n_chunks = (int)blob[H_N_CHUNKS];
@@ -528,8 +611,16 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
       s_pair[i] = make_int4(1 + ua.x + ub.x - uc.x, ua.y + ub.y - uc.y, ua.z + ub.z - uc.z, ua.w + ub.w - uc.w);
     }
   }
+  // Ring flow control without a CTA-wide barrier: a warp that is through with a stage counts itself out, and the last one
+  // refills the stage.  Groups therefore drift apart by up to n_stages chunks, so that one group's phase 2 and level
+  // ends (issue-bound) overlap another group's phase 1 (shared-memory bound) instead of all groups moving in lockstep.
+  uint32_t* released = reinterpret_cast<uint32_t*>(bars + kSlicedMaxStages);
+  const uint32_t n_warps = blockDim.x >> 5;
   if (tid == 0) {
-    for (int i = 0; i < prm.n_stages; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < prm.n_stages; ++i) {
+      mbar_init(&bars[i], 1);
+      released[i] = 0u;
+    }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -550,12 +641,36 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
   long long q = 0;
   uint32_t pbuf = 0;  // plane buffer of the current wave (double-buffered: one group barrier per wave)
   for (int round = 0; round < rounds; ++round) {
-    const int ggrp = (round * prm.ng + grp) * (int)gridDim.x + (int)blockIdx.x;
-    const bool gactive = ggrp < n_groups;  // uniform over the group's warps
-    const int slab = ggrp * 32 + lane;
-    const bool active = gactive && slab < n_slabs;
-    const unsigned long long shot0 =
-        (unsigned long long)prm.shot_offset + (unsigned long long)slab * 32ull + (unsigned long long)(w * SH);
+    // units of this group in this round, the lane's slabs and its column of the group's matrix.  Lanes 16..31 of a
+    // half-filled wide group sit out (owner = false): 64-bit shared-memory accesses are served per half-warp, so an
+    // idle half costs no wavefront, and the group's traffic stays proportional to its shots.
+    int slab0;
+    const int col = lane;
+    bool gactive, owner = true;
+    if constexpr (WIDE) {
+      const int cu = 2 * grp;  // first unit of the group inside the CTA
+      const int u0 = (round * prm.ng + cu) * (int)gridDim.x + (int)blockIdx.x;
+      const int u1 = (round * prm.ng + cu + 1) * (int)gridDim.x + (int)blockIdx.x;
+      gactive = cu < prm.ng && u0 < n_units;
+      const bool have1 = cu + 1 < prm.ng && u1 < n_units;
+      const bool upper = lane >= 16;
+      if (upper && !have1) owner = false;
+      slab0 = ((upper && have1) ? u1 : u0) * 32 + 2 * (lane & 15);
+    } else {
+      const int u0 = (round * prm.ng + grp) * (int)gridDim.x + (int)blockIdx.x;
+      gactive = u0 < n_units;  // uniform over the group's warps
+      slab0 = u0 * 32 + lane;
+    }
+    bool active[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) active[h] = gactive && slab0 + h < n_slabs;
+    // word offsets of this thread's columns; made opaque so that the compiler keeps them in registers instead of
+    // re-deriving them from threadIdx inside the block loop (it did, ten instructions per block)
+    uint32_t xoff = grp * prm.rows * 32 + col;
+    uint32_t ploff = grp * (2 * SPLIT * plane_words) + col;  // two plane buffers per group
+    asm volatile("" : "+r"(xoff), "+r"(ploff));
+    LW* xcol = reinterpret_cast<LW*>(smem + prm.smem_xt_off) + xoff;
+    LW* plg = reinterpret_cast<LW*>(smem + prm.smem_pl_off) + ploff;
 
     int xt_row0 = 0, draw0 = 0;
     for (int ci = 0; ci < n_comp; ++ci) {
@@ -564,10 +679,19 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
       if (gactive) {
         group_sync(grp, SPLIT * 32);  // the previous component's readers are done with the columns
         for (int i = w; i < prm.rows; i += SPLIT) {
-          uint32_t v = 0u;
-          if (i < F) v = active ? prm.xt[(size_t)(xt_row0 + i) * prm.slab_cap + slab] : 0u;
-          else if (i == one_row) v = 0xFFFFFFFFu;
-          xcol[i * 32] = v;
+          LW v = L::zero();
+          if (i < F) {
+            const uint32_t* src = prm.xt + (size_t)(xt_row0 + i) * prm.slab_cap + slab0;
+            if constexpr (WIDE) {
+              v.x = active[0] ? src[0] : 0u;
+              v.y = active[1] ? src[1] : 0u;
+            } else {
+              v = active[0] ? src[0] : 0u;
+            }
+          } else if (i == one_row) {
+            v = L::ones();
+          }
+          if (owner) xcol[i * 32] = v;
         }
       }
 
@@ -575,12 +699,12 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
         const uint32_t* __restrict__ lvl = level_tab + (comp[C_FIRST_LEVEL] + k) * kLevelWords;
         const bool approx = (lvl[L_FLAGS] & 1u) != 0u;
         if (gactive) {
-          if (k > 0 && w == 0) xcol[(F + k - 1) * 32] = 0xFFFFFFFFu;  // trying bit 1 for every shot
+          if (k > 0 && w == 0 && owner) xcol[(F + k - 1) * 32] = L::ones();  // trying bit 1 for every shot
           group_sync(grp, SPLIT * 32);
         }
-        Acc acc[SH];
+        Acc acc[NH * SH];
 #pragma unroll
-        for (int s = 0; s < SH; ++s) {
+        for (int s = 0; s < NH * SH; ++s) {
           if constexpr (HAS_EXACT) acc[s] = make_uint4(0u, 0u, 0u, 0u);
           else acc[s] = make_float2(0.0f, 0.0f);
         }
@@ -595,17 +719,24 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
             for (int w0 = 0; w0 < n_g; w0 += SPLIT) {
               // A warp may write the other buffer for the next wave as soon as it is through with this one: everybody
               // passed this wave's barrier, hence finished reading that buffer in the wave before.
-              uint32_t* pw = plg + pbuf * (SPLIT * plane_words);
-              if (w0 + w < n_g) sliced_phase1(cbase, cbase[w0 + w], xcol, pw + w * plane_words, sel);
+              LW* pw = plg + pbuf * (SPLIT * plane_words);
+              if (w0 + w < n_g && owner) sliced_phase1<LW>(cbase, cbase[w0 + w], xcol, pw + w * plane_words, sel);
               group_sync(grp, SPLIT * 32);
               const int nj = min(SPLIT, n_g - w0);
-              for (int j = 0; j < nj; ++j)
-                sliced_phase2<SH, HAS_EXACT>(cbase, cbase[w0 + j], pw + j * plane_words, w, approx, prm.sel_e, acc, s_pair);
+              if (owner)
+                for (int j = 0; j < nj; ++j)
+                  sliced_phase2<SH, HAS_EXACT, LW>(cbase, cbase[w0 + j], pw + j * plane_words, w, approx, prm.sel_e, acc, s_pair);
               pbuf ^= 1u;
             }
           }
-          __syncthreads();  // every group is done with this stage
-          if (tid == 0 && q + prm.n_stages < total_q) issue(q + prm.n_stages);
+          __syncwarp();
+          if (lane == 0 && atom_add_acq_rel_shared(&released[stage], 1u) == n_warps - 1u) {  // every warp is done with this stage
+            released[stage] = 0u;
+            if (q + prm.n_stages < total_q) {
+              fence_proxy_async();
+              issue(q + prm.n_stages);
+            }
+          }
           ++q;
         }
         // finish the level for this warp's shots: |amp|, draw, chain rule
@@ -617,63 +748,78 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT), 1) sample_sliced_ke
             k0 = prm.subkeys[2 * (draw0 + k - 1)];
             k1 = prm.subkeys[2 * (draw0 + k - 1) + 1];
           }
-          // chain-rule state of this warp's shots lives in global memory between levels (L2-resident, 32 B per lane)
-          float4* pvp = reinterpret_cast<float4*>(prm.pv + (size_t)slab * 32 + w * SH);
-          float pvv[SH];
 #pragma unroll
-          for (int s = 0; s < SH; s += 4) {
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k > 0 && active) t = pvp[s >> 2];
-            pvv[s] = t.x; pvv[s + 1] = t.y; pvv[s + 2] = t.z; pvv[s + 3] = t.w;
-          }
-          uint32_t rid[SH];  // HAS_ROWS: batch row (= RNG counter) of each shot of this lane's slab
-          if constexpr (HAS_ROWS) {
-            const uint4* rp = reinterpret_cast<const uint4*>(prm.row_list + (size_t)slab * 32 + w * SH);
+          for (int h = 0; h < NH; ++h) {
+            if (!owner) break;
+            const int slab = slab0 + h;
+            const unsigned long long shot0 =
+                (unsigned long long)prm.shot_offset + (unsigned long long)slab * 32ull + (unsigned long long)(w * SH);
+            // chain-rule state of this warp's shots lives in global memory between levels (L2-resident, 32 B per lane)
+            float4* pvp = reinterpret_cast<float4*>(prm.pv + (size_t)slab * 32 + w * SH);
+            float pvv[SH];
 #pragma unroll
             for (int s = 0; s < SH; s += 4) {
-              uint4 t = make_uint4(0u, 0u, 0u, 0u);
-              if (k > 0 && active) t = rp[s >> 2];
-              rid[s] = t.x; rid[s + 1] = t.y; rid[s + 2] = t.z; rid[s + 3] = t.w;
+              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (k > 0 && active[h]) t = pvp[s >> 2];
+              pvv[s] = t.x; pvv[s + 1] = t.y; pvv[s + 2] = t.z; pvv[s + 3] = t.w;
             }
-          }
-          uint32_t bits = 0;
+            uint32_t rid[SH];  // HAS_ROWS: batch row (= RNG counter) of each shot of this lane's slab
+            if constexpr (HAS_ROWS) {
+              const uint4* rp = reinterpret_cast<const uint4*>(prm.row_list + (size_t)slab * 32 + w * SH);
 #pragma unroll
-          for (int s = 0; s < SH; ++s) {
-            float re = 0.0f, im = 0.0f;
-            if (approx) {
-              if constexpr (HAS_EXACT) { re = __uint_as_float(acc[s].x); im = __uint_as_float(acc[s].y); }
-              else { re = acc[s].x; im = acc[s].y; }
-            } else {
-              if constexpr (HAS_EXACT) {
-                ZW cz = ZW{acc[s].x, acc[s].y, acc[s].z, acc[s].w};
-                int p = p_lo;
-                zw_fixpoint(cz, p);
-                zw_to_complex(cz, p, re, im);
+              for (int s = 0; s < SH; s += 4) {
+                uint4 t = make_uint4(0u, 0u, 0u, 0u);
+                if (k > 0 && active[h]) t = rp[s >> 2];
+                rid[s] = t.x; rid[s + 1] = t.y; rid[s + 2] = t.z; rid[s + 3] = t.w;
               }
             }
-            if (empty) { re = 0.0f; im = 0.0f; }
-            const float p1 = complex_abs(re, im);
-            if (k == 0) {
-              pvv[s] = p1;
-            } else {
-              const float pv = pvv[s];
-              const unsigned long long ctr = HAS_ROWS ? (unsigned long long)prm.shot_offset + (unsigned long long)rid[s]
-                                                      : shot0 + (unsigned long long)s;
-              const float u = uniform_f32(k0, k1, ctr);
-              const bool bit = u < __fdiv_rn(p1, pv);
-              pvv[s] = bit ? p1 : __fsub_rn(pv, p1);
-              bits |= (bit ? 1u : 0u) << s;
+            uint32_t bits = 0;
+#pragma unroll
+            for (int s = 0; s < SH; ++s) {
+              const Acc a = acc[h * SH + s];
+              float re = 0.0f, im = 0.0f;
+              if (approx) {
+                if constexpr (HAS_EXACT) { re = __uint_as_float(a.x); im = __uint_as_float(a.y); }
+                else { re = a.x; im = a.y; }
+              } else {
+                if constexpr (HAS_EXACT) {
+                  ZW cz = ZW{a.x, a.y, a.z, a.w};
+                  int p = p_lo;
+                  zw_fixpoint(cz, p);
+                  zw_to_complex(cz, p, re, im);
+                }
+              }
+              if (empty) { re = 0.0f; im = 0.0f; }
+              const float p1 = complex_abs(re, im);
+              if (k == 0) {
+                pvv[s] = p1;
+              } else {
+                const float pv = pvv[s];
+                const unsigned long long ctr = HAS_ROWS ? (unsigned long long)prm.shot_offset + (unsigned long long)rid[s]
+                                                        : shot0 + (unsigned long long)s;
+                const float u = uniform_f32(k0, k1, ctr);
+                const bool bit = u < __fdiv_rn(p1, pv);
+                pvv[s] = bit ? p1 : __fsub_rn(pv, p1);
+                bits |= (bit ? 1u : 0u) << s;
+              }
+            }
+            if (active[h] && k < n_c) {
+#pragma unroll
+              for (int s = 0; s < SH; s += 4) pvp[s >> 2] = make_float4(pvv[s], pvv[s + 1], pvv[s + 2], pvv[s + 3]);
+            }
+            if (k > 0) {
+              constexpr uint32_t kField = SH == 32 ? 0xFFFFFFFFu : ((1u << SH) - 1u);
+              atomicAnd(reinterpret_cast<uint32_t*>(&xcol[(F + k - 1) * 32]) + h, (bits << (w * SH)) | ~(kField << (w * SH)));
             }
           }
-          if (active && k < n_c) {
-#pragma unroll
-            for (int s = 0; s < SH; s += 4) pvp[s >> 2] = make_float4(pvv[s], pvv[s + 1], pvv[s + 2], pvv[s + 3]);
-          }
           if (k > 0) {
-            constexpr uint32_t kField = SH == 32 ? 0xFFFFFFFFu : ((1u << SH) - 1u);
-            atomicAnd(&xcol[(F + k - 1) * 32], (bits << (w * SH)) | ~(kField << (w * SH)));
             group_sync(grp, SPLIT * 32);
-            if (w == 0 && active) prm.ot[(size_t)(draw0 + k - 1) * prm.slab_cap + slab] = xcol[(F + k - 1) * 32];
+            if (w == 0 && owner) {
+              const uint32_t* drawn = reinterpret_cast<const uint32_t*>(&xcol[(F + k - 1) * 32]);
+#pragma unroll
+              for (int h = 0; h < NH; ++h)
+                if (active[h]) prm.ot[(size_t)(draw0 + k - 1) * prm.slab_cap + slab0 + h] = drawn[h];
+            }
           }
         }
       }

@@ -672,7 +672,7 @@ struct tsb_program {
   uint32_t* h_heavy_seen = nullptr;  // pinned: heavy-row count of an earlier memoised sliced launch (launch-shape hint only)
   long long heavy_seen_B = 0;
   // MODE_SLICED
-  int is_sliced = 0, s_has_exact = 0, s_rows = 0, s_plane_rows = 0, s_smem_limit = 0, s_stage_words = 0;
+  int is_sliced = 0, s_has_exact = 0, s_rows = 0, s_plane_rows = 0, s_smem_limit = 0, s_stage_words = 0, s_index_scale = 1;
   int total_F = 0, max_nc = 0;
   tsb_program* aux = nullptr;   // companion per-row program (norm check); not owned
   cudaStream_t side = nullptr;  // the norm check of shot 0 runs here, overlapped with the rest of the batch
@@ -758,26 +758,34 @@ static EvalFn eval_fn_for(int W) {
   }
 }
 typedef void (*SlicedFn)(const SParams);
-// exact-branch accumulators are four words per shot: only the 8-way split keeps them in registers
-static SlicedFn sliced_fn(int split, int has_exact, bool rows = false) {
+// exact-branch accumulators are four words per shot: only the 8-way split keeps them in registers; the wide layout
+// (64-bit lanes) exists for the 4-way split of all-approximate programs
+static SlicedFn sliced_fn(int split, int has_exact, bool rows = false, bool wide = false) {
+  if (wide) return rows ? sample_sliced_kernel<4, false, true, true> : sample_sliced_kernel<4, false, false, true>;
   if (rows) {
-    if (has_exact) return sample_sliced_kernel<8, true, true>;
-    return split == 4 ? sample_sliced_kernel<4, false, true> : sample_sliced_kernel<8, false, true>;
+    if (has_exact) return sample_sliced_kernel<8, true, true, false>;
+    return split == 4 ? sample_sliced_kernel<4, false, true, false> : sample_sliced_kernel<8, false, true, false>;
   }
-  if (has_exact) return sample_sliced_kernel<8, true, false>;
-  return split == 4 ? sample_sliced_kernel<4, false, false> : sample_sliced_kernel<8, false, false>;
+  if (has_exact) return sample_sliced_kernel<8, true, false, false>;
+  return split == 4 ? sample_sliced_kernel<4, false, false, false> : sample_sliced_kernel<8, false, false, false>;
 }
 
 // Shared-memory plan of one sliced launch: `ng` groups of `split` warps (sliced_kernels.cuh).
+// `ng` = units (32 slabs = 1024 shots) per CTA and round: one narrow group each, or half a wide group (64-bit lanes).
 struct SlicedPlan {
-  int split = 0, ng = 0, rounds = 0, grid = 0, n_stages = 0;
+  int split = 0, ng = 0, rounds = 0, grid = 0, n_stages = 0, wide = 0, groups = 0;
   int xt_off = 0, pl_off = 0, data_off = 0, smem_bytes = 0;
 };
-static int sliced_group_words(int rows, int split, int plane_rows) { return rows * 32 + 2 * split * plane_rows * 32; }  // matrix + two plane buffers
-// largest number of groups (<= cap) that leaves room for `want_stages` stages; 0 if not even one group fits
-static int sliced_fit_groups(int rows, int plane_rows, int split, int cap, int stage_words, int want_stages, int smem_limit) {
-  for (int ng = cap; ng >= 1; --ng)
-    if (((long long)kBarWords + (long long)ng * sliced_group_words(rows, split, plane_rows) + (long long)want_stages * stage_words) * 4 <= smem_limit) return ng;
+// matrix + two plane buffers of one group, in 32-bit words
+static int sliced_group_words(int rows, int split, int plane_rows, bool wide = false) {
+  return (rows * 32 + 2 * split * plane_rows * 32) * (wide ? 2 : 1);
+}
+// largest number of units (<= cap) that leaves room for `want_stages` stages; 0 if not even one fits
+static int sliced_fit_groups(int rows, int plane_rows, int split, int cap, int stage_words, int want_stages, int smem_limit, bool wide = false) {
+  for (int nu = cap; nu >= 1; --nu) {
+    const int groups = wide ? (nu + 1) / 2 : nu;
+    if (((long long)kBarWords + (long long)groups * sliced_group_words(rows, split, plane_rows, wide) + (long long)want_stages * stage_words) * 4 <= smem_limit) return nu;
+  }
   return 0;
 }
 static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl, bool row_list, long long expect_rows);
@@ -831,6 +839,7 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
   if (mode == kModeSliced) {
     p->is_sliced = 1;
     p->s_rows = (int)blob[H_ZERO_ROW] + 1;
+    p->s_index_scale = blob[H_INDEX_SCALE] == 2u ? 2 : 1;
     p->s_plane_rows = kMinPlaneRows;
     const uint32_t* lv = blob + blob[H_OFF_LEVEL];
     for (uint32_t i = 0; i < blob[H_N_LEVELS]; ++i)
@@ -851,12 +860,15 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
       if (v > 0) lim_smem = std::min(lim_smem, v);
     }
     // static shared memory of the kernels (the pair-factor table of the exact variants) comes out of the same budget
+    const bool can_wide = !p->s_has_exact && p->s_index_scale == 2;
     for (int split : {4, 8})
-      for (bool rows : {false, true}) {
-        cudaFuncAttributes fa;
-        CUB(cudaFuncGetAttributes(&fa, (const void*)sliced_fn(split, p->s_has_exact, rows)));
-        lim_smem = std::min<int>(lim_smem, (int)prop.sharedMemPerBlockOptin - (int)fa.sharedSizeBytes);
-      }
+      for (bool rows : {false, true})
+        for (bool wide : {false, true}) {
+          if (wide && !(can_wide && split == 4)) continue;
+          cudaFuncAttributes fa;
+          CUB(cudaFuncGetAttributes(&fa, (const void*)sliced_fn(split, p->s_has_exact, rows, wide)));
+          lim_smem = std::min<int>(lim_smem, (int)prop.sharedMemPerBlockOptin - (int)fa.sharedSizeBytes);
+        }
     p->s_smem_limit = lim_smem;
     p->s_stage_words = std::max(32, ((int)blob[H_MAX_CHUNK] + 31) & ~31);
     const int split_min = p->s_has_exact ? 8 : 4;
@@ -867,7 +879,10 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
     }
     for (int split : {4, 8})
       for (bool rows : {false, true})
-        CUB(cudaFuncSetAttribute((const void*)sliced_fn(split, p->s_has_exact, rows), cudaFuncAttributeMaxDynamicSharedMemorySize, lim_smem));
+        for (bool wide : {false, true}) {
+          if (wide && !(can_wide && split == 4)) continue;
+          CUB(cudaFuncSetAttribute((const void*)sliced_fn(split, p->s_has_exact, rows, wide), cudaFuncAttributeMaxDynamicSharedMemorySize, lim_smem));
+        }
     fixed_words = kBarWords;
   }
   fixed_words = (fixed_words + 31) & ~31;  // 128-byte align the data region
@@ -910,7 +925,7 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
   if (mode == kModeSliced) {  // report the plan of a chip-filling batch
     SlicedPlan pl;
     sliced_plan(p, p->sm_count * 7 * 32, pl, false, -1);
-    in.threads = pl.ng * pl.split * 32; in.smem_bytes = pl.smem_bytes; in.resident = 0;
+    in.threads = pl.groups * pl.split * 32; in.smem_bytes = pl.smem_bytes; in.resident = 0;
     p->n_stages = pl.n_stages; p->stage_words = p->s_stage_words;
   }
 #undef CUB
@@ -1184,19 +1199,32 @@ static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl, bool 
   }
   const int n_chunks = (int)p->host_blob[H_N_CHUNKS];
   const int want = std::min(2, std::max(1, n_chunks));
-  int cap = std::min(sliced_max_groups(split), gpc);
-  int ng = sliced_fit_groups(p->s_rows, p->s_plane_rows, split, cap, p->s_stage_words, want, p->s_smem_limit);
-  if (!ng) ng = sliced_fit_groups(p->s_rows, p->s_plane_rows, split, cap, p->s_stage_words, 1, p->s_smem_limit);
+  // Wide layout (64-bit lanes, two units per group): fewer instructions per shot, fewer warps per SM.  Opt-in through
+  // TSIM_B200_SLICED_WIDE=1 (tuning knob).
+  bool wide = false;
+  int nu_wide = 0;
+  if (split == 4 && !p->s_has_exact && p->s_index_scale == 2) {
+    nu_wide = sliced_fit_groups(p->s_rows, p->s_plane_rows, 4, std::min(2 * kWideMaxGroups, gpc), p->s_stage_words, want, p->s_smem_limit, true);
+    // measured on cfg2 (10^6 shots): 25 % fewer instructions but 16 instead of 28 warps per SM, 0.718 vs 0.687 ms -- the
+    // narrow layout stays the default
+    if (const char* e = getenv("TSIM_B200_SLICED_WIDE")) wide = atoi(e) != 0 && nu_wide >= 1;
+  }
+  int cap = wide ? std::min(2 * kWideMaxGroups, gpc) : std::min(sliced_max_groups(split), gpc);
+  int ng = wide ? nu_wide : sliced_fit_groups(p->s_rows, p->s_plane_rows, split, cap, p->s_stage_words, want, p->s_smem_limit);
+  if (!ng) ng = sliced_fit_groups(p->s_rows, p->s_plane_rows, split, cap, p->s_stage_words, 1, p->s_smem_limit, wide);
   if (!ng) return false;
   pl.split = split;
+  pl.wide = wide ? 1 : 0;
   pl.rounds = (gpc + ng - 1) / ng;
   pl.ng = (gpc + pl.rounds - 1) / pl.rounds;
   if (row_list) pl.ng = ng;  // rounds are derived on the device from the live count
+  pl.groups = wide ? (pl.ng + 1) / 2 : pl.ng;
+  const int lane_words = wide ? 2 : 1;
   pl.xt_off = kBarWords;
-  pl.pl_off = pl.xt_off + pl.ng * p->s_rows * 32;
-  pl.data_off = pl.pl_off + pl.ng * 2 * split * p->s_plane_rows * 32;
+  pl.pl_off = pl.xt_off + pl.groups * p->s_rows * 32 * lane_words;
+  pl.data_off = pl.pl_off + pl.groups * 2 * split * p->s_plane_rows * 32 * lane_words;
   const long long room = (long long)p->s_smem_limit / 4 - pl.data_off;
-  pl.n_stages = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kMaxStages, std::max(1, n_chunks)), room / p->s_stage_words));
+  pl.n_stages = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kSlicedMaxStages, std::max(1, n_chunks)), room / p->s_stage_words));
   pl.smem_bytes = (pl.data_off + pl.n_stages * p->s_stage_words) * 4;
   return true;
 }
@@ -1241,11 +1269,15 @@ static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long 
     k.n_groups = (n_slabs + 31) / 32; k.ng = pl.ng; k.rounds = pl.rounds;
     k.n_stages = pl.n_stages; k.stage_words = p->s_stage_words;
     k.smem_xt_off = pl.xt_off; k.smem_pl_off = pl.pl_off; k.smem_data_off = pl.data_off;
-    k.rows = p->s_rows; k.plane_rows = p->s_plane_rows; k.sel = make_uint4(0x80u, 0x8000u, 0x800000u, 0x80000000u);
+    k.rows = p->s_rows; k.plane_rows = p->s_plane_rows;
+    {  // row stride in bytes (128 narrow, 256 wide) over the scale of the stored index bytes
+      const uint32_t sb = (pl.wide ? 256u : 128u) / (uint32_t)p->s_index_scale;
+      k.sel = make_uint4(sb, sb << 8, sb << 16, sb << 24);
+    }
     k.sel_e = make_uint4(8u, 8u << 8, 8u << 16, 8u << 24);
     k.row_list = rows; k.n_rows = n_rows;
     if (!memo && k1s_start) CU(cudaEventRecord(k1s_start, st));
-    sliced_fn(pl.split, p->s_has_exact, memo)<<<pl.grid, pl.ng * pl.split * 32, pl.smem_bytes, st>>>(k);
+    sliced_fn(pl.split, p->s_has_exact, memo, pl.wide != 0)<<<pl.grid, pl.groups * pl.split * 32, pl.smem_bytes, st>>>(k);
     CU(cudaGetLastError());
     if (!memo && k1s_stop) CU(cudaEventRecord(k1s_stop, st));
   }

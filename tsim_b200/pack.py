@@ -26,6 +26,8 @@ See DESIGN.md for ``MODE_FAST``.
 
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -33,7 +35,7 @@ import numpy as np
 from .program import CompiledProgram, CompiledScalarGraphs
 
 MAGIC = 0x32425354  # "TSB2"
-VERSION = 6
+VERSION = 7
 MODE_FAITHFUL = 0
 MODE_FAST = 1
 MODE_SLICED = 2
@@ -54,6 +56,7 @@ H_OFF_FSEL, H_OFF_DEST, H_OFF_DATA, H_DATA_WORDS = 16, 17, 18, 19
 H_TOTAL_WORDS, H_WF64, H_WOUT64, H_OFF_TABLES = 20, 21, 22, 23
 H_TABLE_WORDS = 24
 H_ONE_ROW, H_ZERO_ROW = 25, 26
+H_INDEX_SCALE = 28  # sliced: row index bytes are stored times this (see pack_sliced._index_words)
 H_PLANE_ROWS = 27  # sliced: plane rows per graph slot in shared memory (vanish + index planes + multiplied-pair planes)
 
 
@@ -308,7 +311,11 @@ def pack_program(
     has_exact_level = any(
         lv.num_graphs > 0 and not lv.prefactor.has_approximate_floatfactors for c in comps for lv in c.compiled_scalar_graphs
     )
+    # rows = max_p + 2 (parameters, all-ones row, all-zeros row); doubled index bytes must stay below 256
+    index_scale = 2 if max_p + 1 <= 127 else 1
     sliced_chunk_words = 11264 if has_exact_level else 12288
+    if os.environ.get("TSIM_B200_SLICED_CHUNK_WORDS"):  # tuning knob: stage size of the ring (multiple of 32 words)
+        sliced_chunk_words = max(1024, int(os.environ["TSIM_B200_SLICED_CHUNK_WORDS"]) & ~31)
     for ci, c in enumerate(comps):
         F = len(c.f_selection)
         n_c = len(c.compiled_scalar_graphs) - 1
@@ -329,7 +336,7 @@ def pack_program(
                 from .pack_sliced import sliced_level_chunks, sliced_level_records
 
                 left = None if sliced_budget_bytes is None else max(0, sliced_budget_bytes // 4 - data_off)
-                graphs, (A, H, C, D), p_lo = sliced_level_records(lv, max_p, max_p + 1, budget_words=left)
+                graphs, (A, H, C, D), p_lo = sliced_level_records(lv, max_p, max_p + 1, budget_words=left, index_scale=index_scale)
                 graph_lists = []
                 for rec, _tbl in graphs:
                     plane_rows = max(plane_rows, 1 + (int(rec[1]) & 0xFF) + 2 * ((int(rec[1]) >> 16) & 0xFF))
@@ -407,6 +414,7 @@ def pack_program(
     header[H_ONE_ROW] = max_p
     header[H_ZERO_ROW] = max_p + 1
     header[H_PLANE_ROWS] = plane_rows
+    header[H_INDEX_SCALE] = index_scale if mode_id == MODE_SLICED else 1
 
     blob = np.zeros(total, dtype=np.uint32)
     blob[:HEADER_WORDS] = header

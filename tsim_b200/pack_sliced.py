@@ -114,9 +114,11 @@ RUN_GENERIC = 15
 PI_CLASSES = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]
 
 
-def _index_words(rows, n_words: int, zero_row: int) -> list[int]:
-    """Row indices four per word (the kernel turns byte k into an address with one dp4a), padded with the zero row."""
-    r = list(rows) + [zero_row] * (4 * n_words - len(rows))
+def _index_words(rows, n_words: int, zero_row: int, scale: int = 1) -> list[int]:
+    """Row indices four per word (the kernel turns byte k into an address with one dp4a), padded with the zero row.
+    Bytes hold ``row * scale`` (``H_INDEX_SCALE``: 2 when the program has at most 127 rows, so that the kernel's 64-bit
+    lanes -- row stride 256 bytes -- are addressed with the same byte selectors)."""
+    r = [v * scale for v in list(rows) + [zero_row] * (4 * n_words - len(rows))]
     return [r[i] | (r[i + 1] << 8) | (r[i + 2] << 16) | (r[i + 3] << 24) for i in range(0, 4 * n_words, 4)]
 
 
@@ -127,16 +129,16 @@ def _row_class(rows) -> int:
     return 3
 
 
-def _block(op: int, params: int, rows: list[int], zero_row: int) -> list[int]:
+def _block(op: int, params: int, rows: list[int], zero_row: int, scale: int = 1) -> list[int]:
     """Generic parity block: ``[op | params << 3, n_words, index words...]`` padded to an even number of words."""
     if params >> 29:
         raise _Unsupported("block parameters do not fit")
     n = max(1, (len(rows) + 3) // 4)
     n += n % 2
-    return [op | (params << 3), n] + _index_words(rows, n, zero_row)
+    return [op | (params << 3), n] + _index_words(rows, n, zero_row, scale)
 
 
-def _emit_runs(terms, zero_row: int) -> list[int]:
+def _emit_runs(terms, zero_row: int, scale: int = 1) -> list[int]:
     """The term stream of a graph as typed runs: ``[kind | count << 16, 0, 0, 0]`` followed by ``count`` items of one
     shape, so that the kernel dispatches once per run and then loops over straight-line code.  The order of a graph's
     terms is irrelevant (their plane updates commute).  Runs and items are 16-byte aligned.
@@ -150,19 +152,19 @@ def _emit_runs(terms, zero_row: int) -> list[int]:
     """
     runs: dict[int, list[int]] = {}
     counts: dict[int, int] = {}
-    zw = zero_row * 0x01010101
+    zw = zero_row * scale * 0x01010101
     for t in terms:
         if t[0] == "lin":
             _, params, rows = t
             cls = _row_class(rows)
             if cls < 3:
                 kind = (RUN_LIN2 if params == 2 else RUN_LIN) + cls
-                iw = _index_words(rows, CLASS_WORDS[cls], zero_row)
+                iw = _index_words(rows, CLASS_WORDS[cls], zero_row, scale)
                 item = [params] + iw + [zw] * (3 - len(iw)) if cls < 2 else [params] + iw + [zw] * 3
                 runs.setdefault(kind, []).extend(item)
                 counts[kind] = counts.get(kind, 0) + 1
                 continue
-            words = _block(OP_LIN, params, rows, zero_row)
+            words = _block(OP_LIN, params, rows, zero_row, scale)
         else:
             _, op, params, r1, r2 = t
             c1, c2 = _row_class(r1), _row_class(r2)
@@ -170,15 +172,15 @@ def _emit_runs(terms, zero_row: int) -> list[int]:
                 if c1 > c2:
                     r1, r2, c1, c2 = r2, r1, c2, c1
                 kind = RUN_PI + PI_CLASSES.index((c1, c2))
-                runs.setdefault(kind, []).extend(_index_words(r1, 4, zero_row) + _index_words(r2, 4, zero_row))
+                runs.setdefault(kind, []).extend(_index_words(r1, 4, zero_row, scale) + _index_words(r2, 4, zero_row, scale))
                 counts[kind] = counts.get(kind, 0) + 1
                 continue
             if op in (OP_PAIRGEN, OP_PAIRMON) and c1 < 3 and c2 < 3:
                 kind = RUN_PAIR + max(c1, c2)
-                runs.setdefault(kind, []).extend([op | (params << 3), 0, 0, 0] + _index_words(r1, 4, zero_row) + _index_words(r2, 4, zero_row))
+                runs.setdefault(kind, []).extend([op | (params << 3), 0, 0, 0] + _index_words(r1, 4, zero_row, scale) + _index_words(r2, 4, zero_row, scale))
                 counts[kind] = counts.get(kind, 0) + 1
                 continue
-            words = _block(OP_FIRST, 0, r1, zero_row) + _block(op, params, r2, zero_row)
+            words = _block(OP_FIRST, 0, r1, zero_row, scale) + _block(op, params, r2, zero_row, scale)
         runs.setdefault(RUN_GENERIC, []).extend(words)
         counts[RUN_GENERIC] = len(runs[RUN_GENERIC])
     body: list[int] = []
@@ -196,13 +198,14 @@ class _Unsupported(ValueError):
     pass
 
 
-def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int, budget_words: int | None = None):
+def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int, budget_words: int | None = None,
+                         index_scale: int = 1):
     """-> (list of per-graph uint32 records, (A, H, C, D), p_lo).  Raises ValueError if a graph does not fit."""
     G = lv.num_graphs
     n, h, p, q, pre = lv.node_phases, lv.halfpi_phases, lv.pi_products, lv.phase_pairs, lv.prefactor
     A, H, C, D = n.phases.shape[1], h.coeffs.shape[1], p.psi_const.shape[1], q.alpha.shape[1]
     approx = bool(pre.has_approximate_floatfactors)
-    if zero_row > 255:
+    if zero_row * index_scale > 255:
         raise _Unsupported("more than 254 parameters per level")
 
     def rows_of(mask, const=0):
@@ -373,7 +376,7 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int, 
             k2 = _zw_mul(k1, SQRT2)
             if max(abs(v) for v in k1 + k2) >= 2**31:
                 raise _Unsupported("graph constants overflow int32")
-            body = _emit_runs(terms + gates, zero_row)
+            body = _emit_runs(terms + gates, zero_row, index_scale)
             if len(body) > 0xFFFF:
                 raise _Unsupported("too many terms")
             trailer = [sum(c << (8 * i) for i, c in enumerate(mul_ctl)), 0, 0, 0] if mul_ctl else []

@@ -133,6 +133,28 @@ int tsb_sample_noisy_host(tsb_program* p, tsb_noise* n, int64_t B, int64_t shot_
                           uint64_t noise_seed, uint64_t noise_call, int skip_shot0, void* out, int out_format,
                           float* norm_dev, uint64_t* f_out);
 
+/* The same pipeline with the result in the caller's column layout -- the flag ladder of CompiledDetectorSampler.sample
+ * (src/tsim/sampler.py:791-868: detector / observable split, prepend / append observables, reference-sample XOR) and
+ * _maybe_bit_pack (:263-276) applied on the device, so that only the bytes the caller asked for cross PCIe.
+ * layout: up to four column ranges [lo, lo + n) concatenated along the bit axis; bit_packed = 1 gives
+ * np.packbits(..., bitorder="little") bytes per row, bit_packed = 0 one bool byte per column.  split > 0 sends the first
+ * `split` ranges to `out` and the rest to a second array `out2` (separate_observables); row sizes: tsb_layout_row_bytes
+ * (which = 0 / 1).  xor_row: uint64[words_out64] XORed into every row first (NULL = none).  ref_mask (NULL = none): shot 0
+ * of the batch is the reference sample (:404-409): (row 0 & ref_mask) is XORed into every row as well, row 0 itself goes
+ * to row0_out (uint64[words_out64]) and is left out of the result, which then has B - 1 rows. */
+typedef struct {
+  int32_t n_segments;
+  int32_t lo[4];
+  int32_t n[4];
+  int32_t bit_packed;
+  int32_t split;
+} tsb_layout;
+int64_t tsb_layout_row_bytes(const tsb_layout* layout, int which);
+int tsb_sample_noisy_host_layout(tsb_program* p, tsb_noise* n, int64_t B, int64_t shot_offset, uint32_t k0, uint32_t k1,
+                                 uint64_t noise_seed, uint64_t noise_call, int skip_shot0, const tsb_layout* layout,
+                                 const uint64_t* xor_row, const uint64_t* ref_mask, uint8_t* out, uint8_t* out2, uint64_t* row0_out,
+                                 float* norm_dev);
+
 /* ---- post-selection session (reference src/tsim/sampler.py:422-545, _sample_batches_with_postselection) ----
  * The host keeps the reference's control flow and key schedule; the data path stays on the GPU.  Per chunk of at most
  * batch_size shots (push_host: packed f rows from the host; push_noise: rows generated by K5): the direct detector bits

@@ -35,6 +35,8 @@ EXPORTS = (
     "tsb_noise_sample_device",
     "tsb_noise_sample_host",
     "tsb_sample_noisy_host",
+    "tsb_sample_noisy_host_layout",
+    "tsb_layout_row_bytes",
     "tsb_program_set_pattern_cache",
     "tsb_program_set_aux",
     "tsb_postselect_create",
@@ -68,6 +70,32 @@ class TsbInfo(C.Structure):
 
     def as_dict(self) -> dict:
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class TsbLayout(C.Structure):
+    """``tsb_layout``: column ranges of the result, concatenated along the bit axis (include/tsim_b200.h)."""
+
+    _fields_ = [
+        ("n_segments", C.c_int32),
+        ("lo", C.c_int32 * 4),
+        ("n", C.c_int32 * 4),
+        ("bit_packed", C.c_int32),
+        ("split", C.c_int32),
+    ]
+
+    @classmethod
+    def make(cls, segments, *, bit_packed: bool, split: int = 0) -> "TsbLayout":
+        segments = [(int(lo), int(n)) for lo, n in segments]
+        if not 0 <= len(segments) <= 4:
+            raise ValueError("a layout has at most four column ranges")
+        out = cls()
+        out.n_segments = len(segments)
+        for i, (lo, n) in enumerate(segments):
+            out.lo[i], out.n[i] = lo, n
+        if not 0 <= int(split) <= len(segments):
+            raise ValueError("split must be a number of leading column ranges")
+        out.bit_packed, out.split = int(bool(bit_packed)), int(split)
+        return out
 
 
 _lib = None
@@ -124,6 +152,10 @@ def load() -> C.CDLL:
     lib.tsb_noise_sample_host.argtypes = [vp, i64, i64, u64, u64, i32, vp]
     lib.tsb_sample_noisy_host.restype = i32
     lib.tsb_sample_noisy_host.argtypes = [vp, vp, i64, i64, u32, u32, u64, u64, i32, vp, i32, vp, vp]
+    lib.tsb_sample_noisy_host_layout.restype = i32
+    lib.tsb_sample_noisy_host_layout.argtypes = [vp, vp, i64, i64, u32, u32, u64, u64, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.tsb_layout_row_bytes.restype = i64
+    lib.tsb_layout_row_bytes.argtypes = [vp, i32]
     lib.tsb_program_set_aux.restype = i32
     lib.tsb_program_set_aux.argtypes = [vp, vp]
     lib.tsb_program_set_pattern_cache.restype = i32

@@ -267,6 +267,68 @@ class DeviceProgram:
         dev = dev[: self.info["n_components"]]
         return (out, dev, f_out) if return_f else (out, dev)
 
+    def layout_row_bytes(self, segments, *, bit_packed: bool, split: int = 0) -> tuple[int, int]:
+        """Bytes per row of the (first, second) result array of a column layout (``tsb_layout_row_bytes``)."""
+        lay = _lib.TsbLayout.make(segments, bit_packed=bit_packed, split=split)
+        n = tuple(int(self._lib.tsb_layout_row_bytes(C.byref(lay), w)) for w in (0, 1))
+        if min(n) < 0:
+            raise ValueError("bad column layout")
+        return n
+
+    def sample_noisy_layout(self, noise, B: int, key, segments, *, bit_packed: bool, split: int = 0,
+                            xor_row: np.ndarray | None = None, ref_mask: np.ndarray | None = None, call: int | None = None,
+                            skip_shot0: bool = False, out: np.ndarray | None = None, out2: np.ndarray | None = None):
+        """``sample_noisy`` with the result already in the caller's column layout (``tsb_sample_noisy_host_layout``):
+        ``segments`` = column ranges ``(lo, n)`` concatenated along the bit axis, as ``np.packbits(bitorder="little")``
+        bytes (``bit_packed``) or one bool byte per column; ``split > 0`` returns the first ``split`` ranges and the rest
+        as two arrays.  ``xor_row`` (``uint64[words_out64]``) is XORed into every row first; with ``ref_mask`` shot 0 is
+        the reference sample: ``row0 & ref_mask`` is XORed in as well and row 0 is returned instead of being part of
+        the result.  -> ``(uint8[rows, row_bytes], uint8[rows, row_bytes2] | None, norm_dev, row0 | None)``."""
+        if self.joint:
+            raise ValueError("a joint-mode program can only be evaluated, not sampled")
+        if noise.num_f != self.num_f:
+            raise ValueError(f"noise sampler produces {noise.num_f} f bits, the program expects {self.num_f}")
+        if call is None:
+            call = noise.next_call()
+        k0, k1 = key_words(key)
+        B = int(B)
+        lay = _lib.TsbLayout.make(segments, bit_packed=bit_packed, split=split)
+        rb = self.layout_row_bytes(segments, bit_packed=bit_packed, split=split)
+        rows = max(0, B - (1 if ref_mask is not None else 0))
+        two = 0 < split < len(segments)
+
+        def result(buf, row_bytes):
+            if buf is None:
+                return _result_pool.take((rows, row_bytes), np.uint8) if rows * row_bytes > 0 else np.empty((rows, row_bytes), np.uint8)
+            if buf.dtype != np.uint8 or buf.ndim != 2 or buf.shape[0] < rows or buf.shape[1] != row_bytes or not buf.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous uint8[>= rows, row_bytes] array")
+            return buf
+
+        out = result(out, rb[0])
+        out2 = result(out2, rb[1]) if two else None
+        wo = self.info["words_out64"]
+
+        def row_arg(a):
+            if a is None:
+                return None, None
+            a = np.ascontiguousarray(np.asarray(a, dtype=np.uint64).reshape(-1))
+            if a.shape[0] != wo:
+                raise ValueError(f"packed output rows have {wo} words")
+            return a, a.ctypes.data_as(C.c_void_p)
+
+        xr, xr_p = row_arg(xor_row)
+        rm, rm_p = row_arg(ref_mask)
+        row0 = np.zeros(wo, dtype=np.uint64) if ref_mask is not None else None
+        dev = np.zeros(max(1, self.info["n_components"]), dtype=np.float32)
+        _lib.check(
+            self._lib.tsb_sample_noisy_host_layout(
+                self._active(), noise._h, B, 0, k0, k1, int(noise.seed), int(call), int(skip_shot0), C.byref(lay), xr_p, rm_p,
+                out.ctypes.data_as(C.c_void_p), out2.ctypes.data_as(C.c_void_p) if out2 is not None else None,
+                row0.ctypes.data_as(C.c_void_p) if row0 is not None else None, dev.ctypes.data_as(C.c_void_p),
+            )
+        )
+        return out[:rows], (out2[:rows] if out2 is not None else None), dev[: self.info["n_components"]], row0
+
     def sample_device(self, d_f: int, B: int, key, d_out: int, *, shot_offset: int = 0, d_norm_dev: int = 0, stream: int = 0) -> None:
         """Launch on device pointers (e.g. ``torch.Tensor.data_ptr()``); asynchronous on ``stream``."""
         k0, k1 = key_words(key)

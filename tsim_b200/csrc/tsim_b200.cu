@@ -278,6 +278,49 @@ __global__ void unpack_rows_kernel(const uint64_t* __restrict__ packed, long lon
   bytes[i] = (uint8_t)((packed[row * words64 + (col >> 6)] >> (col & 63)) & 1ull);
 }
 
+// The layout flags of CompiledDetectorSampler.sample (sampler.py:791-868: detector / observable split, prepend / append,
+// reference-sample XOR, _maybe_bit_pack) applied to packed rows: up to four column ranges concatenated along the bit axis.
+struct LayoutDev {
+  int n_seg;
+  int lo[4], n[4], start[4];  // source column, length and first output bit of each segment
+  int total_bits, row_bytes, bit_packed;
+};
+__device__ __forceinline__ uint32_t layout_bit(const uint64_t* __restrict__ row, const uint64_t* __restrict__ x, const LayoutDev& L, int t) {
+  int col = -1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i < L.n_seg && t >= L.start[i] && t < L.start[i] + L.n[i]) col = L.lo[i] + (t - L.start[i]);
+  if (col < 0) return 0u;  // alignment padding between segments
+  return (uint32_t)(((row[col >> 6] ^ (x ? x[col >> 6] : 0ull)) >> (col & 63)) & 1ull);
+}
+// rows [skip, n_rows) of `packed` -> out rows [0, n_rows - skip); one thread per output byte
+__global__ void layout_rows_kernel(const uint64_t* __restrict__ packed, long long n_rows, int skip, int words64,
+                                   const uint64_t* __restrict__ xor_row, LayoutDev L, uint8_t* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long rows = n_rows - skip;
+  if (i >= rows * L.row_bytes) return;
+  const long long r = i / L.row_bytes;
+  const int j = (int)(i % L.row_bytes);
+  const uint64_t* row = packed + (r + skip) * words64;
+  if (L.bit_packed) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+      if (8 * j + b < L.total_bits) v |= layout_bit(row, xor_row, L, 8 * j + b) << b;
+    out[i] = (uint8_t)v;
+  } else {
+    out[i] = (uint8_t)layout_bit(row, xor_row, L, j);
+  }
+}
+// xor_final = xor_in ^ (row0 & ref_mask): the reference sample is in-batch shot 0 (sampler.py:404-409)
+__global__ void layout_ref_kernel(const uint64_t* __restrict__ row0, const uint64_t* __restrict__ xor_in, const uint64_t* __restrict__ ref_mask,
+                                  int words64, uint64_t* __restrict__ xor_final, uint64_t* __restrict__ row0_copy) {
+  const int w = threadIdx.x;
+  if (w >= words64) return;
+  xor_final[w] = (xor_in ? xor_in[w] : 0ull) ^ (row0[w] & ref_mask[w]);
+  row0_copy[w] = row0[w];
+}
+
 // draw subkeys on the device: K_0 = batch key; (K_{j+1}, sub_j) = split(K_j)   (sampler.py:74,148)
 __global__ void derive_subkeys_kernel(uint32_t k0, uint32_t k1, int n, uint32_t* __restrict__ out) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -638,6 +681,8 @@ struct Slot {
   uint64_t* d_f = nullptr;
   uint64_t* d_out = nullptr;
   uint8_t* d_out_bytes = nullptr;
+  uint8_t* d_layout = nullptr;  // rows in the caller's column layout (tsb_sample_noisy_host_layout)
+  size_t layout_bytes = 0;
   uint32_t* d_subkeys = nullptr;
   uint32_t* d_heavy = nullptr;  // pattern-cache pass 2: count at [0], row indices from [kHeavyRows] (16-byte aligned)
   uint32_t* d_xt = nullptr;     // sliced mode: transposed parameters [total_F][cap/32]
@@ -678,6 +723,8 @@ struct tsb_program {
   cudaStream_t side = nullptr;  // the norm check of shot 0 runs here, overlapped with the rest of the batch
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   uint64_t* d_row0 = nullptr;   // copies of f row 0 and output row 0 for the check
+  uint64_t* d_layout_rows = nullptr;  // [4][words_out64]: xor_in | ref_mask | xor_final | copy of row 0 (tsb_sample_noisy_host_layout)
+  cudaEvent_t ev_ref = nullptr;       // xor_final is ready
   uint32_t* d_xt = nullptr;     // scratch for tsb_sample_device
   uint32_t* d_ot = nullptr;
   long long scratch_slabs = 0;
@@ -939,6 +986,7 @@ static void free_slot(Slot& s) {
   if (s.d_f) cudaFree(s.d_f);
   if (s.d_out) cudaFree(s.d_out);
   if (s.d_out_bytes) cudaFree(s.d_out_bytes);
+  if (s.d_layout) cudaFree(s.d_layout);
   if (s.d_subkeys) cudaFree(s.d_subkeys);
   if (s.d_heavy) cudaFree(s.d_heavy);
   if (s.d_xt) cudaFree(s.d_xt);
@@ -969,6 +1017,8 @@ int tsb_program_destroy(tsb_program* p) {
   if (p->d_xt) cudaFree(p->d_xt);
   if (p->d_ot) cudaFree(p->d_ot);
   if (p->d_row0) cudaFree(p->d_row0);
+  if (p->d_layout_rows) cudaFree(p->d_layout_rows);
+  if (p->ev_ref) cudaEventDestroy(p->ev_ref);
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   if (p->ev_join) cudaEventDestroy(p->ev_join);
   if (p->side) cudaStreamDestroy(p->side);
@@ -1783,16 +1833,19 @@ int tsb_noise_sample_host(tsb_noise* n, int64_t B, int64_t shot_offset, uint64_t
 }
 
 // noise -> sample -> (unpack) -> D2H, all on the device: CompiledDetectorSampler.sample() without host noise
-int tsb_sample_noisy_host(tsb_program* p, tsb_noise* n, int64_t B, int64_t shot_offset, uint32_t k0, uint32_t k1,
-                          uint64_t noise_seed, uint64_t noise_call, int skip_shot0, void* out, int out_format,
-                          float* norm_dev, uint64_t* f_out) {
+// noise -> sample [-> column layout] -> D2H, pipelined over slices; lay == nullptr: whole rows in out_format
+static int sample_noisy_host_impl(tsb_program* p, tsb_noise* n, int64_t B, int64_t shot_offset, uint32_t k0, uint32_t k1,
+                                  uint64_t noise_seed, uint64_t noise_call, int skip_shot0, void* out, int out_format,
+                                  float* norm_dev, uint64_t* f_out, const LayoutDev* lay, const uint64_t* xor_row,
+                                  const uint64_t* ref_mask, uint64_t* row0_out, const LayoutDev* lay2 = nullptr, void* out2 = nullptr) {
   if (!p || !n) return fail(TSB_ERR_INVALID, "null handle");
   if (B < 0 || shot_offset < 0) return fail(TSB_ERR_INVALID, "negative batch size or offset");
-  if (out_format != TSB_OUT_BYTES && out_format != TSB_OUT_PACKED) return fail(TSB_ERR_INVALID, "bad out_format");
+  if (!lay && out_format != TSB_OUT_BYTES && out_format != TSB_OUT_PACKED) return fail(TSB_ERR_INVALID, "bad out_format");
   const tsb_info& in = p->info;
   if (n->device != p->device) return fail(TSB_ERR_INVALID, "noise sampler and program live on different devices");
   if (n->words != in.words_f64) return fail(TSB_ERR_INVALID, "noise sampler row width does not match the program");
   if (B > 0 && !out && in.num_outputs > 0) return fail(TSB_ERR_INVALID, "null host buffer");
+  if (ref_mask && shot_offset != 0) return fail(TSB_ERR_INVALID, "the reference sample is shot 0 of the batch: shot_offset must be 0");
   CU(cudaSetDevice(p->device));
   p->last_ms = 0.f;
   p->last_launches = 0;
@@ -1800,9 +1853,21 @@ int tsb_sample_noisy_host(tsb_program* p, tsb_noise* n, int64_t B, int64_t shot_
     for (int i = 0; i < in.n_components; ++i) norm_dev[i] = 0.f;
   if (B == 0) return TSB_OK;
   CU(cudaMemsetAsync(p->d_norm_dev, 0, sizeof(float) * std::max(1, in.n_components), p->stream));
+  const int wo = in.words_out64;
+  const uint64_t* d_xor = nullptr;
+  if (lay && (xor_row || ref_mask)) {
+    if (!p->d_layout_rows) {
+      CU(cudaMalloc(&p->d_layout_rows, 4 * (size_t)wo * 8));
+      CU(cudaEventCreateWithFlags(&p->ev_ref, cudaEventDisableTiming));
+    }
+    if (xor_row) CU(cudaMemcpyAsync(p->d_layout_rows, xor_row, (size_t)wo * 8, cudaMemcpyHostToDevice, p->stream));
+    if (ref_mask) CU(cudaMemcpyAsync(p->d_layout_rows + wo, ref_mask, (size_t)wo * 8, cudaMemcpyHostToDevice, p->stream));
+    d_xor = ref_mask ? p->d_layout_rows + 2 * wo : p->d_layout_rows;
+  }
   CU(cudaStreamSynchronize(p->stream));
   const long long slice = std::min<long long>(pipeline_slice(p), B);
-  const size_t out_row = out_format == TSB_OUT_BYTES ? (size_t)in.num_outputs : (size_t)in.words_out64 * 8;
+  const size_t out_row = lay ? (size_t)lay->row_bytes : out_format == TSB_OUT_BYTES ? (size_t)in.num_outputs : (size_t)wo * 8;
+  const int skip = ref_mask ? 1 : 0;  // the reference row itself is not part of the result (sampler.py:408)
   const int n_slices = (int)((B + slice - 1) / slice);
   for (int i = 0; i < n_slices; ++i) {
     Slot& s = p->slots[i % kSlots];
@@ -1828,17 +1893,56 @@ int tsb_sample_noisy_host(tsb_program* p, tsb_noise* n, int64_t B, int64_t shot_
     if (rc) return rc;
     CU(cudaEventRecord(s.k_stop, s.stream));
     s.timed = true;
-    p->last_launches += 3 + (out_format == TSB_OUT_BYTES ? 1 : 0);
+    p->last_launches += 3 + ((lay || out_format == TSB_OUT_BYTES) ? 1 : 0);
     if (f_out) CU(cudaMemcpyAsync(f_out + (size_t)lo * in.words_f64, s.d_f, (size_t)cnt * in.words_f64 * 8, cudaMemcpyDeviceToHost, s.stream));
-    uint8_t* dst = (uint8_t*)out + (size_t)lo * out_row;
-    if (out_row > 0) {
-      if (out_format == TSB_OUT_BYTES) {
-        rc = tsb_unpack_out_device(p, s.d_out, cnt, s.d_out_bytes, s.stream);
-        if (rc) return rc;
-        CU(cudaMemcpyAsync(dst, s.d_out_bytes, (size_t)cnt * out_row, cudaMemcpyDeviceToHost, s.stream));
-      } else {
-        CU(cudaMemcpyAsync(dst, s.d_out, (size_t)cnt * out_row, cudaMemcpyDeviceToHost, s.stream));
+    if (out_row == 0 && !(lay2 && lay2->row_bytes)) continue;
+    if (lay) {
+      if (ref_mask) {
+        if (i == 0) {  // shot 0 of the batch is the reference sample
+          layout_ref_kernel<<<1, std::max(32, wo), 0, s.stream>>>(s.d_out, xor_row ? p->d_layout_rows : nullptr, p->d_layout_rows + wo, wo,
+                                                                   p->d_layout_rows + 2 * wo, p->d_layout_rows + 3 * wo);
+          CU(cudaGetLastError());
+          CU(cudaEventRecord(p->ev_ref, s.stream));
+          if (row0_out) CU(cudaMemcpyAsync(row0_out, p->d_layout_rows + 3 * wo, (size_t)wo * 8, cudaMemcpyDeviceToHost, s.stream));
+        } else {
+          CU(cudaStreamWaitEvent(s.stream, p->ev_ref, 0));
+        }
       }
+      const int sk = i == 0 ? skip : 0;
+      const long long rows_out = cnt - sk;
+      if (rows_out > 0) {
+        const size_t row2 = lay2 ? (size_t)lay2->row_bytes : 0;
+        const size_t need = (size_t)slice * (out_row + row2);
+        if (s.layout_bytes < need) {
+          CU(cudaStreamSynchronize(s.stream));
+          if (s.d_layout) cudaFree(s.d_layout);
+          s.d_layout = nullptr; s.layout_bytes = 0;
+          CU(cudaMalloc(&s.d_layout, need));
+          s.layout_bytes = need;
+        }
+        const size_t first_row = (size_t)(lo - (i == 0 ? 0 : skip));
+        const LayoutDev* ls[2] = {lay, lay2};
+        uint8_t* hosts[2] = {(uint8_t*)out, (uint8_t*)out2};
+        uint8_t* d_dst = s.d_layout;
+        for (int a = 0; a < 2; ++a) {  // one or two result arrays (separate_observables)
+          if (!ls[a] || ls[a]->row_bytes == 0) continue;
+          const size_t rb = (size_t)ls[a]->row_bytes;
+          const long long nthreads = rows_out * (long long)rb;
+          layout_rows_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, s.stream>>>(s.d_out, cnt, sk, wo, d_xor, *ls[a], d_dst);
+          CU(cudaGetLastError());
+          CU(cudaMemcpyAsync(hosts[a] + first_row * rb, d_dst, (size_t)rows_out * rb, cudaMemcpyDeviceToHost, s.stream));
+          d_dst += (size_t)slice * rb;
+        }
+      }
+      continue;
+    }
+    uint8_t* dst = (uint8_t*)out + (size_t)lo * out_row;
+    if (out_format == TSB_OUT_BYTES) {
+      rc = tsb_unpack_out_device(p, s.d_out, cnt, s.d_out_bytes, s.stream);
+      if (rc) return rc;
+      CU(cudaMemcpyAsync(dst, s.d_out_bytes, (size_t)cnt * out_row, cudaMemcpyDeviceToHost, s.stream));
+    } else {
+      CU(cudaMemcpyAsync(dst, s.d_out, (size_t)cnt * out_row, cudaMemcpyDeviceToHost, s.stream));
     }
   }
   for (int i = 0; i < kSlots; ++i) {
@@ -1856,6 +1960,59 @@ int tsb_sample_noisy_host(tsb_program* p, tsb_noise* n, int64_t B, int64_t shot_
   if (norm_dev && in.n_components > 0)
     CU(cudaMemcpy(norm_dev, p->d_norm_dev, sizeof(float) * in.n_components, cudaMemcpyDeviceToHost));
   return TSB_OK;
+}
+
+int tsb_sample_noisy_host(tsb_program* p, tsb_noise* n, int64_t B, int64_t shot_offset, uint32_t k0, uint32_t k1,
+                          uint64_t noise_seed, uint64_t noise_call, int skip_shot0, void* out, int out_format,
+                          float* norm_dev, uint64_t* f_out) {
+  return sample_noisy_host_impl(p, n, B, shot_offset, k0, k1, noise_seed, noise_call, skip_shot0, out, out_format, norm_dev, f_out,
+                                nullptr, nullptr, nullptr, nullptr);
+}
+
+// segments [first, last) of a layout as one result array
+static int64_t layout_part_bytes(const tsb_layout* layout, int first, int last) {
+  long long bits = 0;
+  for (int i = first; i < last; ++i) {
+    if (layout->n[i] < 0 || layout->lo[i] < 0) return -1;
+    bits += layout->n[i];
+  }
+  return layout->bit_packed ? (bits + 7) / 8 : bits;
+}
+static bool layout_ok(const tsb_layout* layout) {
+  return layout && layout->n_segments >= 0 && layout->n_segments <= 4 && layout->split >= 0 && layout->split <= layout->n_segments;
+}
+int64_t tsb_layout_row_bytes(const tsb_layout* layout, int which) {
+  if (!layout_ok(layout) || which < 0 || which > 1) return -1;
+  const int cut = layout->split > 0 ? layout->split : layout->n_segments;
+  return which == 0 ? layout_part_bytes(layout, 0, cut) : layout_part_bytes(layout, cut, layout->n_segments);
+}
+
+int tsb_sample_noisy_host_layout(tsb_program* p, tsb_noise* n, int64_t B, int64_t shot_offset, uint32_t k0, uint32_t k1,
+                                 uint64_t noise_seed, uint64_t noise_call, int skip_shot0, const tsb_layout* layout,
+                                 const uint64_t* xor_row, const uint64_t* ref_mask, uint8_t* out, uint8_t* out2, uint64_t* row0_out,
+                                 float* norm_dev) {
+  if (!p || !layout) return fail(TSB_ERR_INVALID, "null argument");
+  if (!layout_ok(layout) || tsb_layout_row_bytes(layout, 0) < 0 || tsb_layout_row_bytes(layout, 1) < 0)
+    return fail(TSB_ERR_INVALID, "bad column layout");
+  const int cut = layout->split > 0 ? layout->split : layout->n_segments;
+  LayoutDev L[2] = {};
+  for (int a = 0; a < 2; ++a) {
+    const int first = a == 0 ? 0 : cut, last = a == 0 ? cut : layout->n_segments;
+    int bits = 0;
+    for (int i = first; i < last; ++i) {
+      if (layout->lo[i] + layout->n[i] > p->info.num_outputs) return fail(TSB_ERR_INVALID, "column range exceeds num_outputs");
+      const int k = L[a].n_seg++;
+      L[a].lo[k] = layout->lo[i]; L[a].n[k] = layout->n[i]; L[a].start[k] = bits;
+      bits += layout->n[i];
+    }
+    L[a].total_bits = bits;
+    L[a].bit_packed = layout->bit_packed ? 1 : 0;
+    L[a].row_bytes = layout->bit_packed ? (bits + 7) / 8 : bits;
+  }
+  const bool two = cut < layout->n_segments;
+  if (two && B > 0 && L[1].row_bytes > 0 && !out2) return fail(TSB_ERR_INVALID, "null host buffer for the second array");
+  return sample_noisy_host_impl(p, n, B, shot_offset, k0, k1, noise_seed, noise_call, skip_shot0, out, TSB_OUT_PACKED, norm_dev, nullptr,
+                                &L[0], xor_row, ref_mask, row0_out, two ? &L[1] : nullptr, out2);
 }
 
 // =============================================================================================

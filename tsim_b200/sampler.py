@@ -553,6 +553,19 @@ class CompiledMeasurementSampler(_CompiledSamplerBase):
         return self._sample_batches(shots, batch_size)
 
 
+def _layout_segments(nd: int, n_out: int, *, prepend: bool, append: bool, separate: bool):
+    """Column ranges of ``CompiledDetectorSampler.sample``'s result (sampler.py:852-868) over the combined columns
+    ``[detectors | observables]``."""
+    det, obs = (0, nd), (nd, n_out - nd)
+    if prepend and append:
+        return [obs, det, obs]
+    if append or separate:
+        return [det, obs]
+    if prepend:
+        return [obs, det]
+    return [det]
+
+
 def _packed_columns(rows: np.ndarray, lo: int, hi: int) -> np.ndarray:
     """Columns ``[lo, hi)`` of packed ``uint64[B, W]`` rows as ``np.packbits(..., bitorder="little")`` bytes.
 
@@ -614,6 +627,9 @@ def _maybe_bit_pack(array: np.ndarray, *, bit_packed: bool) -> np.ndarray:
 class CompiledDetectorSampler(_CompiledSamplerBase):
     """Reference ``CompiledDetectorSampler`` (sampler.py:672-868)."""
 
+    #: with a device channel sampler the layout flags are applied on the GPU (False: host NumPy, same bits)
+    DEVICE_LAYOUT = True
+
     def sample(
         self,
         shots: int,
@@ -641,6 +657,14 @@ class CompiledDetectorSampler(_CompiledSamplerBase):
             if not (mask & self._direct_detector_mask).any() or not self._program.components:
                 postselection_mask = None
 
+        if (self.DEVICE_LAYOUT and postselection_mask is None and shots > 0 and isinstance(self._channel_sampler, DeviceChannelSampler)
+                and isinstance(self._device_program, DeviceProgram) and (batch_size is None or batch_size >= 1)):
+            # noise, sampling, column selection, reference XOR and bit packing all on the GPU: only the bytes of the
+            # returned arrays cross PCIe (tsb_sample_noisy_host_layout)
+            return self._sample_layout_device(
+                shots, batch_size, prepend=prepend_observables, append=append_observables, separate=separate_observables,
+                bit_packed=bit_packed, ref_det=use_detector_reference_sample, ref_obs=use_observable_reference_sample,
+            )
         if postselection_mask is not None:
             if compute_reference:
                 samples, reference, direct_discarded = self._sample_batches_with_postselection(
@@ -695,6 +719,59 @@ class CompiledDetectorSampler(_CompiledSamplerBase):
         if separate_observables:
             return _maybe_bit_pack(det_samples, bit_packed=bit_packed), _maybe_bit_pack(obs_samples, bit_packed=bit_packed)
         return _maybe_bit_pack(det_samples, bit_packed=bit_packed)
+
+
+    def _sample_layout_device(self, shots: int, batch_size: int | None, *, prepend: bool, append: bool, separate: bool,
+                              bit_packed: bool, ref_det: bool, ref_obs: bool):
+        """The batch loop of ``_sample_batches`` (sampler.py:340-420) with the layout flags applied on the device."""
+        nd, n_out = self._num_detectors, self._program.num_outputs
+        compute_reference = ref_det or ref_obs
+        if batch_size is None:
+            max_batch_size = self._estimate_batch_size()
+            num_batches = max(1, ceil(shots / max_batch_size))
+            batch_size = ceil(shots / num_batches)
+        else:
+            num_batches = ceil(shots / batch_size)
+        if compute_reference and batch_size * num_batches == shots:
+            batch_size += 1
+        segments = _layout_segments(nd, n_out, prepend=prepend, append=append, separate=separate)
+        split = 1 if separate else 0  # separate_observables: detectors and observables as two arrays
+        dp = self._device_program
+        ref_mask = None
+        if compute_reference:
+            m = np.zeros(n_out, dtype=np.bool_)
+            m[:nd] = ref_det
+            m[nd:] = ref_obs
+            ref_mask = pack_bool_rows(m[None, :])[0]
+        from .backend import _result_pool
+
+        total = num_batches * batch_size - (1 if compute_reference else 0)
+
+        def take(row_bytes):
+            return _result_pool.take((total, row_bytes), np.uint8) if total * row_bytes > 0 else np.empty((total, row_bytes), np.uint8)
+
+        rb = dp.layout_row_bytes(segments, bit_packed=bit_packed, split=split)
+        out, out2 = take(rb[0]), (take(rb[1]) if separate else None)
+        pos, xor_row = 0, None
+        for b in range(num_batches):
+            first_ref = compute_reference and b == 0
+            part, _, devs, row0 = dp.sample_noisy_layout(
+                self._channel_sampler, batch_size, self._next_subkey(), segments, bit_packed=bit_packed, split=split,
+                xor_row=xor_row, skip_shot0=first_ref, ref_mask=ref_mask if first_ref else None, out=out[pos:],
+                out2=out2[pos:] if out2 is not None else None,
+            )
+            pos += part.shape[0]
+            check_norm_deviations(devs)
+            if first_ref:
+                xor_row = row0 & ref_mask
+
+        def finish(a):
+            a = a[:shots]
+            return a if bit_packed else a.view(np.bool_)
+
+        if separate:
+            return finish(out), finish(out2)
+        return finish(out)
 
 
 class CompiledStateProbs(_CompiledSamplerBase):

@@ -124,6 +124,26 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
             while o < end:
                 kind, count = int(data[o]) & 0xFFFF, int(data[o]) >> 16
                 o += 4
+                if kind in (16, 17):  # LIN_1 / LIN2_1: [params, index word]
+                    for _i in range(count):
+                        prm = int(data[o])
+                        if kind == 17:
+                            assert prm in (0, 2)  # 0: the alignment filler over the all-zeros row
+                            prm = 2
+                        lin_op(prm, par_words(o + 1, 1))
+                        o += 2
+                    continue
+                if 18 <= kind < 21:  # PI_1 + k: [index word, 3 index words]
+                    for _i in range(count):
+                        A[2] ^= par_words(o, 1) & par_words(o + 1, kind - 17)
+                        o += 4
+                    continue
+                if kind == 21:  # PAIR_1: [op | params << 3, index word, index word, 0]
+                    for _i in range(count):
+                        hdr = int(data[o])
+                        pair_op(hdr & 7, hdr >> 3, par_words(o + 1, 1), par_words(o + 2, 1))
+                        o += 4
+                    continue
                 if kind < 3 or 9 <= kind < 12:  # LIN / LIN2 runs
                     cls = kind % 3
                     nw = CLASS_WORDS[cls]

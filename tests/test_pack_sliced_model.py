@@ -39,10 +39,11 @@ def test_monoid_exponents_of_all_pair_factors():
 
 
 @pytest.mark.parametrize("approx", [False, True])
+@pytest.mark.parametrize("density", [0.3, 0.06])  # 0.06: mostly one-word parities (the compact LIN_1 / PI_1 / PAIR_1 items)
 @pytest.mark.parametrize("P,seed", [(5, 0), (31, 1), (40, 2), (70, 3)])
-def test_sliced_records_reproduce_oracle(P, seed, approx):
+def test_sliced_records_reproduce_oracle(P, seed, approx, density):
     rng = np.random.default_rng(seed)
-    lv = random_level(rng, G=6, P=P, A=5, H=4, C=5, D=4, approx=approx, density=0.3)
+    lv = random_level(rng, G=6, P=P, A=5, H=4, C=5, D=4, approx=approx, density=density)
     lv.prefactor.floatfactor[:] = rng.integers(-3, 4, size=(6, 4))
     lv.prefactor.floatfactor[0] = [1, 0, 0, 0]
     prog = _one_level_program(lv, P)

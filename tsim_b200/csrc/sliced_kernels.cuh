@@ -242,7 +242,12 @@ __device__ __forceinline__ LW par_words(uint32_t xs, const uint32_t* w, const ui
 // N words (multiple of 4) from a 16-byte aligned, warp-uniform address
 template <int N>
 __device__ __forceinline__ void ld_words(const uint32_t* __restrict__ b, uint32_t (&w)[N]) {
-  static_assert(N % 4 == 0, "items are 16-byte multiples");
+  static_assert(N % 4 == 0 || N == 2, "items are 16-byte multiples, or 8 bytes");
+  if constexpr (N == 2) {
+    const uint2 v = *reinterpret_cast<const uint2*>(b);
+    w[0] = v.x; w[1] = v.y;
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < N; i += 4) {
     const uint4 v = *reinterpret_cast<const uint4*>(b + i);
@@ -251,7 +256,11 @@ __device__ __forceinline__ void ld_words(const uint32_t* __restrict__ b, uint32_
 }
 
 enum SlicedOp { OP_FIRST = 0, OP_LIN = 1, OP_PI = 2, OP_PAIRGEN = 3, OP_PAIRMON = 4 };
-enum SlicedRun { RUN_LIN = 0, RUN_PI = 3, RUN_LIN2 = 9, RUN_PAIR = 12, RUN_GENERIC = 15 };
+enum SlicedRun {
+  RUN_LIN = 0, RUN_PI = 3, RUN_LIN2 = 9, RUN_PAIR = 12, RUN_GENERIC = 15,
+  // one-word parities (<= 4 rows) in compact items (pack_sliced.py::_emit_runs)
+  RUN_LIN_1 = 16, RUN_LIN2_1 = 17, RUN_PI_1 = 18, RUN_PAIR_1 = 21
+};
 
 template <class LW>
 struct Planes {
@@ -322,12 +331,14 @@ __device__ __forceinline__ void pair_op(Planes<LW>& P, uint32_t op, uint32_t prm
     plw[(r0 + 1u) * 32u] = p;
     return;
   }
-  const LW wd[3] = {q, p, q & p};
-#pragma unroll
+  // rare items (a few per graph): rolled loops keep the code small (the kernel is ~100 KB of SASS, instruction fetch counts)
+#pragma unroll 1
   for (int v = 0; v < 3; ++v) {
-    add_a3(P.A0, P.A1, P.A2, (prm >> (6 * v)) & 7u, wd[v]);
+    const LW wv = v == 0 ? q : v == 1 ? p : (q & p);
+    add_a3(P.A0, P.A1, P.A2, (prm >> (6 * v)) & 7u, wv);
     const int db = (int)((prm >> (6 * v + 3)) & 7u) - 3;
-    const LW w = db > 0 ? wd[v] : ~wd[v];
+    const LW w = db > 0 ? wv : ~wv;
+#pragma unroll 1
     for (int r = 0; r < (db < 0 ? -db : db); ++r) add_cnt5(P.Bp, w);
   }
   const uint32_t ztt = (prm >> 18) & 15u;
@@ -354,6 +365,32 @@ __device__ __forceinline__ const uint32_t* pair_run(const uint32_t* __restrict__
                                                      uint32_t nb, LW* __restrict__ plw) {
   return run_items<12, false>(b, count, [&](const uint32_t(&w)[12]) {
     const LW q = par_words<LW, NW>(xs, w + 4, sel), p = par_words<LW, NW>(xs, w + 8, sel);
+    pair_op(P, w[0] & 7u, w[0] >> 3, q, p, nb, plw);
+  });
+}
+
+// compact items of one-word parities (<= 4 rows)
+template <class LW>
+__device__ __forceinline__ const uint32_t* lin1_run(const uint32_t* __restrict__ b, uint32_t count, uint32_t xs, const uint4& sel, Planes<LW>& P) {
+  return run_items<2, false>(b, count, [&](const uint32_t(&w)[2]) { lin_op(P, w[0], par4<LW>(xs, w[1], sel)); });
+}
+template <class LW>
+__device__ __forceinline__ const uint32_t* lin2_1_run(const uint32_t* __restrict__ b, uint32_t count, uint32_t xs, const uint4& sel, Planes<LW>& P) {
+  return run_items<2, false>(b, count, [&](const uint32_t(&w)[2]) {
+    const LW p = par4<LW>(xs, w[1], sel);
+    P.A2 ^= P.A1 & p;
+    P.A1 ^= p;
+  });
+}
+template <class LW, int N2>
+__device__ __forceinline__ const uint32_t* pi1_run(const uint32_t* __restrict__ b, uint32_t count, uint32_t xs, const uint4& sel, Planes<LW>& P) {
+  return run_items<4, false>(b, count, [&](const uint32_t(&w)[4]) { P.A2 ^= par4<LW>(xs, w[0], sel) & par_words<LW, N2>(xs, w + 1, sel); });
+}
+template <class LW>
+__device__ __forceinline__ const uint32_t* pair1_run(const uint32_t* __restrict__ b, uint32_t count, uint32_t xs, const uint4& sel, Planes<LW>& P,
+                                                      uint32_t nb, LW* __restrict__ plw) {
+  return run_items<4, false>(b, count, [&](const uint32_t(&w)[4]) {
+    const LW q = par4<LW>(xs, w[1], sel), p = par4<LW>(xs, w[2], sel);
     pair_op(P, w[0] & 7u, w[0] >> 3, q, p, nb, plw);
   });
 }
@@ -422,6 +459,12 @@ __device__ __forceinline__ void sliced_phase1(const uint32_t* __restrict__ cbase
       case RUN_PAIR + 0: b = pair_run<LW, 2>(b, count, xs, sel, P, nb, plw); break;
       case RUN_PAIR + 1: b = pair_run<LW, 3>(b, count, xs, sel, P, nb, plw); break;
       case RUN_PAIR + 2: b = pair_run<LW, 4>(b, count, xs, sel, P, nb, plw); break;
+      case RUN_LIN_1: b = lin1_run<LW>(b, count, xs, sel, P); break;
+      case RUN_LIN2_1: b = lin2_1_run<LW>(b, count, xs, sel, P); break;
+      case RUN_PI_1 + 0: b = pi1_run<LW, 1>(b, count, xs, sel, P); break;
+      case RUN_PI_1 + 1: b = pi1_run<LW, 2>(b, count, xs, sel, P); break;
+      case RUN_PI_1 + 2: b = pi1_run<LW, 3>(b, count, xs, sel, P); break;
+      case RUN_PAIR_1: b = pair1_run<LW>(b, count, xs, sel, P, nb, plw); break;
       default: b = generic_run<LW>(b, count, xs, sel, P, nb, plw); break;
     }
   }
@@ -626,19 +669,20 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
   }
   __syncthreads();
 
-  const long long total_q = (long long)rounds * n_chunks;
-  auto issue = [&](long long q) {
-    const int ch = (int)(q % n_chunks);
+  // chunk fills are numbered q = 0 .. rounds * n_chunks - 1 (fits 32 bits: the host plans at most 2^20 rounds)
+  const uint32_t total_q = (uint32_t)rounds * (uint32_t)n_chunks;
+  auto issue = [&](uint32_t q) {
+    const uint32_t ch = q % (uint32_t)n_chunks;
     const uint32_t* row = chunk_tab + ch * kChunkWords;
-    const int stage = (int)(q % prm.n_stages);
+    const uint32_t stage = q % (uint32_t)prm.n_stages;
     const uint32_t bytes = row[K_WORDS] * 4u;
     mbar_expect_tx(&bars[stage], bytes);
     tma_bulk_g2s(sdata + (size_t)stage * prm.stage_words, gdata + row[K_OFF], bytes, &bars[stage]);
   };
   if (tid == 0)
-    for (long long q = 0; q < prm.n_stages && q < total_q; ++q) issue(q);
+    for (uint32_t q = 0; q < (uint32_t)prm.n_stages && q < total_q; ++q) issue(q);
 
-  long long q = 0;
+  uint32_t q = 0, q_stage = 0, q_phase = 0;  // q_stage = q % n_stages, q_phase = (q / n_stages) & 1, kept incrementally
   uint32_t pbuf = 0;  // plane buffer of the current wave (double-buffered: one group barrier per wave)
   for (int round = 0; round < rounds; ++round) {
     // units of this group in this round, the lane's slabs and its column of the group's matrix.  Lanes 16..31 of a
@@ -711,8 +755,8 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
         const int first_chunk = (int)lvl[L_FIRST_CHUNK], nck = (int)lvl[L_N_CHUNKS];
         for (int c = 0; c < nck; ++c) {
           const uint32_t* row = chunk_tab + (first_chunk + c) * kChunkWords;
-          const int stage = (int)(q % prm.n_stages);
-          mbar_wait(&bars[stage], (uint32_t)((q / prm.n_stages) & 1));
+          const uint32_t stage = q_stage;
+          mbar_wait(&bars[stage], q_phase);
           const uint32_t* __restrict__ cbase = sdata + (size_t)stage * prm.stage_words;
           const int n_g = (int)row[K_GRAPHS];
           if (gactive) {
@@ -738,6 +782,10 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
             }
           }
           ++q;
+          if (++q_stage == (uint32_t)prm.n_stages) {
+            q_stage = 0;
+            q_phase ^= 1u;
+          }
         }
         // finish the level for this warp's shots: |amp|, draw, chain rule
         if (gactive) {

@@ -314,8 +314,22 @@ def pack_program(
     # rows = max_p + 2 (parameters, all-ones row, all-zeros row); doubled index bytes must stay below 256
     index_scale = 2 if max_p + 1 <= 127 else 1
     sliced_chunk_words = 11264 if has_exact_level else 12288
+    if not has_exact_level:
+        # All-approximate programs run seven groups of four warps per SM (sliced_kernels.cuh): the stage must leave room for
+        # their matrices and plane buffers next to a two-stage ring in the 227 KB of an SM, or the launch plan falls back to
+        # fewer groups in several rounds (measured: 0.68 -> 0.85 ms on a variant of cfg2 whose largest chunk was 1 KB bigger).
+        room = 232448 - 256 - 7 * ((max_p + 2) * 32 + 2 * 4 * 12 * 32) * 4
+        if room // 8 >= 8192:
+            sliced_chunk_words = min(sliced_chunk_words, (room // 8) & ~31)
     if os.environ.get("TSIM_B200_SLICED_CHUNK_WORDS"):  # tuning knob: stage size of the ring (multiple of 32 words)
         sliced_chunk_words = max(1024, int(os.environ["TSIM_B200_SLICED_CHUNK_WORDS"]) & ~31)
+    sliced_compact = False
+    if mode_id == MODE_SLICED:
+        from .pack_sliced import compact_items_pay
+
+        sliced_compact = compact_items_pay([lv for c in comps for lv in c.compiled_scalar_graphs])
+        if os.environ.get("TSIM_B200_SLICED_COMPACT"):  # tuning knob
+            sliced_compact = os.environ["TSIM_B200_SLICED_COMPACT"] != "0"
     for ci, c in enumerate(comps):
         F = len(c.f_selection)
         n_c = len(c.compiled_scalar_graphs) - 1
@@ -336,7 +350,8 @@ def pack_program(
                 from .pack_sliced import sliced_level_chunks, sliced_level_records
 
                 left = None if sliced_budget_bytes is None else max(0, sliced_budget_bytes // 4 - data_off)
-                graphs, (A, H, C, D), p_lo = sliced_level_records(lv, max_p, max_p + 1, budget_words=left, index_scale=index_scale)
+                graphs, (A, H, C, D), p_lo = sliced_level_records(lv, max_p, max_p + 1, budget_words=left, index_scale=index_scale,
+                                                                  compact=sliced_compact)
                 graph_lists = []
                 for rec, _tbl in graphs:
                     plane_rows = max(plane_rows, 1 + (int(rec[1]) & 0xFF) + 2 * ((int(rec[1]) >> 16) & 0xFF))

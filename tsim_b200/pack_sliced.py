@@ -45,6 +45,7 @@ Row indices (8 bits, four per word): parameter i -> row i; ``zero_row`` is all z
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 
@@ -112,6 +113,11 @@ RUN_LIN2 = 9  # + class: linear terms that only add 2 to ``a`` (the half-pi fami
 RUN_PAIR = 12  # + max(class1, class2): PAIRGEN / PAIRMON items
 RUN_GENERIC = 15
 PI_CLASSES = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]
+# one-word parities (<= 4 rows: sparse masks, the common case of structured programs) get compact items
+RUN_LIN_1 = 16  # item = [params, index word]
+RUN_LIN2_1 = 17  # item = [2, index word]
+RUN_PI_1 = 18  # + (words of the heavier parity - 1), 0..2: item = [index word of the lighter parity, 3 index words of the heavier]
+RUN_PAIR_1 = 21  # item = [op | params << 3, index word, index word, 0]
 
 
 def _index_words(rows, n_words: int, zero_row: int, scale: int = 1) -> list[int]:
@@ -138,11 +144,13 @@ def _block(op: int, params: int, rows: list[int], zero_row: int, scale: int = 1)
     return [op | (params << 3), n] + _index_words(rows, n, zero_row, scale)
 
 
-def _emit_runs(terms, zero_row: int, scale: int = 1) -> list[int]:
+def _emit_runs(terms, zero_row: int, scale: int = 1, rotate: int = 0, compact: bool = True) -> list[int]:
     """The term stream of a graph as typed runs: ``[kind | count << 16, 0, 0, 0]`` followed by ``count`` items of one
     shape, so that the kernel dispatches once per run and then loops over straight-line code.  The order of a graph's
     terms is irrelevant (their plane updates commute).  Runs and items are 16-byte aligned.
 
+        LIN_1 / LIN2_1   item = [params, index word] (<= 4 rows); PI_1 + k: item = [index word, 3 index words] (lighter parity
+                         <= 4 rows, heavier <= 4 (k + 1)); PAIR_1: item = [op | params << 3, index word, index word, 0]
         LIN + cls        item = [params, index words...]: 4 words for classes 0 / 1 (<= 8 / 12 rows), 8 for class 2 (<= 16)
         LIN2 + cls       the same for params == 2 (a += 2 p and nothing else): the kernel skips the generic update
         PAIR + cls       item = [op | params << 3, 0, 0, 0, 4 index words of the first parity, 4 of the second];
@@ -153,38 +161,62 @@ def _emit_runs(terms, zero_row: int, scale: int = 1) -> list[int]:
     runs: dict[int, list[int]] = {}
     counts: dict[int, int] = {}
     zw = zero_row * scale * 0x01010101
+
+    def add(kind, item):
+        runs.setdefault(kind, []).extend(item)
+        counts[kind] = counts.get(kind, 0) + 1
+
+    def words_of(rows):
+        return max(1, (len(rows) + 3) // 4)
+
     for t in terms:
         if t[0] == "lin":
             _, params, rows = t
             cls = _row_class(rows)
+            if compact and words_of(rows) == 1:
+                add(RUN_LIN2_1 if params == 2 else RUN_LIN_1, [params] + _index_words(rows, 1, zero_row, scale))
+                continue
             if cls < 3:
                 kind = (RUN_LIN2 if params == 2 else RUN_LIN) + cls
                 iw = _index_words(rows, CLASS_WORDS[cls], zero_row, scale)
-                item = [params] + iw + [zw] * (3 - len(iw)) if cls < 2 else [params] + iw + [zw] * 3
-                runs.setdefault(kind, []).extend(item)
-                counts[kind] = counts.get(kind, 0) + 1
+                add(kind, [params] + iw + [zw] * (3 - len(iw)) if cls < 2 else [params] + iw + [zw] * 3)
                 continue
             words = _block(OP_LIN, params, rows, zero_row, scale)
         else:
             _, op, params, r1, r2 = t
             c1, c2 = _row_class(r1), _row_class(r2)
             if op == OP_PI and c1 < 3 and c2 < 3:
+                if len(r1) > len(r2):
+                    r1, r2, c1, c2 = r2, r1, c2, c1
+                if compact and words_of(r1) == 1 and words_of(r2) <= 3:
+                    add(RUN_PI_1 + words_of(r2) - 1, _index_words(r1, 1, zero_row, scale) + _index_words(r2, 3, zero_row, scale))
+                    continue
                 if c1 > c2:
                     r1, r2, c1, c2 = r2, r1, c2, c1
-                kind = RUN_PI + PI_CLASSES.index((c1, c2))
-                runs.setdefault(kind, []).extend(_index_words(r1, 4, zero_row, scale) + _index_words(r2, 4, zero_row, scale))
-                counts[kind] = counts.get(kind, 0) + 1
+                add(RUN_PI + PI_CLASSES.index((c1, c2)), _index_words(r1, 4, zero_row, scale) + _index_words(r2, 4, zero_row, scale))
                 continue
             if op in (OP_PAIRGEN, OP_PAIRMON) and c1 < 3 and c2 < 3:
-                kind = RUN_PAIR + max(c1, c2)
-                runs.setdefault(kind, []).extend([op | (params << 3), 0, 0, 0] + _index_words(r1, 4, zero_row, scale) + _index_words(r2, 4, zero_row, scale))
-                counts[kind] = counts.get(kind, 0) + 1
+                if compact and words_of(r1) == 1 and words_of(r2) == 1:
+                    add(RUN_PAIR_1, [op | (params << 3)] + _index_words(r1, 1, zero_row, scale) + _index_words(r2, 1, zero_row, scale) + [0])
+                    continue
+                add(RUN_PAIR + max(c1, c2), [op | (params << 3), 0, 0, 0] + _index_words(r1, 4, zero_row, scale) + _index_words(r2, 4, zero_row, scale))
                 continue
             words = _block(OP_FIRST, 0, r1, zero_row, scale) + _block(op, params, r2, zero_row, scale)
         runs.setdefault(RUN_GENERIC, []).extend(words)
         counts[RUN_GENERIC] = len(runs[RUN_GENERIC])
+    for kind in (RUN_LIN_1, RUN_LIN2_1):  # two-word items: keep the next run header 16-byte aligned
+        if kind in runs and len(runs[kind]) % 4:
+            runs[kind] += [0, zw]  # a no-op item: params 0 (nothing to update) over the all-zeros row
+            counts[kind] += 1
     body: list[int] = []
-    for kind in sorted(runs):
+    # The order of the runs is free.  Graphs of a level often have the same mix of runs (always, when they share their
+    # masks); starting every graph at a different run keeps the warps of a wave -- and the groups of a CTA, which walk
+    # the same chunk -- out of step, so that their bursts of row loads do not all hit the LSU at the same time.
+    order = sorted(runs)
+    if order and os.environ.get("TSIM_B200_SLICED_ROTATE", "1") != "0":
+        k = rotate % len(order)
+        order = order[k:] + order[:k]
+    for kind in order:
         if counts[kind] > 0xFFFF:
             raise _Unsupported("too many terms")
         if kind == RUN_GENERIC:
@@ -198,8 +230,22 @@ class _Unsupported(ValueError):
     pass
 
 
+def compact_items_pay(levels) -> bool:
+    """Whether the one-word item types (<= 4 rows per parity) are worth their extra runs: they are when at least a fifth
+    of a program's parities have at most four rows.  Measured on variants of cfg2 (tools/structure_sweep.py): mask density
+    0.05 (73 % of the parities) 0.58 -> 0.51 ms, density 0.15 (10 %) 0.66 -> 0.68 ms."""
+    small = total = 0
+    for lv in levels:
+        for m in (lv.node_phases.params, lv.halfpi_phases.params, lv.pi_products.psi_params, lv.pi_products.phi_params,
+                  lv.phase_pairs.alpha_params, lv.phase_pairs.beta_params):
+            w = np.asarray(m).reshape(-1, m.shape[-1]).sum(axis=1) if m.size else np.zeros(0)
+            total += int(np.count_nonzero(w))
+            small += int(np.count_nonzero((w > 0) & (w <= 4)))
+    return total > 0 and small * 5 >= total
+
+
 def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int, budget_words: int | None = None,
-                         index_scale: int = 1):
+                         index_scale: int = 1, compact: bool = True):
     """-> (list of per-graph uint32 records, (A, H, C, D), p_lo).  Raises ValueError if a graph does not fit."""
     G = lv.num_graphs
     n, h, p, q, pre = lv.node_phases, lv.halfpi_phases, lv.pi_products, lv.phase_pairs, lv.prefactor
@@ -376,7 +422,7 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int, 
             k2 = _zw_mul(k1, SQRT2)
             if max(abs(v) for v in k1 + k2) >= 2**31:
                 raise _Unsupported("graph constants overflow int32")
-            body = _emit_runs(terms + gates, zero_row, index_scale)
+            body = _emit_runs(terms + gates, zero_row, index_scale, rotate=len(recs), compact=compact)
             if len(body) > 0xFFFF:
                 raise _Unsupported("too many terms")
             trailer = [sum(c << (8 * i) for i, c in enumerate(mul_ctl)), 0, 0, 0] if mul_ctl else []

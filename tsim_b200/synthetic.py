@@ -55,8 +55,19 @@ def _masks(rng, G, T, P, density):
 
 
 def random_level(rng, G: int, P: int, A: int, H: int, C: int, D: int, *, approx: bool, density: float = 0.15,
-                 power2_range=(-4, 0)) -> CompiledScalarGraphs:
-    """One level with i.i.d. contents ("Synthetic inputs")."""
+                 power2_range=(-4, 0), shared_masks: bool = False) -> CompiledScalarGraphs:
+    """One level with i.i.d. contents ("Synthetic inputs").  ``shared_masks``: every graph of the
+    level uses the parameter masks of graph 0 (phases, constants and prefactors stay per graph) -- the shape a stabiliser
+    decomposition of ONE ZX diagram produces, where the terms of a level differ in their phases, not in their wiring."""
+    if shared_masks:
+        draw = _masks
+
+        def _shared(rng_, G_, T, P_, dens):
+            return np.repeat(draw(rng_, 1, T, P_, dens), G_, axis=0)
+
+        masks = _shared
+    else:
+        masks = _masks
 
     def counts(T):
         return rng.integers((T + 1) // 2, T + 1, size=G) if T else np.zeros(G, np.int64)
@@ -68,10 +79,10 @@ def random_level(rng, G: int, P: int, A: int, H: int, C: int, D: int, *, approx:
     return make_scalar_graphs(
         P,
         num_graphs=G,
-        node=(rng.integers(0, 8, (G, A)), _masks(rng, G, A, P, density), counts(A)),
-        halfpi=(rng.choice([2, 4, 6], size=(G, H)), _masks(rng, G, H, P, density)),
-        pi=(rng.integers(0, 2, (G, C)), _masks(rng, G, C, P, density), rng.integers(0, 2, (G, C)), _masks(rng, G, C, P, density)),
-        pairs=(rng.integers(0, 8, (G, D)), _masks(rng, G, D, P, density), rng.integers(0, 8, (G, D)), _masks(rng, G, D, P, density), counts(D)),
+        node=(rng.integers(0, 8, (G, A)), masks(rng, G, A, P, density), counts(A)),
+        halfpi=(rng.choice([2, 4, 6], size=(G, H)), masks(rng, G, H, P, density)),
+        pi=(rng.integers(0, 2, (G, C)), masks(rng, G, C, P, density), rng.integers(0, 2, (G, C)), masks(rng, G, C, P, density)),
+        pairs=(rng.integers(0, 8, (G, D)), masks(rng, G, D, P, density), rng.integers(0, 8, (G, D)), masks(rng, G, D, P, density), counts(D)),
         phase_indices=rng.integers(0, 8, G),
         floatfactor=np.tile(np.array([1, 0, 0, 0]), (G, 1)),
         power2=rng.integers(power2_range[0], power2_range[1] + 1, G),
@@ -123,15 +134,20 @@ def _rescale_levels(levels: list[CompiledScalarGraphs], F: int) -> None:
         prev = mag * 2.0**shift
 
 
-def synthetic_component(rng, n_c: int, F: int, graphs, f_pool, first_output: int, *, A, H, C, D, approx, density=0.15):
-    levels = [random_level(rng, graphs[k], F + k, A, H, C, D, approx=approx, density=density) for k in range(n_c + 1)]
+def synthetic_component(rng, n_c: int, F: int, graphs, f_pool, first_output: int, *, A, H, C, D, approx, density=0.15,
+                        shared_masks: bool = False):
+    levels = [random_level(rng, graphs[k], F + k, A, H, C, D, approx=approx, density=density, shared_masks=shared_masks)
+              for k in range(n_c + 1)]
     _rescale_levels(levels, F)
     f_selection = np.sort(rng.choice(f_pool, size=F, replace=False)).astype(np.int32)
     return CompiledComponent(tuple(range(first_output, first_output + n_c)), f_selection, tuple(levels))
 
 
-def synthetic_program(name: str, seed: int = 20260101) -> CompiledProgram:
-    """Program with the shapes of benchmark configuration ``name`` (see ``CONFIGS``)."""
+def synthetic_program(name: str, seed: int = 20260101, *, density: float = 0.15, shared_masks: bool = False,
+                      graph_scale: int = 1) -> CompiledProgram:
+    """Program with the shapes of benchmark configuration ``name`` (see ``CONFIGS``).  The keyword arguments vary the
+    structure for sensitivity sweeps (tools/structure_sweep.py): mask density, masks shared by the graphs of a level,
+    ``graph_scale`` times as many graphs per level; the defaults are the benchmark programs."""
     cfg = CONFIGS[name]
     rng = np.random.default_rng(seed)
     num_f = cfg["num_f"]
@@ -143,7 +159,8 @@ def synthetic_program(name: str, seed: int = 20260101) -> CompiledProgram:
     for n_c, F, graphs in cfg["comps"]:
         comps.append(
             synthetic_component(
-                rng, n_c, F, graphs, np.arange(num_f), out, A=cfg["A"], H=cfg["H"], C=cfg["C"], D=cfg["D"], approx=cfg["approx"]
+                rng, n_c, F, tuple(int(g) * graph_scale for g in graphs), np.arange(num_f), out, A=cfg["A"], H=cfg["H"], C=cfg["C"],
+                D=cfg["D"], approx=cfg["approx"], density=density, shared_masks=shared_masks,
             )
         )
         out += n_c

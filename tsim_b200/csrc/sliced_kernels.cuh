@@ -60,6 +60,11 @@ struct SParams {
   // rounds itself.  The row index is also the shot's RNG counter (sampler.py:75: bernoulli over the whole batch).
   const uint32_t* __restrict__ row_list;
   const uint32_t* __restrict__ n_rows;
+  // narrow layout: the transposes of K0t / K2a done by the groups themselves (no separate launches, no xt round trip):
+  // f_rows != nullptr -> a group builds its matrix from the packed f rows; out_rows != nullptr -> it assembles its shots'
+  // packed output rows (direct bits + drawn bits) when it is through with the last component
+  const uint64_t* __restrict__ f_rows;
+  uint64_t* __restrict__ out_rows;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -619,8 +624,10 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
   typedef LaneWord<LW> L;
   // a *unit* is 32 slabs (1024 shots): a narrow group, or half the lanes of a wide group
   int n_slabs = prm.n_slabs, n_units = prm.n_groups, rounds = prm.rounds;
+  long long n_live = prm.B;  // slots of the launch (batch rows, or entries of the row list)
   if constexpr (HAS_ROWS) {
     const long long nr = (long long)*prm.n_rows;
+    n_live = nr;
     n_slabs = (int)((nr + 31) / 32);
     n_units = (n_slabs + 31) / 32;
     if ((int)blockIdx.x >= n_units) return;  // this CTA owns no unit in any round
@@ -688,7 +695,7 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
     // units of this group in this round, the lane's slabs and its column of the group's matrix.  Lanes 16..31 of a
     // half-filled wide group sit out (owner = false): 64-bit shared-memory accesses are served per half-warp, so an
     // idle half costs no wavefront, and the group's traffic stays proportional to its shots.
-    int slab0;
+    int slab0, unit0 = 0;
     const int col = lane;
     bool gactive, owner = true;
     if constexpr (WIDE) {
@@ -704,6 +711,7 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
       const int u0 = (round * prm.ng + grp) * (int)gridDim.x + (int)blockIdx.x;
       gactive = u0 < n_units;  // uniform over the group's warps
       slab0 = u0 * 32 + lane;
+      unit0 = u0;
     }
     bool active[NH];
 #pragma unroll
@@ -722,20 +730,75 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
       const int F = (int)comp[C_F], n_c = (int)comp[C_NC];
       if (gactive) {
         group_sync(grp, SPLIT * 32);  // the previous component's readers are done with the columns
-        for (int i = w; i < prm.rows; i += SPLIT) {
-          LW v = L::zero();
-          if (i < F) {
-            const uint32_t* src = prm.xt + (size_t)(xt_row0 + i) * prm.slab_cap + slab0;
-            if constexpr (WIDE) {
-              v.x = active[0] ? src[0] : 0u;
-              v.y = active[1] ? src[1] : 0u;
-            } else {
-              v = active[0] ? src[0] : 0u;
+        bool fused_in = false;
+        if constexpr (!WIDE) fused_in = prm.f_rows != nullptr;
+        if (fused_in) {
+          if constexpr (!WIDE) {
+            // K0t inside the group: warp w turns the f rows of slabs w * SPW .. of the unit into matrix columns (lane =
+            // shot; one ballot per selected f bit gives the row word of the slab).  The f words of all the warp's slabs
+            // are fetched first (one DRAM round trip), the selection table travels lane to lane by shuffles (no dependent
+            // global loads in the bit loop).  Stores of one slab hit one bank: ~50 wavefronts per slab and component,
+            // against ~4 500 row loads per slab in phase 1.
+            for (int i = F + w; i < prm.rows; i += SPLIT) xcol[i * 32] = i == one_row ? 0xFFFFFFFFu : 0u;
+            const uint32_t* __restrict__ fsel = blob + blob[H_OFF_FSEL] + comp[C_FSEL_OFF];
+            const int wf = (int)blob[H_WF64];  // <= 4 (host: wider rows keep the separate kernels)
+            uint32_t* xg = xcol - lane;
+            constexpr int SPW = 32 / SPLIT;
+            auto row_ptr = [&](int j) -> const uint64_t* {  // f row of this lane's shot in slab j of the warp, or null
+              const long long slot = ((long long)unit0 * 32 + w * SPW + j) * 32 + lane;
+              if (slot >= n_live) return nullptr;
+              const long long r = HAS_ROWS ? (long long)prm.row_list[slot] : slot;
+              return prm.f_rows + r * wf;
+            };
+            uint64_t fw[SPW];  // word 0 of every slab's row, fetched up front
+#pragma unroll
+            for (int j = 0; j < SPW; ++j) {
+              const uint64_t* fr = row_ptr(j);
+              fw[j] = fr ? fr[0] : 0ull;
             }
-          } else if (i == one_row) {
-            v = L::ones();
+            for (int i0 = 0; i0 < F; i0 += 32) {
+              const int lim = min(32, F - i0);
+              const uint32_t fi_lane = lane < lim ? fsel[i0 + lane] : 0u;
+#pragma unroll
+              for (int j = 0; j < SPW; ++j) {
+                uint64_t w1 = 0, w2 = 0, w3 = 0;  // further words of wide f rows: fetched where needed (L1 / L2)
+                if (wf > 1) {
+                  const uint64_t* fr = row_ptr(j);
+                  if (fr) {
+                    w1 = fr[1];
+                    if (wf > 2) w2 = fr[2];
+                    if (wf > 3) w3 = fr[3];
+                  }
+                }
+                uint32_t mine = 0;
+#pragma unroll 8
+                for (int jj = 0; jj < lim; ++jj) {
+                  const uint32_t fi = __shfl_sync(0xFFFFFFFFu, fi_lane, jj);
+                  const uint32_t wsel = fi >> 6;
+                  const uint64_t wv = wsel == 0 ? fw[j] : wsel == 1 ? w1 : wsel == 2 ? w2 : w3;
+                  const uint32_t word = __ballot_sync(0xFFFFFFFFu, ((uint32_t)(wv >> (fi & 63u)) & 1u) != 0u);
+                  if (lane == jj) mine = word;
+                }
+                if (lane < lim) xg[(i0 + lane) * 32 + w * SPW + j] = mine;
+              }
+            }
           }
-          if (owner) xcol[i * 32] = v;
+        } else {
+          for (int i = w; i < prm.rows; i += SPLIT) {
+            LW v = L::zero();
+            if (i < F) {
+              const uint32_t* src = prm.xt + (size_t)(xt_row0 + i) * prm.slab_cap + slab0;
+              if constexpr (WIDE) {
+                v.x = active[0] ? src[0] : 0u;
+                v.y = active[1] ? src[1] : 0u;
+              } else {
+                v = active[0] ? src[0] : 0u;
+              }
+            } else if (i == one_row) {
+              v = L::ones();
+            }
+            if (owner) xcol[i * 32] = v;
+          }
         }
       }
 
@@ -873,6 +936,55 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
       }
       xt_row0 += F;
       draw0 += n_c;
+    }
+    if constexpr (!WIDE) {
+      if (prm.out_rows != nullptr && gactive) {
+        // K2a inside the group: packed output rows of the unit's shots (direct bits of f + the drawn bits, which the
+        // group has just written to ot).  Warp w takes slabs w * SPW ..; lane = shot.  Table entries (direct_tab, dest)
+        // and the slab's drawn words are loaded one per lane and passed around by shuffles.
+        group_sync(grp, SPLIT * 32);
+        const int wf = (int)blob[H_WF64], wo = (int)blob[H_WOUT64];
+        const int n_direct = (int)blob[H_N_DIRECT], n_draws = (int)blob[H_N_DRAWS];
+        const uint32_t* __restrict__ direct_tab = blob + blob[H_OFF_DIRECT];
+        const uint32_t* __restrict__ dest = blob + blob[H_OFF_DEST];
+        constexpr int SPW = 32 / SPLIT;
+        for (int j = 0; j < SPW; ++j) {
+          const long long gslab = (long long)unit0 * 32 + w * SPW + j;
+          const long long slot = gslab * 32 + lane;
+          const bool valid = slot < n_live;
+          long long r = 0;
+          if (valid) r = HAS_ROWS ? (long long)prm.row_list[slot] : slot;
+          const uint64_t* __restrict__ frow = prm.f_rows + r * wf;
+          uint64_t v0 = 0, v1 = 0;  // output words 0 and 1 (host: wider rows keep the separate kernel)
+          for (int jd0 = 0; jd0 < n_direct; jd0 += 32) {
+            const int lim = min(32, n_direct - jd0);
+            const uint32_t fi_lane = lane < lim ? direct_tab[2 * (jd0 + lane)] : 0u;
+            const uint32_t dd_lane = lane < lim ? direct_tab[2 * (jd0 + lane) + 1] : 0u;
+            for (int jd = 0; jd < lim; ++jd) {
+              const uint32_t fi = __shfl_sync(0xFFFFFFFFu, fi_lane, jd), dd = __shfl_sync(0xFFFFFFFFu, dd_lane, jd);
+              const uint32_t d = dd & 0x7FFFFFFFu;
+              const uint64_t bit = (valid ? ((frow[fi >> 6] >> (fi & 63u)) & 1ull) : 0ull) ^ (uint64_t)(dd >> 31);
+              if (d < 64u) v0 |= bit << d;
+              else v1 |= bit << (d - 64u);
+            }
+          }
+          for (int jd0 = 0; jd0 < n_draws; jd0 += 32) {
+            const int lim = min(32, n_draws - jd0);
+            const uint32_t d_lane = lane < lim ? dest[jd0 + lane] : 0u;
+            const uint32_t o_lane = (lane < lim && gslab < n_slabs) ? prm.ot[(size_t)(jd0 + lane) * prm.slab_cap + gslab] : 0u;
+            for (int jd = 0; jd < lim; ++jd) {
+              const uint32_t d = __shfl_sync(0xFFFFFFFFu, d_lane, jd), ow = __shfl_sync(0xFFFFFFFFu, o_lane, jd);
+              const uint64_t bit = (uint64_t)((ow >> lane) & 1u);
+              if (d < 64u) v0 |= bit << d;
+              else v1 |= bit << (d - 64u);
+            }
+          }
+          if (valid) {
+            prm.out_rows[r * wo] = v0;
+            if (wo > 1) prm.out_rows[r * wo + 1] = v1;
+          }
+        }
+      }
     }
   }
 }

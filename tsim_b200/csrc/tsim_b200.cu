@@ -1302,16 +1302,21 @@ static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long 
       p->heavy_seen_B = B;
     }
   }
-  if (p->total_F > 0) {
-    transpose_in_kernel<<<tblocks, 256, 0, st>>>(p->d_blob, d_f, B, n_slabs, (int)slab_cap, d_xt, rows, n_rows);
-    CU(cudaGetLastError());
-  }
+  SlicedPlan pl;
+  bool fused = false;  // narrow layout: the groups transpose their inputs and assemble their output rows themselves
   if (in.n_draws > 0) {
-    SlicedPlan pl;
     long long expect = -1;
     if (memo && p->h_heavy_seen && p->heavy_seen_B > 0)  // scale the last count to this batch size (+ 25 % headroom)
       expect = std::min<long long>(B, (long long)((double)*p->h_heavy_seen * 1.25 * (double)B / (double)p->heavy_seen_B) + 1024);
     if (!sliced_plan(p, n_slabs, pl, memo, expect)) return fail(TSB_ERR_UNSUPPORTED, "internal: no sliced launch plan fits in shared memory");
+    fused = !pl.wide && in.words_f64 <= 4 && in.words_out64 <= 2;  // f words held in registers, two output words
+    if (const char* e = getenv("TSIM_B200_SLICED_FUSE")) fused = fused && atoi(e) != 0;  // tuning knob: 0 = separate K0t / K2a launches
+  }
+  if (p->total_F > 0 && in.n_draws > 0 && !fused) {
+    transpose_in_kernel<<<tblocks, 256, 0, st>>>(p->d_blob, d_f, B, n_slabs, (int)slab_cap, d_xt, rows, n_rows);
+    CU(cudaGetLastError());
+  }
+  if (in.n_draws > 0) {
     SParams k;
     k.blob = p->d_blob; k.xt = d_xt; k.ot = d_ot; k.subkeys = d_subkeys; k.B = B; k.shot_offset = shot_offset;
     k.pv = reinterpret_cast<float*>(d_ot + (((size_t)slab_cap * std::max(1, in.n_draws) + 3) & ~(size_t)3));  // 16-byte aligned
@@ -1326,13 +1331,16 @@ static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long 
     }
     k.sel_e = make_uint4(8u, 8u << 8, 8u << 16, 8u << 24);
     k.row_list = rows; k.n_rows = n_rows;
+    k.f_rows = fused ? d_f : nullptr; k.out_rows = fused ? d_out : nullptr;
     if (!memo && k1s_start) CU(cudaEventRecord(k1s_start, st));
     sliced_fn(pl.split, p->s_has_exact, memo, pl.wide != 0)<<<pl.grid, pl.groups * pl.split * 32, pl.smem_bytes, st>>>(k);
     CU(cudaGetLastError());
     if (!memo && k1s_stop) CU(cudaEventRecord(k1s_stop, st));
   }
-  assemble_out_kernel<<<tblocks, 256, 0, st>>>(p->d_blob, d_f, d_ot, B, n_slabs, (int)slab_cap, d_out, rows, n_rows);
-  CU(cudaGetLastError());
+  if (!fused) {
+    assemble_out_kernel<<<tblocks, 256, 0, st>>>(p->d_blob, d_f, d_ot, B, n_slabs, (int)slab_cap, d_out, rows, n_rows);
+    CU(cudaGetLastError());
+  }
   if (memo && k1s_stop) CU(cudaEventRecord(k1s_stop, st));
   if (shot_offset == 0 && in.n_components > 0 && p->aux) {
     // fork: the check works on copies of row 0, on a side stream, while st carries on with the next slice / step

@@ -180,6 +180,10 @@ int tsb_postselect_destroy(tsb_postselect* s);
  * batch's sampling kernel.  dst is a peer-mapped (or local) device address, e.g. from CUDA IPC / symmetric memory. */
 int tsb_memcpy_peer_async(void* dst, const void* src, size_t nbytes, void* stream);
 
+/* free / total device memory in bytes: what the reference's automatic batch size is derived from
+ * (src/tsim/sampler.py:294-320, _estimate_batch_size). */
+int tsb_device_mem_info(int device, int64_t* free_bytes, int64_t* total_bytes);
+
 void* tsb_host_alloc(size_t nbytes); /* page-locked host memory, NULL on failure */
 void tsb_host_free(void* ptr);
 

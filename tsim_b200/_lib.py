@@ -37,6 +37,7 @@ EXPORTS = (
     "tsb_sample_noisy_host",
     "tsb_sample_noisy_host_layout",
     "tsb_layout_row_bytes",
+    "tsb_device_mem_info",
     "tsb_program_set_pattern_cache",
     "tsb_program_set_aux",
     "tsb_postselect_create",
@@ -154,6 +155,8 @@ def load() -> C.CDLL:
     lib.tsb_sample_noisy_host.argtypes = [vp, vp, i64, i64, u32, u32, u64, u64, i32, vp, i32, vp, vp]
     lib.tsb_sample_noisy_host_layout.restype = i32
     lib.tsb_sample_noisy_host_layout.argtypes = [vp, vp, i64, i64, u32, u32, u64, u64, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.tsb_device_mem_info.restype = i32
+    lib.tsb_device_mem_info.argtypes = [i32, C.POINTER(i64), C.POINTER(i64)]
     lib.tsb_layout_row_bytes.restype = i64
     lib.tsb_layout_row_bytes.argtypes = [vp, i32]
     lib.tsb_program_set_aux.restype = i32

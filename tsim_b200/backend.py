@@ -267,6 +267,12 @@ class DeviceProgram:
         dev = dev[: self.info["n_components"]]
         return (out, dev, f_out) if return_f else (out, dev)
 
+    def mem_info(self) -> tuple[int, int]:
+        """(free, total) bytes of this program's device."""
+        free, total = C.c_int64(0), C.c_int64(0)
+        _lib.check(self._lib.tsb_device_mem_info(int(self.device), C.byref(free), C.byref(total)))
+        return int(free.value), int(total.value)
+
     def layout_row_bytes(self, segments, *, bit_packed: bool, split: int = 0) -> tuple[int, int]:
         """Bytes per row of the (first, second) result array of a column layout (``tsb_layout_row_bytes``)."""
         lay = _lib.TsbLayout.make(segments, bit_packed=bit_packed, split=split)

@@ -65,6 +65,10 @@ struct SParams {
   // packed output rows (direct bits + drawn bits) when it is through with the last component
   const uint64_t* __restrict__ f_rows;
   uint64_t* __restrict__ out_rows;
+  // ring flow control: 0 = warps count themselves out of a stage and the last one refills it (groups drift apart: one
+  // group's phase 2 overlaps another's phase 1); 1 = one CTA-wide barrier per chunk (all groups in the same code at the
+  // same time: fewer instruction-cache misses, which wins for the larger exact-level kernels -- cfg4: 13.0 vs 11.8 ms)
+  int lockstep;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -750,37 +754,42 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
               const long long r = HAS_ROWS ? (long long)prm.row_list[slot] : slot;
               return prm.f_rows + r * wf;
             };
-            uint64_t fw[SPW];  // word 0 of every slab's row, fetched up front
-#pragma unroll
+            // word 0 of the slabs' rows is fetched two slabs ahead (DRAM latency); the slab loop stays rolled: this
+            // runs once per component and must not bloat the kernel's code
+            auto word0 = [&](int j) -> uint64_t {
+              const uint64_t* fr = j < SPW ? row_ptr(j) : nullptr;
+              return fr ? fr[0] : 0ull;
+            };
+            uint64_t f_cur = word0(0), f_n1 = word0(1);
+#pragma unroll 1
             for (int j = 0; j < SPW; ++j) {
-              const uint64_t* fr = row_ptr(j);
-              fw[j] = fr ? fr[0] : 0ull;
-            }
-            for (int i0 = 0; i0 < F; i0 += 32) {
-              const int lim = min(32, F - i0);
-              const uint32_t fi_lane = lane < lim ? fsel[i0 + lane] : 0u;
-#pragma unroll
-              for (int j = 0; j < SPW; ++j) {
-                uint64_t w1 = 0, w2 = 0, w3 = 0;  // further words of wide f rows: fetched where needed (L1 / L2)
-                if (wf > 1) {
-                  const uint64_t* fr = row_ptr(j);
-                  if (fr) {
-                    w1 = fr[1];
-                    if (wf > 2) w2 = fr[2];
-                    if (wf > 3) w3 = fr[3];
-                  }
+              const uint64_t f_n2 = word0(j + 2);
+              uint64_t w1 = 0, w2 = 0, w3 = 0;  // further words of wide f rows: fetched where needed (L1 / L2)
+              if (wf > 1) {
+                const uint64_t* fr = row_ptr(j);
+                if (fr) {
+                  w1 = fr[1];
+                  if (wf > 2) w2 = fr[2];
+                  if (wf > 3) w3 = fr[3];
                 }
+              }
+#pragma unroll 1
+              for (int i0 = 0; i0 < F; i0 += 32) {
+                const int lim = min(32, F - i0);
+                const uint32_t fi_lane = lane < lim ? fsel[i0 + lane] : 0u;
                 uint32_t mine = 0;
-#pragma unroll 8
+#pragma unroll 4
                 for (int jj = 0; jj < lim; ++jj) {
                   const uint32_t fi = __shfl_sync(0xFFFFFFFFu, fi_lane, jj);
                   const uint32_t wsel = fi >> 6;
-                  const uint64_t wv = wsel == 0 ? fw[j] : wsel == 1 ? w1 : wsel == 2 ? w2 : w3;
+                  const uint64_t wv = wsel == 0 ? f_cur : wsel == 1 ? w1 : wsel == 2 ? w2 : w3;
                   const uint32_t word = __ballot_sync(0xFFFFFFFFu, ((uint32_t)(wv >> (fi & 63u)) & 1u) != 0u);
                   if (lane == jj) mine = word;
                 }
                 if (lane < lim) xg[(i0 + lane) * 32 + w * SPW + j] = mine;
               }
+              f_cur = f_n1;
+              f_n1 = f_n2;
             }
           }
         } else {
@@ -836,12 +845,17 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
               pbuf ^= 1u;
             }
           }
-          __syncwarp();
-          if (lane == 0 && atom_add_acq_rel_shared(&released[stage], 1u) == n_warps - 1u) {  // every warp is done with this stage
-            released[stage] = 0u;
-            if (q + prm.n_stages < total_q) {
-              fence_proxy_async();
-              issue(q + prm.n_stages);
+          if (prm.lockstep) {  // CTA-wide barrier per chunk: all groups walk the same code at the same time
+            __syncthreads();
+            if (tid == 0 && q + prm.n_stages < total_q) issue(q + prm.n_stages);
+          } else {
+            __syncwarp();
+            if (lane == 0 && atom_add_acq_rel_shared(&released[stage], 1u) == n_warps - 1u) {  // every warp is done with this stage
+              released[stage] = 0u;
+              if (q + prm.n_stages < total_q) {
+                fence_proxy_async();
+                issue(q + prm.n_stages);
+              }
             }
           }
           ++q;

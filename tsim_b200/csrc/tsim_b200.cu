@@ -21,6 +21,7 @@
 #include "postselect.cuh"
 #include "sampler_kernels.cuh"
 #include "sliced_kernels.cuh"
+#include <nvtx3/nvToolsExt.h>
 
 namespace tsb {
 
@@ -34,6 +35,12 @@ namespace tsb {
 //   then  wf32 x kThreads        f row of every shot of the tile   (word-major: [w][tid])
 //   then  wout32 x kThreads      output row of every shot          (word-major)
 //   then  data region (resident) or n_stages x stage_words ring    (128-byte aligned)
+// NVTX range around an entry point (header-only NVTX 3: a no-op unless a profiler is attached)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 constexpr int kBarWords = 64;
 constexpr int kMaxStages = 32;
 
@@ -706,6 +713,7 @@ struct tsb_program {
   uint32_t* d_subkeys = nullptr;
   float last_ms = 0.f;
   int last_launches = 0;
+  int last_sliced_launches = 0;  // kernels of the last launch_sliced call (light pass, K0t, K1s, K2a, norm check)
   int sm_count = 0;
   // pattern cache
   int cache_wmax = -1;  // -1: off
@@ -1284,6 +1292,7 @@ static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl, bool 
 static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long long shot_offset, const uint32_t* d_subkeys,
                          uint64_t* d_out, float* d_norm_dev, cudaStream_t st, uint32_t* d_xt, uint32_t* d_ot, long long slab_cap,
                          bool join = false, cudaEvent_t k1s_start = nullptr, cudaEvent_t k1s_stop = nullptr, uint32_t* d_heavy = nullptr) {
+  p->last_sliced_launches = 0;
   if (B <= 0) return TSB_OK;
   const tsb_info& in = p->info;
   const int n_slabs = (int)((B + 31) / 32);
@@ -1297,6 +1306,7 @@ static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long 
   if (memo) {
     int rc = launch_light(p, d_f, B, shot_offset, d_subkeys, d_out, d_heavy + kHeavyRows, d_heavy, st);
     if (rc) return rc;
+    ++p->last_sliced_launches;
     if (p->h_heavy_seen) {  // remember the count for the next call's launch shape (read whenever it lands)
       CU(cudaMemcpyAsync(p->h_heavy_seen, d_heavy, 4, cudaMemcpyDeviceToHost, st));
       p->heavy_seen_B = B;
@@ -1315,6 +1325,7 @@ static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long 
   if (p->total_F > 0 && in.n_draws > 0 && !fused) {
     transpose_in_kernel<<<tblocks, 256, 0, st>>>(p->d_blob, d_f, B, n_slabs, (int)slab_cap, d_xt, rows, n_rows);
     CU(cudaGetLastError());
+    ++p->last_sliced_launches;
   }
   if (in.n_draws > 0) {
     SParams k;
@@ -1332,17 +1343,22 @@ static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long 
     k.sel_e = make_uint4(8u, 8u << 8, 8u << 16, 8u << 24);
     k.row_list = rows; k.n_rows = n_rows;
     k.f_rows = fused ? d_f : nullptr; k.out_rows = fused ? d_out : nullptr;
+    k.lockstep = p->s_has_exact ? 1 : 0;
+    if (const char* e = getenv("TSIM_B200_SLICED_LOCKSTEP")) k.lockstep = atoi(e) != 0;  // tuning knob
     if (!memo && k1s_start) CU(cudaEventRecord(k1s_start, st));
     sliced_fn(pl.split, p->s_has_exact, memo, pl.wide != 0)<<<pl.grid, pl.groups * pl.split * 32, pl.smem_bytes, st>>>(k);
     CU(cudaGetLastError());
+    ++p->last_sliced_launches;
     if (!memo && k1s_stop) CU(cudaEventRecord(k1s_stop, st));
   }
   if (!fused) {
     assemble_out_kernel<<<tblocks, 256, 0, st>>>(p->d_blob, d_f, d_ot, B, n_slabs, (int)slab_cap, d_out, rows, n_rows);
     CU(cudaGetLastError());
+    ++p->last_sliced_launches;
   }
   if (memo && k1s_stop) CU(cudaEventRecord(k1s_stop, st));
   if (shot_offset == 0 && in.n_components > 0 && p->aux) {
+    ++p->last_sliced_launches;  // the norm check of shot 0 (side stream)
     // fork: the check works on copies of row 0, on a side stream, while st carries on with the next slice / step
     const tsb_program* a = p->aux;
     CU(cudaMemcpyAsync(p->d_row0, d_f, 8 * (size_t)in.words_f64, cudaMemcpyDeviceToDevice, st));
@@ -1374,6 +1390,7 @@ int tsb_program_set_aux(tsb_program* p, tsb_program* aux) {
 
 int tsb_sample_device(tsb_program* p, const uint64_t* d_f, int64_t B, int64_t shot_offset, uint32_t k0, uint32_t k1,
                       uint64_t* d_out, float* d_norm_dev, void* stream) {
+  NvtxRange nvtx_range("tsb_sample_device");
   if (!p) return fail(TSB_ERR_INVALID, "null handle");
   if (B < 0 || shot_offset < 0) return fail(TSB_ERR_INVALID, "negative batch size or offset");
   if (B > 0 && (!d_f || !d_out)) return fail(TSB_ERR_INVALID, "null device buffer");
@@ -1405,7 +1422,7 @@ int tsb_sample_device(tsb_program* p, const uint64_t* d_f, int64_t B, int64_t sh
                            p->d_ot, p->scratch_slabs, d_norm_dev != nullptr, p->ev_a, p->ev_b, p->cache_wmax >= 0 ? p->d_heavy : nullptr);
     if (rc) return rc;
     if (p->info.n_draws == 0) CU(cudaEventRecord(p->ev_b, st));  // no sampling kernel ran: empty interval
-    p->last_launches = B > 0 ? 5 : 0;
+    p->last_launches = B > 0 ? 1 + p->last_sliced_launches : 0;  // derive_subkeys + the sliced pipeline
     p->last_ms = -1.f;
     return TSB_OK;
   }
@@ -1504,6 +1521,7 @@ int tsb_unpack_out_device(tsb_program* p, const uint64_t* d_packed, int64_t B, u
 
 int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int64_t shot_offset, uint32_t k0, uint32_t k1,
                     void* out, int out_format, float* norm_dev) {
+  NvtxRange nvtx_range("tsb_sample_host");
   if (!p) return fail(TSB_ERR_INVALID, "null handle");
   if (B < 0 || shot_offset < 0) return fail(TSB_ERR_INVALID, "negative batch size or offset");
   if (f_format != TSB_F_BYTES && f_format != TSB_F_PACKED) return fail(TSB_ERR_INVALID, "bad f_format");
@@ -1616,7 +1634,7 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
     if (rc) return rc;
     CU(cudaEventRecord(s.k_stop, s.stream));
     s.timed = true;
-    p->last_launches += 2 + (f_format == TSB_F_BYTES ? 1 : 0) + (out_format == TSB_OUT_BYTES ? 1 : 0);
+    p->last_launches += 1 + (p->is_sliced ? p->last_sliced_launches : 1) + (f_format == TSB_F_BYTES ? 1 : 0) + (out_format == TSB_OUT_BYTES ? 1 : 0);
     uint8_t* dst = (uint8_t*)out + (size_t)lo * out_row;
     if (out_row > 0) {
       if (out_format == TSB_OUT_BYTES) {
@@ -1658,6 +1676,7 @@ int tsb_sample_host(tsb_program* p, const void* f, int f_format, int64_t B, int6
 }
 
 int tsb_evaluate_host(tsb_program* p, int component, int level, const uint8_t* params, int64_t B, float* amp) {
+  NvtxRange nvtx_range("tsb_evaluate_host");
   if (!p) return fail(TSB_ERR_INVALID, "null handle");
   if (p->is_sliced) {
     if (!p->aux) return fail(TSB_ERR_UNSUPPORTED, "a sliced program evaluates rows through its companion program (tsb_program_set_aux)");
@@ -1791,6 +1810,7 @@ int tsb_noise_destroy(tsb_noise* n) {
 
 int tsb_noise_sample_device(tsb_noise* n, int64_t B, int64_t shot_offset, uint64_t seed, uint64_t call, int skip_shot0,
                             uint64_t* d_f, void* stream) {
+  NvtxRange nvtx_range("tsb_noise_sample_device");
   if (!n) return fail(TSB_ERR_INVALID, "null handle");
   if (B < 0 || shot_offset < 0) return fail(TSB_ERR_INVALID, "negative batch size or offset");
   if (B == 0) return TSB_OK;
@@ -1846,6 +1866,7 @@ static int sample_noisy_host_impl(tsb_program* p, tsb_noise* n, int64_t B, int64
                                   uint64_t noise_seed, uint64_t noise_call, int skip_shot0, void* out, int out_format,
                                   float* norm_dev, uint64_t* f_out, const LayoutDev* lay, const uint64_t* xor_row,
                                   const uint64_t* ref_mask, uint64_t* row0_out, const LayoutDev* lay2 = nullptr, void* out2 = nullptr) {
+  NvtxRange nvtx_range("tsb_sample_noisy_host");
   if (!p || !n) return fail(TSB_ERR_INVALID, "null handle");
   if (B < 0 || shot_offset < 0) return fail(TSB_ERR_INVALID, "negative batch size or offset");
   if (!lay && out_format != TSB_OUT_BYTES && out_format != TSB_OUT_PACKED) return fail(TSB_ERR_INVALID, "bad out_format");
@@ -1901,7 +1922,7 @@ static int sample_noisy_host_impl(tsb_program* p, tsb_noise* n, int64_t B, int64
     if (rc) return rc;
     CU(cudaEventRecord(s.k_stop, s.stream));
     s.timed = true;
-    p->last_launches += 3 + ((lay || out_format == TSB_OUT_BYTES) ? 1 : 0);
+    p->last_launches += 2 + (p->is_sliced ? p->last_sliced_launches : 1) + ((lay || out_format == TSB_OUT_BYTES) ? 1 : 0);  // noise, subkeys, sampling, layout
     if (f_out) CU(cudaMemcpyAsync(f_out + (size_t)lo * in.words_f64, s.d_f, (size_t)cnt * in.words_f64 * 8, cudaMemcpyDeviceToHost, s.stream));
     if (out_row == 0 && !(lay2 && lay2->row_bytes)) continue;
     if (lay) {
@@ -1989,6 +2010,15 @@ static int64_t layout_part_bytes(const tsb_layout* layout, int first, int last) 
 static bool layout_ok(const tsb_layout* layout) {
   return layout && layout->n_segments >= 0 && layout->n_segments <= 4 && layout->split >= 0 && layout->split <= layout->n_segments;
 }
+int tsb_device_mem_info(int device, int64_t* free_bytes, int64_t* total_bytes) {
+  size_t f = 0, t = 0;
+  CU(cudaSetDevice(device));
+  CU(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = (int64_t)f;
+  if (total_bytes) *total_bytes = (int64_t)t;
+  return TSB_OK;
+}
+
 int64_t tsb_layout_row_bytes(const tsb_layout* layout, int which) {
   if (!layout_ok(layout) || which < 0 || which > 1) return -1;
   const int cut = layout->split > 0 ? layout->split : layout->n_segments;
@@ -2156,6 +2186,7 @@ int tsb_postselect_push_noise(tsb_postselect* s, tsb_noise* noise, int64_t n, ui
 }
 
 int tsb_postselect_dispatch(tsb_postselect* s, uint32_t k0, uint32_t k1, int final_batch, float* norm_dev, int64_t* pending_out) {
+  NvtxRange nvtx_range("tsb_postselect_dispatch");
   if (!s) return fail(TSB_ERR_INVALID, "null session");
   const tsb_info& in = s->p->info;
   if (s->pending == 0) return fail(TSB_ERR_INVALID, "no pending survivors");

@@ -299,8 +299,23 @@ class _CompiledSamplerBase:
             return self._compute_direct_outputs(f_ref)[0]
         return np.asarray(self._run(f_ref)[0], dtype=np.bool_)
 
+    def _peak_bytes_per_sample(self) -> int:
+        """Device bytes per shot of one batch (reference ``_peak_bytes_per_sample``, sampler.py:294-306, estimates XLA's
+        intermediates; here: packed f and output rows, their byte-format staging and the bit-sliced scratch)."""
+        prog = self._program
+        num_f, n_out = prog.infer_num_f(), int(prog.num_outputs)
+        total_f = sum(len(c.f_selection) for c in prog.components)
+        n_draws = sum(len(c.compiled_scalar_graphs) - 1 for c in prog.components)
+        return max(1, 8 * (-(-num_f // 64) + -(-n_out // 64)) + num_f + n_out + (total_f + n_draws + 32 + 7) // 8 + 4)
+
     def _estimate_batch_size(self) -> int:
-        return self.MAX_AUTO_BATCH
+        """Largest batch that fits in half of the free device memory (reference sampler.py:308-320), capped at
+        ``MAX_AUTO_BATCH``: the device pipeline works through a batch in slices, so larger batches buy nothing."""
+        mem_info = getattr(self._device_program, "mem_info", None)
+        if mem_info is None:
+            return self.MAX_AUTO_BATCH
+        free, _total = mem_info()
+        return max(1, min(self.MAX_AUTO_BATCH, int(free * 0.5) // self._peak_bytes_per_sample()))
 
     def _resolve_batch_size(self, shots: int, batch_size: int | None, *, compute_reference: bool) -> int:
         if batch_size is None:

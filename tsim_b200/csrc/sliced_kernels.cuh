@@ -773,20 +773,30 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
                   if (wf > 3) w3 = fr[3];
                 }
               }
+              const uint32_t f_lo = (uint32_t)f_cur, f_hi = (uint32_t)(f_cur >> 32);
+              uint32_t* xs_slab = xg + w * SPW + j;  // column of this slab; lane 0 stores the row words as they come
 #pragma unroll 1
               for (int i0 = 0; i0 < F; i0 += 32) {
                 const int lim = min(32, F - i0);
                 const uint32_t fi_lane = lane < lim ? fsel[i0 + lane] : 0u;
-                uint32_t mine = 0;
+                if (wf == 1) {  // the common case (num_f <= 64): 32-bit selects and shifts only
+#pragma unroll 8
+                  for (int jj = 0; jj < lim; ++jj) {
+                    const uint32_t fi = __shfl_sync(0xFFFFFFFFu, fi_lane, jj);
+                    const uint32_t half = (fi & 32u) ? f_hi : f_lo;
+                    const uint32_t word = __ballot_sync(0xFFFFFFFFu, ((half >> (fi & 31u)) & 1u) != 0u);
+                    if (lane == 0) xs_slab[(i0 + jj) * 32] = word;
+                  }
+                } else {
 #pragma unroll 4
-                for (int jj = 0; jj < lim; ++jj) {
-                  const uint32_t fi = __shfl_sync(0xFFFFFFFFu, fi_lane, jj);
-                  const uint32_t wsel = fi >> 6;
-                  const uint64_t wv = wsel == 0 ? f_cur : wsel == 1 ? w1 : wsel == 2 ? w2 : w3;
-                  const uint32_t word = __ballot_sync(0xFFFFFFFFu, ((uint32_t)(wv >> (fi & 63u)) & 1u) != 0u);
-                  if (lane == jj) mine = word;
+                  for (int jj = 0; jj < lim; ++jj) {
+                    const uint32_t fi = __shfl_sync(0xFFFFFFFFu, fi_lane, jj);
+                    const uint32_t wsel = fi >> 6;
+                    const uint64_t wv = wsel == 0 ? f_cur : wsel == 1 ? w1 : wsel == 2 ? w2 : w3;
+                    const uint32_t word = __ballot_sync(0xFFFFFFFFu, ((uint32_t)(wv >> (fi & 63u)) & 1u) != 0u);
+                    if (lane == 0) xs_slab[(i0 + jj) * 32] = word;
+                  }
                 }
-                if (lane < lim) xg[(i0 + lane) * 32 + w * SPW + j] = mine;
               }
               f_cur = f_n1;
               f_n1 = f_n2;
@@ -970,6 +980,36 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
           if (valid) r = HAS_ROWS ? (long long)prm.row_list[slot] : slot;
           const uint64_t* __restrict__ frow = prm.f_rows + r * wf;
           uint64_t v0 = 0, v1 = 0;  // output words 0 and 1 (host: wider rows keep the separate kernel)
+          if (wf == 1 && wo == 1) {  // the common case: one f word, one output word, 32-bit halves throughout
+            const uint64_t f0 = valid ? frow[0] : 0ull;
+            const uint32_t f_lo = (uint32_t)f0, f_hi = (uint32_t)(f0 >> 32);
+            uint32_t v_lo = 0, v_hi = 0;
+            for (int jd0 = 0; jd0 < n_direct; jd0 += 32) {
+              const int lim = min(32, n_direct - jd0);
+              const uint32_t fi_lane = lane < lim ? direct_tab[2 * (jd0 + lane)] : 0u;
+              const uint32_t dd_lane = lane < lim ? direct_tab[2 * (jd0 + lane) + 1] : 0u;
+#pragma unroll 4
+              for (int jd = 0; jd < lim; ++jd) {
+                const uint32_t fi = __shfl_sync(0xFFFFFFFFu, fi_lane, jd), dd = __shfl_sync(0xFFFFFFFFu, dd_lane, jd);
+                const uint32_t bit = ((((fi & 32u) ? f_hi : f_lo) >> (fi & 31u)) & 1u) ^ (dd >> 31);
+                if (dd & 32u) v_hi |= bit << (dd & 31u);  // warp-uniform
+                else v_lo |= bit << (dd & 31u);
+              }
+            }
+            for (int jd0 = 0; jd0 < n_draws; jd0 += 32) {
+              const int lim = min(32, n_draws - jd0);
+              const uint32_t d_lane = lane < lim ? dest[jd0 + lane] : 0u;
+              const uint32_t o_lane = (lane < lim && gslab < n_slabs) ? prm.ot[(size_t)(jd0 + lane) * prm.slab_cap + gslab] : 0u;
+              for (int jd = 0; jd < lim; ++jd) {
+                const uint32_t d = __shfl_sync(0xFFFFFFFFu, d_lane, jd), ow = __shfl_sync(0xFFFFFFFFu, o_lane, jd);
+                const uint32_t bit = (ow >> lane) & 1u;
+                if (d & 32u) v_hi |= bit << (d & 31u);
+                else v_lo |= bit << (d & 31u);
+              }
+            }
+            if (valid) prm.out_rows[r] = (uint64_t)v_lo | ((uint64_t)v_hi << 32);
+            continue;
+          }
           for (int jd0 = 0; jd0 < n_direct; jd0 += 32) {
             const int lim = min(32, n_direct - jd0);
             const uint32_t fi_lane = lane < lim ? direct_tab[2 * (jd0 + lane)] : 0u;

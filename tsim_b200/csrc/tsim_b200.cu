@@ -663,10 +663,10 @@ static bool pack_rows_host_begin(const uint8_t* src, long long n, int num_f, int
   return false;
 }
 
-constexpr int kSlots = 3;            // pipeline depth of tsb_sample_host
+constexpr int kSlots = 4;            // pipeline depth of tsb_sample_host
 constexpr int kHeavyRows = 4;        // word offset of the row list inside a heavy buffer (the count sits at word 0)
 static size_t heavy_bytes(long long cap) { return 4 * ((size_t)cap + kHeavyRows + 64); }
-constexpr long long kSliceDefault = 262144;  // shots per pipeline slice (best of the sweep in tools/sweep_slice.py)
+constexpr long long kSliceDefault = 196608;  // shots per pipeline slice (tools/e2e_slice_sweep.py: 1.43 / 1.20 ms per 10^6 shots without / with the pattern cache; 262144: 1.45 / 1.27)
 static long long slice_env() {
   static long long v = [] {
     if (const char* e = getenv("TSIM_B200_SLICE")) {

@@ -742,6 +742,9 @@ struct tsb_program {
 // cfg2 with 10^6 shots: the host-to-device copy of the reference's byte rows (63 MB at ~49 GB/s = 1.3 ms) is the critical
 // path, 262144-shot slices leave the shortest tail behind it (tools/sweep_slice.py, tools/e2e_trace.py).
 static long long pipeline_slice(const tsb_program*) { return slice_env() ? slice_env() : kSliceDefault; }
+// device-noise pipeline (no input copy to hide): 262144-shot slices measured best for cfg2 (0.85 ms per 10^6 shots; 196608:
+// 0.98, 524288: 0.83, one slice: 1.07) and cfg3 (8.7 ms per 10^7; 10^6-shot slices: 9.5)
+static long long noisy_slice(const tsb_program*) { return slice_env() ? slice_env() : 262144; }
 
 const char* tsb_last_error(void) { return g_err.c_str(); }
 
@@ -1894,7 +1897,7 @@ static int sample_noisy_host_impl(tsb_program* p, tsb_noise* n, int64_t B, int64
     d_xor = ref_mask ? p->d_layout_rows + 2 * wo : p->d_layout_rows;
   }
   CU(cudaStreamSynchronize(p->stream));
-  const long long slice = std::min<long long>(pipeline_slice(p), B);
+  const long long slice = std::min<long long>(noisy_slice(p), B);
   const size_t out_row = lay ? (size_t)lay->row_bytes : out_format == TSB_OUT_BYTES ? (size_t)in.num_outputs : (size_t)wo * 8;
   const int skip = ref_mask ? 1 : 0;  // the reference row itself is not part of the result (sampler.py:408)
   const int n_slices = (int)((B + slice - 1) / slice);

@@ -185,7 +185,6 @@ struct LaneWord;
 template <>
 struct LaneWord<uint32_t> {
   static constexpr int kWords = 1;
-  static constexpr bool kPrefetch = false;  // item records of phase 1 (run_items)
   static __device__ __forceinline__ uint32_t zero() { return 0u; }
   static __device__ __forceinline__ uint32_t ones() { return 0xFFFFFFFFu; }
   static __device__ __forceinline__ uint32_t ld(uint32_t saddr) {
@@ -195,7 +194,6 @@ struct LaneWord<uint32_t> {
 template <>
 struct LaneWord<U2> {
   static constexpr int kWords = 2;
-  static constexpr bool kPrefetch = false;  // measured: no gain at 16 warps of 128 registers (0.727 -> 0.738 ms)
   static __device__ __forceinline__ U2 zero() { return U2{0u, 0u}; }
   static __device__ __forceinline__ U2 ones() { return U2{0xFFFFFFFFu, 0xFFFFFFFFu}; }
   static __device__ __forceinline__ U2 ld(uint32_t saddr) {
@@ -318,16 +316,16 @@ __device__ __forceinline__ const uint32_t* run_items(const uint32_t* __restrict_
 }
 
 // LIN run: item = [params, index words]; NW = index words used, item = 4 words (NW <= 3) or 8 words
-template <class LW, int NW>
+template <class LW, int NW, bool PF>
 __device__ __forceinline__ const uint32_t* lin_run(const uint32_t* __restrict__ b, uint32_t count, uint32_t xs, const uint4& sel, Planes<LW>& P) {
   constexpr int IW = NW <= 3 ? 4 : 8;
-  return run_items<IW, LaneWord<LW>::kPrefetch>(b, count, [&](const uint32_t(&w)[IW]) { lin_op(P, w[0], par_words<LW, NW>(xs, w + 1, sel)); });
+  return run_items<IW, PF>(b, count, [&](const uint32_t(&w)[IW]) { lin_op(P, w[0], par_words<LW, NW>(xs, w + 1, sel)); });
 }
 
 // PI run: item = [4 index words psi, 4 index words phi], N1 / N2 of them used
-template <class LW, int N1, int N2>
+template <class LW, int N1, int N2, bool PF>
 __device__ __forceinline__ const uint32_t* pi_run(const uint32_t* __restrict__ b, uint32_t count, uint32_t xs, const uint4& sel, Planes<LW>& P) {
-  return run_items<8, LaneWord<LW>::kPrefetch>(
+  return run_items<8, PF>(
       b, count, [&](const uint32_t(&w)[8]) { P.A2 ^= par_words<LW, N1>(xs, w, sel) & par_words<LW, N2>(xs, w + 4, sel); });
 }
 
@@ -358,10 +356,10 @@ __device__ __forceinline__ void pair_op(Planes<LW>& P, uint32_t op, uint32_t prm
 }
 
 // LIN2 run: a += 2 p and nothing else
-template <class LW, int NW>
+template <class LW, int NW, bool PF>
 __device__ __forceinline__ const uint32_t* lin2_run(const uint32_t* __restrict__ b, uint32_t count, uint32_t xs, const uint4& sel, Planes<LW>& P) {
   constexpr int IW = NW <= 3 ? 4 : 8;
-  return run_items<IW, LaneWord<LW>::kPrefetch>(b, count, [&](const uint32_t(&w)[IW]) {
+  return run_items<IW, PF>(b, count, [&](const uint32_t(&w)[IW]) {
     const LW p = par_words<LW, NW>(xs, w + 1, sel);
     P.A2 ^= P.A1 & p;
     P.A1 ^= p;
@@ -436,7 +434,7 @@ __device__ __forceinline__ const uint32_t* generic_run(const uint32_t* __restric
 // phase 1: the term stream of one graph (typed runs, pack_sliced.py::_emit_runs) for the lanes of the group ->
 // plane rows plw[r * 32]: r = 0 "some factor vanished", 1..3 a, 4..4+nb-1 the b counter, then (pa, pb) of every
 // in-table general pair.
-template <class LW>
+template <class LW, bool PF>
 __device__ __forceinline__ void sliced_phase1(const uint32_t* __restrict__ cbase, uint32_t rec, const LW* __restrict__ xcol,
                                               LW* __restrict__ plw, const uint4& sel) {
   const uint32_t xs = smem_u32(xcol);
@@ -453,18 +451,18 @@ __device__ __forceinline__ void sliced_phase1(const uint32_t* __restrict__ cbase
     const uint32_t kind = rh & 0xFFFFu, count = rh >> 16;
     b += 4;
     switch (kind) {
-      case RUN_LIN + 0: b = lin_run<LW, 2>(b, count, xs, sel, P); break;
-      case RUN_LIN + 1: b = lin_run<LW, 3>(b, count, xs, sel, P); break;
-      case RUN_LIN + 2: b = lin_run<LW, 4>(b, count, xs, sel, P); break;
-      case RUN_PI + 0: b = pi_run<LW, 2, 2>(b, count, xs, sel, P); break;
-      case RUN_PI + 1: b = pi_run<LW, 2, 3>(b, count, xs, sel, P); break;
-      case RUN_PI + 2: b = pi_run<LW, 2, 4>(b, count, xs, sel, P); break;
-      case RUN_PI + 3: b = pi_run<LW, 3, 3>(b, count, xs, sel, P); break;
-      case RUN_PI + 4: b = pi_run<LW, 3, 4>(b, count, xs, sel, P); break;
-      case RUN_PI + 5: b = pi_run<LW, 4, 4>(b, count, xs, sel, P); break;
-      case RUN_LIN2 + 0: b = lin2_run<LW, 2>(b, count, xs, sel, P); break;
-      case RUN_LIN2 + 1: b = lin2_run<LW, 3>(b, count, xs, sel, P); break;
-      case RUN_LIN2 + 2: b = lin2_run<LW, 4>(b, count, xs, sel, P); break;
+      case RUN_LIN + 0: b = lin_run<LW, 2, PF>(b, count, xs, sel, P); break;
+      case RUN_LIN + 1: b = lin_run<LW, 3, PF>(b, count, xs, sel, P); break;
+      case RUN_LIN + 2: b = lin_run<LW, 4, PF>(b, count, xs, sel, P); break;
+      case RUN_PI + 0: b = pi_run<LW, 2, 2, PF>(b, count, xs, sel, P); break;
+      case RUN_PI + 1: b = pi_run<LW, 2, 3, PF>(b, count, xs, sel, P); break;
+      case RUN_PI + 2: b = pi_run<LW, 2, 4, PF>(b, count, xs, sel, P); break;
+      case RUN_PI + 3: b = pi_run<LW, 3, 3, PF>(b, count, xs, sel, P); break;
+      case RUN_PI + 4: b = pi_run<LW, 3, 4, PF>(b, count, xs, sel, P); break;
+      case RUN_PI + 5: b = pi_run<LW, 4, 4, PF>(b, count, xs, sel, P); break;
+      case RUN_LIN2 + 0: b = lin2_run<LW, 2, PF>(b, count, xs, sel, P); break;
+      case RUN_LIN2 + 1: b = lin2_run<LW, 3, PF>(b, count, xs, sel, P); break;
+      case RUN_LIN2 + 2: b = lin2_run<LW, 4, PF>(b, count, xs, sel, P); break;
       case RUN_PAIR + 0: b = pair_run<LW, 2>(b, count, xs, sel, P, nb, plw); break;
       case RUN_PAIR + 1: b = pair_run<LW, 3>(b, count, xs, sel, P, nb, plw); break;
       case RUN_PAIR + 2: b = pair_run<LW, 4>(b, count, xs, sel, P, nb, plw); break;
@@ -624,6 +622,9 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
   static_assert(!WIDE || (SPLIT == 4 && !HAS_EXACT), "the wide layout is built for the 4-way split of approximate programs");
   constexpr int SH = 32 / SPLIT;
   constexpr int NH = WIDE ? 2 : 1;  // slabs per lane
+  // Fetching the record of the next item while the current one waits for its rows (run_items PF) was measured twice and
+  // buys nothing: wide layout at 128 registers 0.727 -> 0.738 ms, thin 8-way launches 0.311 -> 0.311 ms per memoised step.
+  constexpr bool kPrefetchRecords = false;
   typedef typename std::conditional<WIDE, U2, uint32_t>::type LW;
   typedef LaneWord<LW> L;
   // a *unit* is 32 slabs (1024 shots): a narrow group, or half the lanes of a wide group
@@ -846,7 +847,7 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
               // A warp may write the other buffer for the next wave as soon as it is through with this one: everybody
               // passed this wave's barrier, hence finished reading that buffer in the wave before.
               LW* pw = plg + pbuf * (SPLIT * plane_words);
-              if (w0 + w < n_g && owner) sliced_phase1<LW>(cbase, cbase[w0 + w], xcol, pw + w * plane_words, sel);
+              if (w0 + w < n_g && owner) sliced_phase1<LW, kPrefetchRecords>(cbase, cbase[w0 + w], xcol, pw + w * plane_words, sel);
               group_sync(grp, SPLIT * 32);
               const int nj = min(SPLIT, n_g - w0);
               if (owner)

@@ -311,11 +311,16 @@ class _CompiledSamplerBase:
     def _estimate_batch_size(self) -> int:
         """Largest batch that fits in half of the free device memory (reference sampler.py:308-320), capped at
         ``MAX_AUTO_BATCH``: the device pipeline works through a batch in slices, so larger batches buy nothing."""
+        cached = getattr(self, "_auto_batch", None)
+        if cached is not None:
+            return cached
         mem_info = getattr(self._device_program, "mem_info", None)
         if mem_info is None:
             return self.MAX_AUTO_BATCH
+        # asked once per sampler: cudaMemGetInfo costs up to milliseconds, a sample() call of 10^6 shots less than one
         free, _total = mem_info()
-        return max(1, min(self.MAX_AUTO_BATCH, int(free * 0.5) // self._peak_bytes_per_sample()))
+        self._auto_batch = max(1, min(self.MAX_AUTO_BATCH, int(free * 0.5) // self._peak_bytes_per_sample()))
+        return self._auto_batch
 
     def _resolve_batch_size(self, shots: int, batch_size: int | None, *, compute_reference: bool) -> int:
         if batch_size is None:

@@ -116,8 +116,9 @@ float tsb_last_kernel_ms(tsb_program* p, int* n_launches);
 /* ---- K5: error-mechanism sampler on the device (statistical parity with ChannelSampler.sample,
  * src/tsim/noise/channels.py:624-658; tables as produced by _precompute_sparse, :578-622) ----
  * Channel c has n_outcomes[c] non-identity outcomes; thresholds (concatenated over channels) are the cumulative
- * outcome probabilities scaled to 2^64 (the channel fires iff u64 < last threshold of the channel); patterns are
- * the outcomes' packed f rows, [sum n_outcomes][words_f64]. */
+ * outcome probabilities scaled to 2^64 (p_fire = last threshold of the channel / 2^64); patterns are the outcomes' packed
+ * f rows, [sum n_outcomes][words_f64].  Like the reference (:638-656) the sampler walks from fire to fire with geometric
+ * gaps -- per channel and block of 1024 in-batch shots, counter-based Philox4x32-10 -- so the work is O(fires). */
 typedef struct tsb_noise tsb_noise;
 int tsb_noise_create(int n_channels, const int32_t* n_outcomes, const uint64_t* thresholds, const uint64_t* patterns,
                      int words_f64, int device, tsb_noise** out);

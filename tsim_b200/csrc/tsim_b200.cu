@@ -1754,6 +1754,7 @@ struct tsb_noise {
   uint32_t* d_chan = nullptr;
   uint64_t* d_thr = nullptr;
   uint64_t* d_pat = nullptr;
+  double* d_inv = nullptr;  // 1 / log1p(-p_fire) per channel (geometric gaps)
   uint64_t* d_f = nullptr;  // scratch for tsb_noise_sample_host
   long long cap = 0;
   cudaStream_t stream = nullptr;
@@ -1768,6 +1769,7 @@ int tsb_noise_create(int n_channels, const int32_t* n_outcomes, const uint64_t* 
   if (device < 0 || device >= ndev) return fail(TSB_ERR_INVALID, "no such CUDA device");
   CU(cudaSetDevice(device));
   std::vector<uint32_t> chan(2 * (size_t)std::max(1, n_channels));
+  std::vector<double> inv((size_t)std::max(1, n_channels), 0.0);
   long long total = 0;
   for (int c = 0; c < n_channels; ++c) {
     if (n_outcomes[c] < 1) return fail(TSB_ERR_INVALID, "a channel needs at least one non-identity outcome");
@@ -1776,6 +1778,9 @@ int tsb_noise_create(int n_channels, const int32_t* n_outcomes, const uint64_t* 
     for (int k = 1; k < n_outcomes[c]; ++k)
       if (thresholds[total + k] < thresholds[total + k - 1]) return fail(TSB_ERR_INVALID, "thresholds must be cumulative");
     total += n_outcomes[c];
+    // p_fire = last threshold / 2^64; gaps between fires are geometric: K = floor(ln U / ln(1 - p))
+    const double p_fire = std::ldexp((double)thresholds[total - 1], -64);
+    inv[c] = p_fire >= 1.0 ? -0.0 : (p_fire > 0.0 ? 1.0 / std::log1p(-p_fire) : -1e300);
   }
   tsb_noise* n = new tsb_noise();
   n->device = device; n->n_channels = n_channels; n->words = words_f64; n->n_outcomes = (int)total;
@@ -1784,8 +1789,10 @@ int tsb_noise_create(int n_channels, const int32_t* n_outcomes, const uint64_t* 
   chk(cudaMalloc(&n->d_chan, chan.size() * 4));
   chk(cudaMalloc(&n->d_thr, 8 * (size_t)std::max<long long>(1, total)));
   chk(cudaMalloc(&n->d_pat, 8 * (size_t)std::max<long long>(1, total) * words_f64));
+  chk(cudaMalloc(&n->d_inv, 8 * inv.size()));
   chk(cudaStreamCreateWithFlags(&n->stream, cudaStreamNonBlocking));
   if (e == cudaSuccess) chk(cudaMemcpy(n->d_chan, chan.data(), chan.size() * 4, cudaMemcpyHostToDevice));
+  if (e == cudaSuccess) chk(cudaMemcpy(n->d_inv, inv.data(), inv.size() * 8, cudaMemcpyHostToDevice));
   if (e == cudaSuccess && total > 0) {
     chk(cudaMemcpy(n->d_thr, thresholds, 8 * (size_t)total, cudaMemcpyHostToDevice));
     chk(cudaMemcpy(n->d_pat, patterns, 8 * (size_t)total * words_f64, cudaMemcpyHostToDevice));
@@ -1806,6 +1813,7 @@ int tsb_noise_destroy(tsb_noise* n) {
   if (n->d_chan) cudaFree(n->d_chan);
   if (n->d_thr) cudaFree(n->d_thr);
   if (n->d_pat) cudaFree(n->d_pat);
+  if (n->d_inv) cudaFree(n->d_inv);
   if (n->d_f) cudaFree(n->d_f);
   delete n;
   return TSB_OK;
@@ -1823,22 +1831,15 @@ int tsb_noise_sample_device(tsb_noise* n, int64_t B, int64_t shot_offset, uint64
   CU(cudaMemsetAsync(d_f, 0, (size_t)B * n->words * 8, st));
   if (n->n_channels == 0) return TSB_OK;
   NoiseParams k;
-  k.chan = n->d_chan; k.thresholds = n->d_thr; k.patterns = n->d_pat; k.f = d_f;
+  k.chan = n->d_chan; k.thresholds = n->d_thr; k.patterns = n->d_pat; k.inv_log1m = n->d_inv; k.f = d_f;
   k.B = B; k.shot_offset = shot_offset; k.n_channels = n->n_channels; k.words = n->words;
   k.seed_lo = (uint32_t)seed; k.seed_hi = (uint32_t)(seed >> 32);
   k.call_lo = (uint32_t)call; k.call_hi = (uint32_t)(call >> 32);
   k.skip_shot0 = skip_shot0;
-  // enough threads to fill the chip: split the channels over grid.y when the batch alone is too small
-  const long long bx = (B + 255) / 256;
-  int groups = 1;
-  while (bx * groups < 4 * 148 && groups * 2 <= (n->n_channels + 1) / 2) groups *= 2;
-  groups = std::max(groups, (n->n_channels + 255) / 256);  // at most 256 channels per thread
-  int cpt = (n->n_channels + groups - 1) / groups;
-  cpt += cpt & 1;
-  k.chan_per_thread = cpt;
-  groups = (n->n_channels + cpt - 1) / cpt;
-  dim3 grid((unsigned)bx, (unsigned)groups);
-  noise_kernel<<<grid, 256, 0, st>>>(k);
+  k.first_block = shot_offset / kNoiseBlockShots;
+  k.n_blocks = (shot_offset + B - 1) / kNoiseBlockShots - k.first_block + 1;
+  const long long threads = k.n_blocks * n->n_channels;
+  noise_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(k);
   CU(cudaGetLastError());
   return TSB_OK;
 }

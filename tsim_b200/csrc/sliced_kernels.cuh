@@ -115,26 +115,70 @@ __global__ void __launch_bounds__(256) transpose_in_kernel(const uint32_t* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2a: bit-sliced outputs + direct bits -> packed rows.  One warp per slab, lane = shot.
+// K2a: bit-sliced outputs + direct bits -> packed rows.  One warp per slab, lane = shot.  (The sampling kernel assembles
+// its own rows in the narrow layout; this kernel serves the wide layout, rows wider than two words and programs without
+// compiled components, e.g. rank-1 circuits whose outputs are all direct.)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) assemble_out_kernel(const uint32_t* __restrict__ blob, const uint64_t* __restrict__ f,
                                                            const uint32_t* __restrict__ ot, long long B, int n_slabs, int slab_cap,
                                                            uint64_t* __restrict__ out, const uint32_t* __restrict__ row_list,
                                                            const uint32_t* __restrict__ n_rows) {
+  __shared__ uint32_t s_tab[2 * 256];  // a tile of the direct table (f index, destination | flip << 31)
   const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (row_list) {
     B = (long long)*n_rows;
     n_slabs = (int)((B + 31) / 32);
   }
-  if (warp >= n_slabs) return;
   const long long slot = (long long)warp * 32 + lane;
-  if (slot >= B) return;
-  const long long row = row_list ? (long long)row_list[slot] : slot;
+  const bool valid = warp < n_slabs && slot < B;
+  const long long row = valid ? (row_list ? (long long)row_list[slot] : slot) : 0;
   const int wf = (int)blob[H_WF64], wo = (int)blob[H_WOUT64];
   const int n_direct = (int)blob[H_N_DIRECT], n_draws = (int)blob[H_N_DRAWS];
   const uint32_t* __restrict__ direct_tab = blob + blob[H_OFF_DIRECT];
   const uint32_t* __restrict__ dest = blob + blob[H_OFF_DEST];
+  if (wf <= 4 && wo <= 2) {
+    // one pass over the direct table (staged in shared memory tile by tile), the shot's f words in registers
+    uint64_t fw0 = 0, fw1 = 0, fw2 = 0, fw3 = 0;
+    if (valid) {
+      const uint64_t* fr = f + row * wf;
+      fw0 = fr[0];
+      if (wf > 1) fw1 = fr[1];
+      if (wf > 2) fw2 = fr[2];
+      if (wf > 3) fw3 = fr[3];
+    }
+    uint64_t v0 = 0, v1 = 0;
+    for (int j0 = 0; j0 < n_direct; j0 += 256) {
+      const int lim = min(256, n_direct - j0);
+      __syncthreads();
+      if ((int)threadIdx.x < lim) {
+        s_tab[2 * threadIdx.x] = direct_tab[2 * (j0 + threadIdx.x)];
+        s_tab[2 * threadIdx.x + 1] = direct_tab[2 * (j0 + threadIdx.x) + 1];
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int j = 0; j < lim; ++j) {
+        const uint32_t fi = s_tab[2 * j], dd = s_tab[2 * j + 1];
+        const uint32_t ws = fi >> 6;
+        const uint64_t fw = ws == 0 ? fw0 : ws == 1 ? fw1 : ws == 2 ? fw2 : fw3;
+        const uint64_t bit = ((fw >> (fi & 63u)) & 1ull) ^ (uint64_t)(dd >> 31);
+        if (dd & 64u) v1 |= bit << (dd & 63u);  // warp-uniform: destination word 1
+        else v0 |= bit << (dd & 63u);
+      }
+    }
+    if (valid) {
+      for (int j = 0; j < n_draws; ++j) {
+        const uint32_t d = dest[j];
+        const uint64_t bit = (ot[(size_t)j * slab_cap + warp] >> lane) & 1u;
+        if (d & 64u) v1 |= bit << (d & 63u);
+        else v0 |= bit << (d & 63u);
+      }
+      out[row * wo] = v0;
+      if (wo > 1) out[row * wo + 1] = v1;
+    }
+    return;
+  }
+  if (!valid) return;
   for (int w = 0; w < wo; ++w) {
     uint64_t v = 0;
     for (int j = 0; j < n_direct; ++j) {

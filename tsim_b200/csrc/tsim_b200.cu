@@ -300,24 +300,46 @@ __device__ __forceinline__ uint32_t layout_bit(const uint64_t* __restrict__ row,
   if (col < 0) return 0u;  // alignment padding between segments
   return (uint32_t)(((row[col >> 6] ^ (x ? x[col >> 6] : 0ull)) >> (col & 63)) & 1ull);
 }
-// rows [skip, n_rows) of `packed` -> out rows [0, n_rows - skip); one thread per output byte
+// `len` (<= 32) bits of a packed row, starting at column `col`, XOR mask applied
+__device__ __forceinline__ uint32_t layout_bits(const uint64_t* __restrict__ row, const uint64_t* __restrict__ x, int col, int len) {
+  const int w = col >> 6, off = col & 63;
+  uint64_t v = (row[w] ^ (x ? x[w] : 0ull)) >> off;
+  if (off + len > 64) v |= (row[w + 1] ^ (x ? x[w + 1] : 0ull)) << (64 - off);
+  return (uint32_t)v & (len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u));
+}
+// rows [skip, n_rows) of `packed` -> out rows [0, n_rows - skip).  Bit-packed output: one thread per 32-bit word of an
+// output row (word shifts per overlapping column range); bool output: one thread per byte.
 __global__ void layout_rows_kernel(const uint64_t* __restrict__ packed, long long n_rows, int skip, int words64,
                                    const uint64_t* __restrict__ xor_row, LayoutDev L, uint8_t* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long rows = n_rows - skip;
+  if (L.bit_packed) {
+    const int wpr = (L.row_bytes + 3) >> 2;  // 32-bit words per output row
+    if (i >= rows * wpr) return;
+    const long long r = i / wpr;
+    const int j = (int)(i % wpr);
+    const uint64_t* row = packed + (r + skip) * words64;
+    const int t0 = 32 * j;
+    uint32_t v = 0;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      if (s >= L.n_seg) break;
+      const int a = max(t0, L.start[s]), b = min(t0 + 32, L.start[s] + L.n[s]);
+      if (b > a) v |= layout_bits(row, xor_row, L.lo[s] + (a - L.start[s]), b - a) << (a - t0);
+    }
+    uint8_t* dst = out + r * L.row_bytes + 4 * j;
+    const int nb = min(4, L.row_bytes - 4 * j);
+    if (nb == 4 && (reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
+      *reinterpret_cast<uint32_t*>(dst) = v;
+    } else {
+      for (int k = 0; k < nb; ++k) dst[k] = (uint8_t)(v >> (8 * k));
+    }
+    return;
+  }
   if (i >= rows * L.row_bytes) return;
   const long long r = i / L.row_bytes;
   const int j = (int)(i % L.row_bytes);
-  const uint64_t* row = packed + (r + skip) * words64;
-  if (L.bit_packed) {
-    uint32_t v = 0;
-#pragma unroll
-    for (int b = 0; b < 8; ++b)
-      if (8 * j + b < L.total_bits) v |= layout_bit(row, xor_row, L, 8 * j + b) << b;
-    out[i] = (uint8_t)v;
-  } else {
-    out[i] = (uint8_t)layout_bit(row, xor_row, L, j);
-  }
+  out[i] = (uint8_t)layout_bit(packed + (r + skip) * words64, xor_row, L, j);
 }
 // xor_final = xor_in ^ (row0 & ref_mask): the reference sample is in-batch shot 0 (sampler.py:404-409)
 __global__ void layout_ref_kernel(const uint64_t* __restrict__ row0, const uint64_t* __restrict__ xor_in, const uint64_t* __restrict__ ref_mask,
@@ -1960,7 +1982,7 @@ static int sample_noisy_host_impl(tsb_program* p, tsb_noise* n, int64_t B, int64
         for (int a = 0; a < 2; ++a) {  // one or two result arrays (separate_observables)
           if (!ls[a] || ls[a]->row_bytes == 0) continue;
           const size_t rb = (size_t)ls[a]->row_bytes;
-          const long long nthreads = rows_out * (long long)rb;
+          const long long nthreads = rows_out * (long long)(ls[a]->bit_packed ? (rb + 3) / 4 : rb);
           layout_rows_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, s.stream>>>(s.d_out, cnt, sk, wo, d_xor, *ls[a], d_dst);
           CU(cudaGetLastError());
           CU(cudaMemcpyAsync(hosts[a] + first_row * rb, d_dst, (size_t)rows_out * rb, cudaMemcpyDeviceToHost, s.stream));

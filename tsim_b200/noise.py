@@ -151,9 +151,10 @@ class DeviceChannelSampler:
     """Error-mechanism sampler that runs on the GPU (``tsb_noise``; kernel K5).
 
     Same distribution as :class:`ChannelSampler` / the reference's ``ChannelSampler.sample``
-    (``channels.py:624-658``) but a different random stream: each (shot, channel) pair draws one 64-bit
-    uniform from a counter-based generator keyed by ``(seed, call number)``, so parity with the reference is
-    statistical (its own tests use 5-10 % tolerances at 1e5 samples, ``test/unit/noise/test_channels.py:987-1048``).
+    (``channels.py:624-658``) but a different random stream: like the reference it walks from fire to fire with
+    geometric gaps (``:638-656``), here per channel and block of 1024 in-batch shots from a counter-based generator
+    keyed by ``(seed, call number)`` -- the rows depend only on (seed, call, in-batch shot index, channel), never on how
+    a batch is sliced or sharded -- so parity with the reference is statistical (its own tests use 5-10 % tolerances at 1e5 samples, ``test/unit/noise/test_channels.py:987-1048``).
     With a ``DeviceProgram`` the f rows never leave the GPU (:meth:`DeviceProgram.sample_noisy`).
     """
 

@@ -401,8 +401,8 @@ def bench_config(cx: Ctx, name: str, total_shots: int, steps: int):
         # rank-1 (Clifford) program: every output is a direct f bit, the device work is noise sampling + gather + packing.
         # Measured through CompiledDetectorSampler.sample(bit_packed=True) with the device channel sampler (K5 -> direct gather -> column layout -> D2H).
         det = S.CompiledDetectorSampler(prog, DeviceChannelSampler.from_bit_probs(q, seed=1 + cx.rank, device=cx.local), seed=2)
-        for _ in range(3):  # the pinned result pool settles after two calls
-            det.sample(shots, bit_packed=True)
+        for _ in range(3):  # the pinned result pool settles once two results have been alive at the same time
+            res = det.sample(shots, bit_packed=True)
         cx.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):

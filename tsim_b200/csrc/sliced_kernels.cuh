@@ -652,12 +652,8 @@ __host__ __device__ constexpr int sliced_max_threads(int split, bool wide = fals
 __device__ __forceinline__ void group_sync(int grp, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ uint32_t atom_add_acq_rel_shared(uint32_t* p, uint32_t v) {
-  uint32_t old;
-  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
-  return old;
-}
-constexpr int kSlicedMaxStages = 16;  // full barriers in the first half of the barrier words, release counters in the second
+// stages of the ring: one mbarrier ("full") and one named barrier (8 + stage, "empty") each; the groups use named barriers 1..7
+constexpr int kSlicedMaxStages = 8;
 
 // dynamic shared memory (32-bit words): [0,64) mbarriers | xt [groups][rows][32 lanes] | planes
 // [groups][2][SPLIT][plane_rows][32 lanes] | stage ring; a lane is one word (narrow) or two (wide)
@@ -710,16 +706,12 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
       s_pair[i] = make_int4(1 + ua.x + ub.x - uc.x, ua.y + ub.y - uc.y, ua.z + ub.z - uc.z, ua.w + ub.w - uc.w);
     }
   }
-  // Ring flow control without a CTA-wide barrier: a warp that is through with a stage counts itself out, and the last one
-  // refills the stage.  Groups therefore drift apart by up to n_stages chunks, so that one group's phase 2 and level
-  // ends (issue-bound) overlap another group's phase 1 (shared-memory bound) instead of all groups moving in lockstep.
-  uint32_t* released = reinterpret_cast<uint32_t*>(bars + kSlicedMaxStages);
-  const uint32_t n_warps = blockDim.x >> 5;
+  // Ring flow control without a CTA-wide barrier (prm.lockstep == 0): a warp that is through with a stage *arrives* on the
+  // stage's named barrier and carries on; warp 0 *waits* on it and refills the stage (split barrier: bar.arrive /
+  // bar.sync).  Groups therefore drift apart by up to n_stages chunks, so that one group's phase 2 and level ends
+  // (issue-bound) overlap another group's phase 1 (shared-memory bound) instead of all groups moving in lockstep.
   if (tid == 0) {
-    for (int i = 0; i < prm.n_stages; ++i) {
-      mbar_init(&bars[i], 1);
-      released[i] = 0u;
-    }
+    for (int i = 0; i < prm.n_stages; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -904,13 +896,16 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
             __syncthreads();
             if (tid == 0 && q + prm.n_stages < total_q) issue(q + prm.n_stages);
           } else {
-            __syncwarp();
-            if (lane == 0 && atom_add_acq_rel_shared(&released[stage], 1u) == n_warps - 1u) {  // every warp is done with this stage
-              released[stage] = 0u;
-              if (q + prm.n_stages < total_q) {
+            // split barrier per stage: every warp arrives when it is through with the stage, warp 0 waits for all of
+            // them and refills.  Named barriers 8.. (the groups use 1..7); the other warps do not wait.
+            if (wid == 0) {
+              asm volatile("bar.sync %0, %1;" ::"r"(8 + (int)stage), "r"((int)blockDim.x) : "memory");
+              if (tid == 0 && q + prm.n_stages < total_q) {
                 fence_proxy_async();
                 issue(q + prm.n_stages);
               }
+            } else {
+              asm volatile("bar.arrive %0, %1;" ::"r"(8 + (int)stage), "r"((int)blockDim.x) : "memory");
             }
           }
           ++q;

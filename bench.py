@@ -400,7 +400,7 @@ def bench_config(cx: Ctx, name: str, total_shots: int, steps: int):
     if not prog.components:
         # rank-1 (Clifford) program: every output is a direct f bit, the device work is noise sampling + gather + packing.
         # Measured through CompiledDetectorSampler.sample(bit_packed=True) with the device channel sampler (K5 -> direct gather -> column layout -> D2H).
-        det = S.CompiledDetectorSampler(prog, DeviceChannelSampler.from_bit_probs(q, seed=1 + cx.rank, device=cx.local), seed=2)
+        det = S.CompiledDetectorSampler(prog, DeviceChannelSampler.from_bit_probs(q, seed=1 + cx.rank, device=cx.local), seed=2, device=cx.local)
         for _ in range(3):  # the pinned result pool settles once two results have been alive at the same time
             res = det.sample(shots, bit_packed=True)
         cx.barrier()
@@ -587,8 +587,8 @@ def run_gpu(args):
 
         extras = {}
         q = noise_probs(info["num_f"], 1e-3)
-        det_host = S.CompiledDetectorSampler(prog, ChannelSampler.from_bit_probs(q, seed=1), seed=2)
-        det_dev = S.CompiledDetectorSampler(prog, DeviceChannelSampler.from_bit_probs(q, seed=1, device=local), seed=2)
+        det_host = S.CompiledDetectorSampler(prog, ChannelSampler.from_bit_probs(q, seed=1), seed=2, device=local)
+        det_dev = S.CompiledDetectorSampler(prog, DeviceChannelSampler.from_bit_probs(q, seed=1, device=local), seed=2, device=local)
         extras["sample_api_host_noise_shots_per_s"] = shots / timed(lambda: det_host.sample(shots, batch_size=shots, bit_packed=True), 2)
         extras["sample_api_device_noise_shots_per_s"] = shots / timed(lambda: det_dev.sample(shots, batch_size=shots, bit_packed=True))
         extras["note"] = ("sample_api = CompiledDetectorSampler.sample(shots, bit_packed=True) including noise sampling, library defaults "

@@ -53,7 +53,9 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
             h = [int(v) for v in data[off : off + SLICED_HEADER_WORDS]]
             n_words, n_gen = h[0] & 0xFFFF, h[0] >> 16
             n_idx, nb, n_mul = h[1] & 0xFF, (h[1] >> 8) & 0xFF, (h[1] >> 16) & 0xFF
-            mul_ctl = [(int(data[off + h[3] - 4]) >> (8 * j)) & 63 for j in range(n_mul)]
+            mul_ctl = [(int(data[off + (h[3] & 0xFFFF) - 4]) >> (8 * j)) & 63 for j in range(n_mul)]
+            main_words = h[3] >> 16
+            assert 0 < main_words <= n_words or n_words == 0
             tbl = coff + h[2]
             A = [0, 0, 0]
             Bp = [0] * 5

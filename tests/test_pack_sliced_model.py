@@ -127,10 +127,12 @@ def test_sliced_chunk_layout_invariants():
                 n_idx, nb = int(hdr[1]) & 0xFF, (int(hdr[1]) >> 8) & 0xFF
                 assert 3 + nb <= n_idx <= 11 and not hdr[4:8].any()
                 body = int(hdr[0]) & 0xFFFF
-                assert body % 4 == 0 and int(hdr[3]) == SLICED_HEADER_WORDS + body
+                assert body % 4 == 0 and (int(hdr[3]) & 0xFFFF) == SLICED_HEADER_WORDS + body
+                main = int(hdr[3]) >> 16  # [main | aux]: the aux part holds whole pi runs, about half of the row loads
+                assert main % 4 == 0 and 0 < main <= body
                 tbl = int(hdr[2])
                 assert tbl % 4 == 0 and tbl + 2 * (1 << n_idx) <= words
-                end_of_records = rec + int(hdr[3])
+                end_of_records = rec + (int(hdr[3]) & 0xFFFF)
                 assert tbl >= end_of_records or g + 1 < ng
 
 

@@ -5,7 +5,7 @@
 namespace tsb {
 
 constexpr uint32_t kMagic = 0x32425354u;  // "TSB2"
-constexpr uint32_t kVersion = 7;
+constexpr uint32_t kVersion = 8;
 constexpr int kModeFaithful = 0;
 constexpr int kModeFast = 1;
 constexpr int kModeSliced = 2;

@@ -478,18 +478,20 @@ __device__ __forceinline__ const uint32_t* generic_run(const uint32_t* __restric
 // phase 1: the term stream of one graph (typed runs, pack_sliced.py::_emit_runs) for the lanes of the group ->
 // plane rows plw[r * 32]: r = 0 "some factor vanished", 1..3 a, 4..4+nb-1 the b counter, then (pa, pb) of every
 // in-table general pair.
-template <class LW, bool PF>
+// The stream is [main | aux] (pack_sliced.py::_split_streams): MAIN_ONLY stops at the end of the main part, the aux part
+// (pi runs, about half of the row loads) is then a helper warp's (sliced_phase1_aux).
+template <class LW, bool PF, bool MAIN_ONLY>
 __device__ __forceinline__ void sliced_phase1(const uint32_t* __restrict__ cbase, uint32_t rec, const LW* __restrict__ xcol,
                                               LW* __restrict__ plw, const uint4& sel) {
   const uint32_t xs = smem_u32(xcol);
-  const uint2 h0 = *reinterpret_cast<const uint2*>(cbase + rec);
+  const uint4 h0 = *reinterpret_cast<const uint4*>(cbase + rec);
   const uint32_t nb = (h0.y >> 8) & 0xFFu;
   Planes<LW> P;
   P.A0 = P.A1 = P.A2 = P.Z = LaneWord<LW>::zero();
 #pragma unroll
   for (int i = 0; i < 5; ++i) P.Bp[i] = LaneWord<LW>::zero();
   const uint32_t* __restrict__ b = cbase + rec + kSlicedHeaderWords;
-  const uint32_t* __restrict__ end = b + (h0.x & 0xFFFFu);
+  const uint32_t* __restrict__ end = b + (MAIN_ONLY ? (h0.w >> 16) : (h0.x & 0xFFFFu));
   while (b < end) {
     const uint32_t rh = *b;
     const uint32_t kind = rh & 0xFFFFu, count = rh >> 16;
@@ -528,6 +530,37 @@ __device__ __forceinline__ void sliced_phase1(const uint32_t* __restrict__ cbase
     if ((uint32_t)i < nb) plw[(4 + i) * 32] = P.Bp[i];
 }
 
+// phase 1 of a helper warp: the aux part of the stream (pi runs only: A2 ^= q & p, a pure XOR into the top plane of
+// `a`) -> plane row kMinPlaneRows of the graph's slot, XORed into A2 by phase 2
+template <class LW>
+__device__ __forceinline__ void sliced_phase1_aux(const uint32_t* __restrict__ cbase, uint32_t rec, const LW* __restrict__ xcol,
+                                                  LW* __restrict__ plw, const uint4& sel) {
+  const uint32_t xs = smem_u32(xcol);
+  const uint4 h0 = *reinterpret_cast<const uint4*>(cbase + rec);
+  Planes<LW> P;
+  P.A2 = LaneWord<LW>::zero();
+  const uint32_t* __restrict__ b = cbase + rec + kSlicedHeaderWords + (h0.w >> 16);
+  const uint32_t* __restrict__ end = cbase + rec + kSlicedHeaderWords + (h0.x & 0xFFFFu);
+  while (b < end) {
+    const uint32_t rh = *b;
+    const uint32_t kind = rh & 0xFFFFu, count = rh >> 16;
+    b += 4;
+    switch (kind) {
+      case RUN_PI + 0: b = pi_run<LW, 2, 2, false>(b, count, xs, sel, P); break;
+      case RUN_PI + 1: b = pi_run<LW, 2, 3, false>(b, count, xs, sel, P); break;
+      case RUN_PI + 2: b = pi_run<LW, 2, 4, false>(b, count, xs, sel, P); break;
+      case RUN_PI + 3: b = pi_run<LW, 3, 3, false>(b, count, xs, sel, P); break;
+      case RUN_PI + 4: b = pi_run<LW, 3, 4, false>(b, count, xs, sel, P); break;
+      case RUN_PI + 5: b = pi_run<LW, 4, 4, false>(b, count, xs, sel, P); break;
+      case RUN_PI_1 + 0: b = pi1_run<LW, 1>(b, count, xs, sel, P); break;
+      case RUN_PI_1 + 1: b = pi1_run<LW, 2>(b, count, xs, sel, P); break;
+      case RUN_PI_1 + 2: b = pi1_run<LW, 3>(b, count, xs, sel, P); break;
+      default: b = end; break;  // the packer puts nothing else here
+    }
+  }
+  plw[kMinPlaneRows * 32] = P.A2;
+}
+
 template <bool HAS_EXACT>
 struct SlicedAcc { typedef float2 type; };
 template <>
@@ -550,7 +583,7 @@ __device__ __forceinline__ void transpose8x8(uint32_t& lo, uint32_t& hi) {
 __device__ __forceinline__ uint32_t lw_half(uint32_t v, int) { return v; }
 __device__ __forceinline__ uint32_t lw_half(const U2& v, int h) { return h ? v.y : v.x; }
 
-template <int SH, bool HAS_EXACT, class LW>
+template <int SH, bool HAS_EXACT, class LW, bool HELP>
 __device__ __forceinline__ void sliced_phase2(const uint32_t* __restrict__ cbase, uint32_t rec, const LW* __restrict__ plj, int w,
                                               bool approx, const uint4& sel_e, typename SlicedAcc<HAS_EXACT>::type* __restrict__ acc_all,
                                               const int4* __restrict__ pair_tab) {
@@ -569,6 +602,7 @@ __device__ __forceinline__ void sliced_phase2(const uint32_t* __restrict__ cbase
   LW pbw[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) pbw[k] = k < n_idx ? plj[(1 + k) * 32] : LaneWord<LW>::zero();
+  if constexpr (HELP) pbw[2] ^= plj[kMinPlaneRows * 32];  // the helper warp's share of A2 (pi runs of the aux part)
   const LW zw = plj[0];
 #pragma unroll
   for (int h = 0; h < NH; ++h) {
@@ -598,7 +632,7 @@ __device__ __forceinline__ void sliced_phase2(const uint32_t* __restrict__ cbase
       if (!approx) {
         n_mul = (h0.y >> 16) & 0xFFu;
         if (n_mul) {
-          ctlw = cbase[rec + h0.w - 4];
+          ctlw = cbase[rec + (h0.w & 0xFFFFu) - 4];
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if ((uint32_t)j < n_mul)
@@ -645,8 +679,9 @@ __device__ __forceinline__ void sliced_phase2(const uint32_t* __restrict__ cbase
 
 __host__ __device__ constexpr int sliced_max_groups(int split) { return split == 4 ? 7 : 3; }
 constexpr int kWideMaxGroups = 4;  // wide layout: 4 warps per group, up to 8 units of 1024 shots per CTA
-__host__ __device__ constexpr int sliced_max_threads(int split, bool wide = false) {
-  return (wide ? kWideMaxGroups : sliced_max_groups(split)) * split * 32;
+// HELP: one group of 8 main + 8 helper warps (thin launches)
+__host__ __device__ constexpr int sliced_max_threads(int split, bool wide = false, bool help = false) {
+  return help ? 2 * split * 32 : (wide ? kWideMaxGroups : sliced_max_groups(split)) * split * 32;
 }
 
 __device__ __forceinline__ void group_sync(int grp, int nthreads) {
@@ -657,9 +692,15 @@ constexpr int kSlicedMaxStages = 8;
 
 // dynamic shared memory (32-bit words): [0,64) mbarriers | xt [groups][rows][32 lanes] | planes
 // [groups][2][SPLIT][plane_rows][32 lanes] | stage ring; a lane is one word (narrow) or two (wide)
-template <int SPLIT, bool HAS_EXACT, bool HAS_ROWS, bool WIDE>
-__global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sliced_kernel(const SParams prm) {
+// HELP (thin launches: one group per SM, bound by the latency of one warp's walk through a graph): the group gets SPLIT
+// helper warps; helper w runs the aux part of graph wave + w (pi runs, about half of the row loads) while main warp w
+// runs the main part, and phase 2 XORs the helper's plane into A2.  Helpers skip phase 2, so they are already in the
+// next wave's phase 1 while the main warps decode.
+template <int SPLIT, bool HAS_EXACT, bool HAS_ROWS, bool WIDE, bool HELP>
+__global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE, HELP), 1) sample_sliced_kernel(const SParams prm) {
   static_assert(!WIDE || (SPLIT == 4 && !HAS_EXACT), "the wide layout is built for the 4-way split of approximate programs");
+  static_assert(!HELP || (SPLIT == 8 && !HAS_EXACT && !WIDE), "helper warps serve the 8-way split of approximate programs");
+  constexpr int GW = HELP ? 2 * SPLIT : SPLIT;  // warps per group
   constexpr int SH = 32 / SPLIT;
   constexpr int NH = WIDE ? 2 : 1;  // slabs per lane
   // Fetching the record of the next item while the current one waits for its rows (run_items PF) was measured twice and
@@ -683,10 +724,11 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
   extern __shared__ __align__(128) uint32_t smem[];
   const uint32_t* __restrict__ blob = prm.blob;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int grp = wid / SPLIT, w = wid % SPLIT;
+  const int grp = wid / GW, w = wid % SPLIT;
+  const bool helper = HELP && (wid % GW) >= SPLIT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   // one graph slot of a plane buffer (lane words); only exact levels multiply pairs, so all-approximate programs keep the constant
-  const int plane_words = HAS_EXACT ? prm.plane_rows * 32 : kMinPlaneRows * 32;
+  const int plane_words = HAS_EXACT ? prm.plane_rows * 32 : (kMinPlaneRows + (HELP ? 1 : 0)) * 32;
   const uint4 sel = prm.sel;
   uint32_t* sdata = smem + prm.smem_data_off;
 
@@ -754,6 +796,7 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
       slab0 = u0 * 32 + lane;
       unit0 = u0;
     }
+    if (helper) owner = false;  // helpers take no part in the main warps' work (fills, phase 2, level ends, row assembly)
     bool active[NH];
 #pragma unroll
     for (int h = 0; h < NH; ++h) active[h] = gactive && slab0 + h < n_slabs;
@@ -770,11 +813,12 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
       const uint32_t* __restrict__ comp = comp_tab + ci * kCompWords;
       const int F = (int)comp[C_F], n_c = (int)comp[C_NC];
       if (gactive) {
-        group_sync(grp, SPLIT * 32);  // the previous component's readers are done with the columns
+        group_sync(grp, GW * 32);  // the previous component's readers are done with the columns
         bool fused_in = false;
         if constexpr (!WIDE) fused_in = prm.f_rows != nullptr;
         if (fused_in) {
-          if constexpr (!WIDE) {
+          if (!helper) {
+           if constexpr (!WIDE) {
             // K0t inside the group: warp w turns the f rows of slabs w * SPW .. of the unit into matrix columns (lane =
             // shot; one ballot per selected f bit gives the row word of the slab).  The f words of all the warp's slabs
             // are fetched first (one DRAM round trip), the selection table travels lane to lane by shuffles (no dependent
@@ -838,6 +882,7 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
               f_cur = f_n1;
               f_n1 = f_n2;
             }
+           }
           }
         } else {
           for (int i = w; i < prm.rows; i += SPLIT) {
@@ -863,7 +908,7 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
         const bool approx = (lvl[L_FLAGS] & 1u) != 0u;
         if (gactive) {
           if (k > 0 && w == 0 && owner) xcol[(F + k - 1) * 32] = L::ones();  // trying bit 1 for every shot
-          group_sync(grp, SPLIT * 32);
+          group_sync(grp, GW * 32);
         }
         Acc acc[NH * SH];
 #pragma unroll
@@ -883,12 +928,17 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
               // A warp may write the other buffer for the next wave as soon as it is through with this one: everybody
               // passed this wave's barrier, hence finished reading that buffer in the wave before.
               LW* pw = plg + pbuf * (SPLIT * plane_words);
-              if (w0 + w < n_g && owner) sliced_phase1<LW, kPrefetchRecords>(cbase, cbase[w0 + w], xcol, pw + w * plane_words, sel);
-              group_sync(grp, SPLIT * 32);
+              if (w0 + w < n_g) {
+                if (owner) sliced_phase1<LW, kPrefetchRecords, HELP>(cbase, cbase[w0 + w], xcol, pw + w * plane_words, sel);
+                if constexpr (HELP) {
+                  if (helper) sliced_phase1_aux<LW>(cbase, cbase[w0 + w], xcol, pw + w * plane_words, sel);
+                }
+              }
+              group_sync(grp, GW * 32);
               const int nj = min(SPLIT, n_g - w0);
               if (owner)
                 for (int j = 0; j < nj; ++j)
-                  sliced_phase2<SH, HAS_EXACT, LW>(cbase, cbase[w0 + j], pw + j * plane_words, w, approx, prm.sel_e, acc, s_pair);
+                  sliced_phase2<SH, HAS_EXACT, LW, HELP>(cbase, cbase[w0 + j], pw + j * plane_words, w, approx, prm.sel_e, acc, s_pair);
               pbuf ^= 1u;
             }
           }
@@ -988,7 +1038,7 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
             }
           }
           if (k > 0) {
-            group_sync(grp, SPLIT * 32);
+            group_sync(grp, GW * 32);
             if (w == 0 && owner) {
               const uint32_t* drawn = reinterpret_cast<const uint32_t*>(&xcol[(F + k - 1) * 32]);
 #pragma unroll
@@ -1006,13 +1056,13 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE), 1) sample_sli
         // K2a inside the group: packed output rows of the unit's shots (direct bits of f + the drawn bits, which the
         // group has just written to ot).  Warp w takes slabs w * SPW ..; lane = shot.  Table entries (direct_tab, dest)
         // and the slab's drawn words are loaded one per lane and passed around by shuffles.
-        group_sync(grp, SPLIT * 32);
+        group_sync(grp, GW * 32);
         const int wf = (int)blob[H_WF64], wo = (int)blob[H_WOUT64];
         const int n_direct = (int)blob[H_N_DIRECT], n_draws = (int)blob[H_N_DRAWS];
         const uint32_t* __restrict__ direct_tab = blob + blob[H_OFF_DIRECT];
         const uint32_t* __restrict__ dest = blob + blob[H_OFF_DEST];
         constexpr int SPW = 32 / SPLIT;
-        for (int j = 0; j < SPW; ++j) {
+        for (int j = 0; j < (helper ? 0 : SPW); ++j) {
           const long long gslab = (long long)unit0 * 32 + w * SPW + j;
           const long long slot = gslab * 32 + lane;
           const bool valid = slot < n_live;

@@ -840,25 +840,25 @@ static EvalFn eval_fn_for(int W) {
 typedef void (*SlicedFn)(const SParams);
 // exact-branch accumulators are four words per shot: only the 8-way split keeps them in registers; the wide layout
 // (64-bit lanes) exists for the 4-way split of all-approximate programs
-static SlicedFn sliced_fn(int split, int has_exact, bool rows = false, bool wide = false) {
-  if (wide) return rows ? sample_sliced_kernel<4, false, true, true> : sample_sliced_kernel<4, false, false, true>;
+static SlicedFn sliced_fn(int split, int has_exact, bool rows = false, bool wide = false, bool help = false) {
+  if (help) return rows ? sample_sliced_kernel<8, false, true, false, true> : sample_sliced_kernel<8, false, false, false, true>;
+  if (wide) return rows ? sample_sliced_kernel<4, false, true, true, false> : sample_sliced_kernel<4, false, false, true, false>;
   if (rows) {
-    if (has_exact) return sample_sliced_kernel<8, true, true, false>;
-    return split == 4 ? sample_sliced_kernel<4, false, true, false> : sample_sliced_kernel<8, false, true, false>;
+    if (has_exact) return sample_sliced_kernel<8, true, true, false, false>;
+    return split == 4 ? sample_sliced_kernel<4, false, true, false, false> : sample_sliced_kernel<8, false, true, false, false>;
   }
-  if (has_exact) return sample_sliced_kernel<8, true, false, false>;
-  return split == 4 ? sample_sliced_kernel<4, false, false, false> : sample_sliced_kernel<8, false, false, false>;
+  if (has_exact) return sample_sliced_kernel<8, true, false, false, false>;
+  return split == 4 ? sample_sliced_kernel<4, false, false, false, false> : sample_sliced_kernel<8, false, false, false, false>;
 }
 
-// Shared-memory plan of one sliced launch: `ng` groups of `split` warps (sliced_kernels.cuh).
 // `ng` = units (32 slabs = 1024 shots) per CTA and round: one narrow group each, or half a wide group (64-bit lanes).
 struct SlicedPlan {
-  int split = 0, ng = 0, rounds = 0, grid = 0, n_stages = 0, wide = 0, groups = 0;
+  int split = 0, ng = 0, rounds = 0, grid = 0, n_stages = 0, wide = 0, groups = 0, help = 0;
   int xt_off = 0, pl_off = 0, data_off = 0, smem_bytes = 0;
 };
 // matrix + two plane buffers of one group, in 32-bit words
-static int sliced_group_words(int rows, int split, int plane_rows, bool wide = false) {
-  return (rows * 32 + 2 * split * plane_rows * 32) * (wide ? 2 : 1);
+static int sliced_group_words(int rows, int split, int plane_rows, bool wide = false, bool help = false) {
+  return (rows * 32 + 2 * split * (plane_rows + (help ? 1 : 0)) * 32) * (wide ? 2 : 1);  // help: one more plane row per slot
 }
 // largest number of units (<= cap) that leaves room for `want_stages` stages; 0 if not even one fits
 static int sliced_fit_groups(int rows, int plane_rows, int split, int cap, int stage_words, int want_stages, int smem_limit, bool wide = false) {
@@ -949,6 +949,12 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
           CUB(cudaFuncGetAttributes(&fa, (const void*)sliced_fn(split, p->s_has_exact, rows, wide)));
           lim_smem = std::min<int>(lim_smem, (int)prop.sharedMemPerBlockOptin - (int)fa.sharedSizeBytes);
         }
+    if (!p->s_has_exact)
+      for (bool rows : {false, true}) {
+        cudaFuncAttributes fa;
+        CUB(cudaFuncGetAttributes(&fa, (const void*)sliced_fn(8, 0, rows, false, true)));
+        lim_smem = std::min<int>(lim_smem, (int)prop.sharedMemPerBlockOptin - (int)fa.sharedSizeBytes);
+      }
     p->s_smem_limit = lim_smem;
     p->s_stage_words = std::max(32, ((int)blob[H_MAX_CHUNK] + 31) & ~31);
     const int split_min = p->s_has_exact ? 8 : 4;
@@ -963,6 +969,9 @@ int tsb_program_create(const uint32_t* blob, size_t n_words, int device, tsb_pro
           if (wide && !(can_wide && split == 4)) continue;
           CUB(cudaFuncSetAttribute((const void*)sliced_fn(split, p->s_has_exact, rows, wide), cudaFuncAttributeMaxDynamicSharedMemorySize, lim_smem));
         }
+    if (!p->s_has_exact)
+      for (bool rows : {false, true})
+        CUB(cudaFuncSetAttribute((const void*)sliced_fn(8, 0, rows, false, true), cudaFuncAttributeMaxDynamicSharedMemorySize, lim_smem));
     fixed_words = kBarWords;
   }
   fixed_words = (fixed_words + 31) & ~31;  // 128-byte align the data region
@@ -1292,6 +1301,11 @@ static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl, bool 
     // narrow layout stays the default
     if (const char* e = getenv("TSIM_B200_SLICED_WIDE")) wide = atoi(e) != 0 && nu_wide >= 1;
   }
+  // Thin launches (one unit per CTA; all-approximate programs): 8 helper warps next to the 8 main warps of the group take
+  // the aux part of every graph's stream.  TSIM_B200_SLICED_HELP=0/1 overrides (tuning knob).
+  bool help = !wide && split == 8 && !p->s_has_exact && gpc == 1;
+  if (const char* e = getenv("TSIM_B200_SLICED_HELP")) help = help && atoi(e) != 0;
+  if (help && (kBarWords + sliced_group_words(p->s_rows, p->s_plane_rows, 8, false, true) + (long long)want * p->s_stage_words) * 4 > p->s_smem_limit) help = false;
   int cap = wide ? std::min(2 * kWideMaxGroups, gpc) : std::min(sliced_max_groups(split), gpc);
   int ng = wide ? nu_wide : sliced_fit_groups(p->s_rows, p->s_plane_rows, split, cap, p->s_stage_words, want, p->s_smem_limit);
   if (!ng) ng = sliced_fit_groups(p->s_rows, p->s_plane_rows, split, cap, p->s_stage_words, 1, p->s_smem_limit, wide);
@@ -1302,10 +1316,11 @@ static bool sliced_plan(const tsb_program* p, int n_slabs, SlicedPlan& pl, bool 
   pl.ng = (gpc + pl.rounds - 1) / pl.rounds;
   if (row_list) pl.ng = ng;  // rounds are derived on the device from the live count
   pl.groups = wide ? (pl.ng + 1) / 2 : pl.ng;
+  pl.help = (help && pl.ng == 1) ? 1 : 0;
   const int lane_words = wide ? 2 : 1;
   pl.xt_off = kBarWords;
   pl.pl_off = pl.xt_off + pl.groups * p->s_rows * 32 * lane_words;
-  pl.data_off = pl.pl_off + pl.groups * 2 * split * p->s_plane_rows * 32 * lane_words;
+  pl.data_off = pl.pl_off + pl.groups * 2 * split * (p->s_plane_rows + pl.help) * 32 * lane_words;
   const long long room = (long long)p->s_smem_limit / 4 - pl.data_off;
   pl.n_stages = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(kSlicedMaxStages, std::max(1, n_chunks)), room / p->s_stage_words));
   pl.smem_bytes = (pl.data_off + pl.n_stages * p->s_stage_words) * 4;
@@ -1371,7 +1386,7 @@ static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long 
     k.lockstep = p->s_has_exact ? 1 : 0;
     if (const char* e = getenv("TSIM_B200_SLICED_LOCKSTEP")) k.lockstep = atoi(e) != 0;  // tuning knob
     if (!memo && k1s_start) CU(cudaEventRecord(k1s_start, st));
-    sliced_fn(pl.split, p->s_has_exact, memo, pl.wide != 0)<<<pl.grid, pl.groups * pl.split * 32, pl.smem_bytes, st>>>(k);
+    sliced_fn(pl.split, p->s_has_exact, memo, pl.wide != 0, pl.help != 0)<<<pl.grid, pl.groups * pl.split * 32 * (pl.help ? 2 : 1), pl.smem_bytes, st>>>(k);
     CU(cudaGetLastError());
     ++p->last_sliced_launches;
     if (!memo && k1s_stop) CU(cudaEventRecord(k1s_stop, st));

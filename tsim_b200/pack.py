@@ -35,7 +35,7 @@ import numpy as np
 from .program import CompiledProgram, CompiledScalarGraphs
 
 MAGIC = 0x32425354  # "TSB2"
-VERSION = 7
+VERSION = 8
 MODE_FAITHFUL = 0
 MODE_FAST = 1
 MODE_SLICED = 2

@@ -26,7 +26,7 @@ Graph record (uint32 words):
     [0]  words of the term stream | n_general_pairs (in the table index) << 16
     [1]  n_index_bits | n_b_planes << 8
     [2]  offset of the decode table (filled in when the chunk is assembled)
-    [3]  record words
+    [3]  record words | words of the main part of the term stream << 16 (the rest, the aux part, holds pi runs only)
     [1]  also: number of *multiplied* general pairs << 16 (exact levels; their control bytes are the record's last 4 words)
     [4..7] zero (the decode entry of a shot whose value vanished)
     then the term stream as typed runs (``_emit_runs``): LIN / LIN2 / PI / PAIR items with straight-line parities of
@@ -226,6 +226,58 @@ def _emit_runs(terms, zero_row: int, scale: int = 1, rotate: int = 0, compact: b
     return body
 
 
+def _run_loads(body: list[int]) -> list[tuple[int, int, int]]:
+    """(kind, first word, row loads incl. padding) of every run of an emitted stream."""
+    out, o = [], 0
+    while o < len(body):
+        kind, count = body[o] & 0xFFFF, body[o] >> 16
+        start = o
+        o += 4
+        if kind < 3 or 9 <= kind < 12:
+            nw = CLASS_WORDS[kind % 3]
+            loads, o = 4 * nw * count, o + (4 if nw <= 3 else 8) * count
+        elif 3 <= kind < 9:
+            c1, c2 = PI_CLASSES[kind - 3]
+            loads, o = 4 * (CLASS_WORDS[c1] + CLASS_WORDS[c2]) * count, o + 8 * count
+        elif 12 <= kind < 15:
+            loads, o = 8 * CLASS_WORDS[kind - 12] * count, o + 12 * count
+        elif kind in (RUN_LIN_1, RUN_LIN2_1):
+            loads, o = 4 * count, o + 2 * count
+        elif RUN_PI_1 <= kind < RUN_PI_1 + 3:
+            loads, o = 4 * (2 + kind - RUN_PI_1) * count, o + 4 * count
+        elif kind == RUN_PAIR_1:
+            loads, o = 8 * count, o + 4 * count
+        else:
+            loads, o = 4 * count, o + count  # generic block stream: count = words
+        out.append((kind, start, loads))
+    return out
+
+
+def _is_pi_run(kind: int) -> bool:
+    return RUN_PI <= kind < RUN_PI + 6 or RUN_PI_1 <= kind < RUN_PI_1 + 3
+
+
+def _split_streams(terms, zero_row: int, scale: int, *, rotate: int, compact: bool, split: bool):
+    """-> (stream words, words of the main part).  The aux part (the tail) is a set of whole pi runs whose row loads come
+    closest to half of the graph's; empty when ``split`` is off (exact levels: their kernels have no helper warps)."""
+    body = _emit_runs(terms, zero_row, scale, rotate=rotate, compact=compact)
+    if not split:
+        return body, len(body)
+    runs = _run_loads(body)
+    total = sum(r[2] for r in runs)
+    pi = sorted((r for r in runs if _is_pi_run(r[0])), key=lambda r: -r[2])
+    aux_starts, acc = set(), 0
+    for kind, start, loads in pi:  # largest first; take a run when it brings the aux part closer to one half
+        if abs(acc + loads - total / 2) < abs(acc - total / 2):
+            aux_starts.add(start)
+            acc += loads
+    bounds = [r[1] for r in runs] + [len(body)]
+    main, aux = [], []
+    for i, (kind, start, loads) in enumerate(runs):
+        (aux if start in aux_starts else main).extend(body[start : bounds[i + 1]])
+    return main + aux, len(main)
+
+
 class _Unsupported(ValueError):
     pass
 
@@ -422,7 +474,12 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int, 
             k2 = _zw_mul(k1, SQRT2)
             if max(abs(v) for v in k1 + k2) >= 2**31:
                 raise _Unsupported("graph constants overflow int32")
-            body = _emit_runs(terms + gates, zero_row, index_scale, rotate=len(recs), compact=compact)
+            # The stream is laid out as [main | aux]: aux holds whole runs of pi terms (A2 ^= q & p is a pure XOR into
+            # the top plane of ``a``, so it commutes with everything else) worth about half of the graph's row loads.
+            # Thick launches walk the stream as one; thin launches (one group per SM, bound by the latency of one warp's
+            # walk through a graph) give the aux part to a helper warp and XOR its plane in (sliced_kernels.cuh).
+            body, main_words = _split_streams(terms + gates, zero_row, index_scale, rotate=len(recs), compact=compact,
+                                              split=approx)
             if len(body) > 0xFFFF:
                 raise _Unsupported("too many terms")
             trailer = [sum(c << (8 * i) for i, c in enumerate(mul_ctl)), 0, 0, 0] if mul_ctl else []
@@ -435,7 +492,7 @@ def sliced_level_records(lv: CompiledScalarGraphs, one_row: int, zero_row: int, 
                 words = np.concatenate([words, np.zeros(pad, np.uint32)])
             if trailer:  # the last four words of the record: control bytes (alpha | beta << 3) of the multiplied pairs
                 words = np.concatenate([words, np.array(trailer, dtype=np.uint32)])
-            words[3] = len(words)
+            words[3] = len(words) | (main_words << 16)
             recs.append(words)
             shifts_base.append(p_t + power2)
             decode.append(

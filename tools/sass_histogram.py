@@ -14,7 +14,7 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "tsim_b200", "libtsim_b200.so")
-WANT = sys.argv[1:] or [r"sample_sliced_kernelILi4ELb0ELb0ELb0E", r"sample_sliced_kernelILi8ELb1ELb0ELb0E", r"sample_sliced_kernelILi4ELb0ELb1ELb0E",
+WANT = sys.argv[1:] or [r"sample_sliced_kernelILi4ELb0ELb0ELb0E", r"sample_sliced_kernelILi8ELb1ELb0ELb0E", r"sample_sliced_kernelILi4ELb0ELb1ELb0E", r"sample_sliced_kernelILi8ELb0ELb1ELb0ELb1E",
                         r"light_kernel", r"noise_kernel", r"layout_rows_kernel"]
 KEY = ["UBLKCP", "SYNCS", "IDP", "LDS", "STS", "ATOMS", "LOP3", "VOTE", "SHFL", "PRMT", "FADD", "LDG", "STG", "BAR", "BRA", "BRX", "UTMALDG", "UTCHMMA", "HMMA"]
 

@@ -18,7 +18,7 @@ def _records(prog, **kw):
                 yield lv, r
 
 
-def test_aux_part_holds_whole_pi_runs_and_about_half_of_the_loads():
+def test_aux_part_holds_whole_pi_runs_and_its_share_of_the_loads():
     prog = synthetic_program("cfg2_distill35")
     shares = []
     for lv, r in _records(prog, compact=False):
@@ -31,7 +31,7 @@ def test_aux_part_holds_whole_pi_runs_and_about_half_of_the_loads():
         assert not {k for k, _, _ in runs_main} & {k for k, _, _ in runs_aux}
         lm, la = sum(x[2] for x in runs_main), sum(x[2] for x in runs_aux)
         shares.append(la / (lm + la))
-    assert 0.45 < np.mean(shares) < 0.6 and min(shares) > 0.3 and max(shares) < 0.7
+    assert 0.5 < np.mean(shares) < 0.68 and min(shares) > 0.35 and max(shares) < 0.75  # target: pack_sliced.AUX_SHARE
 
 
 def test_exact_levels_have_no_aux_part():

@@ -69,6 +69,10 @@ struct SParams {
   // group's phase 2 overlaps another's phase 1); 1 = one CTA-wide barrier per chunk (all groups in the same code at the
   // same time: fewer instruction-cache misses, which wins for the larger exact-level kernels -- cfg4: 13.0 vs 11.8 ms)
   int lockstep;
+  // component / level / chunk tables staged in shared memory behind the ring when there is room (thin launches: the
+  // walk through the program is latency-bound and these reads sit on its critical path); -1: read them through L2
+  int smem_tab_off;
+  int tab_words;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -733,9 +737,15 @@ __global__ void __launch_bounds__(sliced_max_threads(SPLIT, WIDE, HELP), 1) samp
   uint32_t* sdata = smem + prm.smem_data_off;
 
   const int n_comp = (int)blob[H_N_COMP], n_chunks = (int)blob[H_N_CHUNKS];
-  const uint32_t* __restrict__ comp_tab = blob + blob[H_OFF_COMP];
-  const uint32_t* __restrict__ level_tab = blob + blob[H_OFF_LEVEL];
-  const uint32_t* __restrict__ chunk_tab = blob + blob[H_OFF_CHUNK];
+  const uint32_t* tabs = blob + blob[H_OFF_COMP];  // component | level | chunk tables, contiguous in the blob
+  if (prm.smem_tab_off >= 0) {
+    uint32_t* st = smem + prm.smem_tab_off;
+    for (int i = tid; i < prm.tab_words; i += (int)blockDim.x) st[i] = tabs[i];
+    tabs = st;  // visible after the __syncthreads below
+  }
+  const uint32_t* __restrict__ comp_tab = tabs;
+  const uint32_t* __restrict__ level_tab = tabs + (blob[H_OFF_LEVEL] - blob[H_OFF_COMP]);
+  const uint32_t* __restrict__ chunk_tab = tabs + (blob[H_OFF_CHUNK] - blob[H_OFF_COMP]);
   const uint32_t* __restrict__ gdata = blob + blob[H_OFF_DATA];
   const int one_row = (int)blob[H_ONE_ROW];
 

@@ -1383,6 +1383,16 @@ static int launch_sliced(tsb_program* p, const uint64_t* d_f, long long B, long 
     k.sel_e = make_uint4(8u, 8u << 8, 8u << 16, 8u << 24);
     k.row_list = rows; k.n_rows = n_rows;
     k.f_rows = fused ? d_f : nullptr; k.out_rows = fused ? d_out : nullptr;
+    {  // tables behind the ring, if they fit
+      const uint32_t* hb = p->host_blob.data();
+      const long long tab_words = (long long)hb[H_OFF_FSEL] - (long long)hb[H_OFF_COMP];
+      const long long end_words = (long long)pl.data_off + (long long)pl.n_stages * p->s_stage_words;
+      k.smem_tab_off = -1; k.tab_words = 0;
+      if (tab_words > 0 && tab_words <= 4096 && (end_words + tab_words) * 4 <= p->s_smem_limit) {
+        k.smem_tab_off = (int)end_words; k.tab_words = (int)tab_words;
+        pl.smem_bytes = (int)((end_words + tab_words) * 4);
+      }
+    }
     k.lockstep = p->s_has_exact ? 1 : 0;
     if (const char* e = getenv("TSIM_B200_SLICED_LOCKSTEP")) k.lockstep = atoi(e) != 0;  // tuning knob
     if (!memo && k1s_start) CU(cudaEventRecord(k1s_start, st));

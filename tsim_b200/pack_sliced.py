@@ -253,13 +253,18 @@ def _run_loads(body: list[int]) -> list[tuple[int, int, int]]:
     return out
 
 
+AUX_SHARE = 0.6
+
+
 def _is_pi_run(kind: int) -> bool:
     return RUN_PI <= kind < RUN_PI + 6 or RUN_PI_1 <= kind < RUN_PI_1 + 3
 
 
 def _split_streams(terms, zero_row: int, scale: int, *, rotate: int, compact: bool, split: bool):
     """-> (stream words, words of the main part).  The aux part (the tail) is a set of whole pi runs whose row loads come
-    closest to half of the graph's; empty when ``split`` is off (exact levels: their kernels have no helper warps)."""
+    closest to ``AUX_SHARE`` of the graph's (the main warps also decode -- phase 2 -- while their helpers are already in
+    the next wave, so the helpers take a little more than half); empty when ``split`` is off (exact levels: their
+    kernels have no helper warps)."""
     body = _emit_runs(terms, zero_row, scale, rotate=rotate, compact=compact)
     if not split:
         return body, len(body)
@@ -268,7 +273,7 @@ def _split_streams(terms, zero_row: int, scale: int, *, rotate: int, compact: bo
     pi = sorted((r for r in runs if _is_pi_run(r[0])), key=lambda r: -r[2])
     aux_starts, acc = set(), 0
     for kind, start, loads in pi:  # largest first; take a run when it brings the aux part closer to one half
-        if abs(acc + loads - total / 2) < abs(acc - total / 2):
+        if abs(acc + loads - total * AUX_SHARE) < abs(acc - total * AUX_SHARE):
             aux_starts.add(start)
             acc += loads
     bounds = [r[1] for r in runs] + [len(body)]

@@ -168,7 +168,7 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
                         A[2] ^= par_words(o, CLASS_WORDS[c1]) & par_words(o + 4, CLASS_WORDS[c2])
                         o += 8
                     continue
-                assert kind == 15
+                assert kind in (15, 22)  # generic block stream (22: pi terms only)
                 gend = o + count
                 q = 0
                 while o < gend:

@@ -314,7 +314,8 @@ enum SlicedOp { OP_FIRST = 0, OP_LIN = 1, OP_PI = 2, OP_PAIRGEN = 3, OP_PAIRMON 
 enum SlicedRun {
   RUN_LIN = 0, RUN_PI = 3, RUN_LIN2 = 9, RUN_PAIR = 12, RUN_GENERIC = 15,
   // one-word parities (<= 4 rows) in compact items (pack_sliced.py::_emit_runs)
-  RUN_LIN_1 = 16, RUN_LIN2_1 = 17, RUN_PI_1 = 18, RUN_PAIR_1 = 21
+  RUN_LIN_1 = 16, RUN_LIN2_1 = 17, RUN_PI_1 = 18, RUN_PAIR_1 = 21,
+  RUN_GENERIC_PI = 22  // generic block stream of pi terms only (masks heavier than 16 rows): FIRST + PI block pairs
 };
 
 template <class LW>
@@ -559,6 +560,22 @@ __device__ __forceinline__ void sliced_phase1_aux(const uint32_t* __restrict__ c
       case RUN_PI_1 + 0: b = pi1_run<LW, 1>(b, count, xs, sel, P); break;
       case RUN_PI_1 + 1: b = pi1_run<LW, 2>(b, count, xs, sel, P); break;
       case RUN_PI_1 + 2: b = pi1_run<LW, 3>(b, count, xs, sel, P); break;
+      case RUN_GENERIC_PI: {  // FIRST block (q) + PI block (A2 ^= q & p), masks of any weight
+        const uint32_t* __restrict__ gend = b + count;
+        LW q = LaneWord<LW>::zero();
+        while (b < gend) {
+          const uint2 h = *reinterpret_cast<const uint2*>(b);
+          LW p = LaneWord<LW>::zero();
+          for (uint32_t i = 0; i < h.y; i += 2) {
+            const uint2 w = *reinterpret_cast<const uint2*>(b + 2 + i);
+            p ^= par4<LW>(xs, w.x, sel) ^ par4<LW>(xs, w.y, sel);
+          }
+          b += 2 + h.y;
+          if ((h.x & 7u) == OP_PI) P.A2 ^= q & p;
+          else q = p;  // OP_FIRST (and the zero padding at the end of the run)
+        }
+        break;
+      }
       default: b = end; break;  // the packer puts nothing else here
     }
   }

@@ -118,6 +118,7 @@ RUN_LIN_1 = 16  # item = [params, index word]
 RUN_LIN2_1 = 17  # item = [2, index word]
 RUN_PI_1 = 18  # + (words of the heavier parity - 1), 0..2: item = [index word of the lighter parity, 3 index words of the heavier]
 RUN_PAIR_1 = 21  # item = [op | params << 3, index word, index word, 0]
+RUN_GENERIC_PI = 22  # a generic block stream that holds pi terms only (FIRST + PI block pairs): may live in the aux part
 
 
 def _index_words(rows, n_words: int, zero_row: int, scale: int = 1) -> list[int]:
@@ -156,7 +157,8 @@ def _emit_runs(terms, zero_row: int, scale: int = 1, rotate: int = 0, compact: b
         PAIR + cls       item = [op | params << 3, 0, 0, 0, 4 index words of the first parity, 4 of the second];
                          cls = the heavier class, used for both
         PI + pair index  item = [4 index words of the lighter parity, 4 of the heavier]; the class says how many are used
-        GENERIC          count = words; items are ``_block`` streams (two-parity ops as a FIRST block + op block)
+        GENERIC          count = words; items are ``_block`` streams (two-parity ops as a FIRST block + op block);
+                         GENERIC_PI: the same for heavy pi terms alone
     """
     runs: dict[int, list[int]] = {}
     counts: dict[int, int] = {}
@@ -202,6 +204,10 @@ def _emit_runs(terms, zero_row: int, scale: int = 1, rotate: int = 0, compact: b
                 add(RUN_PAIR + max(c1, c2), [op | (params << 3), 0, 0, 0] + _index_words(r1, 4, zero_row, scale) + _index_words(r2, 4, zero_row, scale))
                 continue
             words = _block(OP_FIRST, 0, r1, zero_row, scale) + _block(op, params, r2, zero_row, scale)
+            if op == OP_PI:  # heavy pi terms get a generic run of their own: a helper warp can take it
+                runs.setdefault(RUN_GENERIC_PI, []).extend(words)
+                counts[RUN_GENERIC_PI] = len(runs[RUN_GENERIC_PI])
+                continue
         runs.setdefault(RUN_GENERIC, []).extend(words)
         counts[RUN_GENERIC] = len(runs[RUN_GENERIC])
     for kind in (RUN_LIN_1, RUN_LIN2_1):  # two-word items: keep the next run header 16-byte aligned
@@ -219,7 +225,7 @@ def _emit_runs(terms, zero_row: int, scale: int = 1, rotate: int = 0, compact: b
     for kind in order:
         if counts[kind] > 0xFFFF:
             raise _Unsupported("too many terms")
-        if kind == RUN_GENERIC:
+        if kind in (RUN_GENERIC, RUN_GENERIC_PI):
             runs[kind] += [0] * ((-len(runs[kind])) % 4)
             counts[kind] = len(runs[kind])
         body += [kind | (counts[kind] << 16), 0, 0, 0] + runs[kind]
@@ -257,7 +263,7 @@ AUX_SHARE = 0.6
 
 
 def _is_pi_run(kind: int) -> bool:
-    return RUN_PI <= kind < RUN_PI + 6 or RUN_PI_1 <= kind < RUN_PI_1 + 3
+    return RUN_PI <= kind < RUN_PI + 6 or RUN_PI_1 <= kind < RUN_PI_1 + 3 or kind == RUN_GENERIC_PI
 
 
 def _split_streams(terms, zero_row: int, scale: int, *, rotate: int, compact: bool, split: bool):

@@ -162,6 +162,7 @@ def _emit_runs(terms, zero_row: int, scale: int = 1, rotate: int = 0, compact: b
     """
     runs: dict[int, list[int]] = {}
     counts: dict[int, int] = {}
+    heavy_pi: list[list[int]] = []
     zw = zero_row * scale * 0x01010101
 
     def add(kind, item):
@@ -204,9 +205,8 @@ def _emit_runs(terms, zero_row: int, scale: int = 1, rotate: int = 0, compact: b
                 add(RUN_PAIR + max(c1, c2), [op | (params << 3), 0, 0, 0] + _index_words(r1, 4, zero_row, scale) + _index_words(r2, 4, zero_row, scale))
                 continue
             words = _block(OP_FIRST, 0, r1, zero_row, scale) + _block(op, params, r2, zero_row, scale)
-            if op == OP_PI:  # heavy pi terms get a generic run of their own: a helper warp can take it
-                runs.setdefault(RUN_GENERIC_PI, []).extend(words)
-                counts[RUN_GENERIC_PI] = len(runs[RUN_GENERIC_PI])
+            if op == OP_PI:  # heavy pi terms get generic runs of their own: a helper warp can take them
+                heavy_pi.append(words)
                 continue
         runs.setdefault(RUN_GENERIC, []).extend(words)
         counts[RUN_GENERIC] = len(runs[RUN_GENERIC])
@@ -229,6 +229,13 @@ def _emit_runs(terms, zero_row: int, scale: int = 1, rotate: int = 0, compact: b
             runs[kind] += [0] * ((-len(runs[kind])) % 4)
             counts[kind] = len(runs[kind])
         body += [kind | (counts[kind] << 16), 0, 0, 0] + runs[kind]
+    # heavy pi terms: runs of at most eight terms, so that the [main | aux] split can balance them
+    for i in range(0, len(heavy_pi), 8):
+        words = [w for t in heavy_pi[i : i + 8] for w in t]
+        words += [0] * ((-len(words)) % 4)
+        if len(words) > 0xFFFF:
+            raise _Unsupported("too many terms")
+        body += [RUN_GENERIC_PI | (len(words) << 16), 0, 0, 0] + words
     return body
 
 

@@ -76,3 +76,25 @@ def test_host_side_bit_packers_agree_with_numpy():
             out = np.zeros((n, wf), np.uint64)
             lib.tsb_host_pack_rows(f.ctypes.data, n, nf, wf, out.ctypes.data, f.size, isa)
             assert np.array_equal(out, want), (nf, isa)
+
+
+def test_layout_row_bytes_is_pure_host_arithmetic():
+    # tsb_layout_row_bytes needs no device: sizes of the result arrays of tsb_sample_noisy_host_layout
+    import ctypes as C
+
+    from tsim_b200 import _lib
+
+    lib = _lib.load()
+
+    def size(segments, bit_packed, split=0):
+        lay = _lib.TsbLayout.make(segments, bit_packed=bit_packed, split=split)
+        return tuple(int(lib.tsb_layout_row_bytes(C.byref(lay), w)) for w in (0, 1))
+
+    assert size([(0, 15)], True) == (2, 0)
+    assert size([(15, 5), (0, 15), (15, 5)], True) == (4, 0)  # prepend + append observables: 25 bits
+    assert size([(0, 15), (15, 5)], True, split=1) == (2, 1)  # separate_observables
+    assert size([(0, 15), (15, 5)], False, split=1) == (15, 5)
+    assert size([(0, 121)], True) == (16, 0)
+    bad = _lib.TsbLayout.make([(0, 3)], bit_packed=True)
+    bad.n_segments = 7
+    assert int(lib.tsb_layout_row_bytes(C.byref(bad), 0)) == -1

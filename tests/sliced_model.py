@@ -123,9 +123,19 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
 
             o = off + SLICED_HEADER_WORDS
             end = o + n_words
+            aux_at = o + main_words  # [main | aux]: a helper warp walks the aux part into a plane of its own
+            saved = None
             while o < end:
+                if o == aux_at and saved is None:
+                    saved = (list(A), list(Bp), Z, dict(gen))
+                    A[:] = [0, 0, 0]
+                    Bp[:] = [0] * 5
+                    Z = 0
+                    gen.clear()
                 kind, count = int(data[o]) & 0xFFFF, int(data[o]) >> 16
                 o += 4
+                if saved is not None:
+                    assert 3 <= kind < 9 or 18 <= kind < 21 or kind == 22  # pi runs only
                 if kind in (16, 17):  # LIN_1 / LIN2_1: [params, index word]
                     for _i in range(count):
                         prm = int(data[o])
@@ -187,6 +197,13 @@ def evaluate_level(pp: PK.PackedProgram, comp: int, level: int, x_bits: np.ndarr
                         pair_op(op, prm, q, p)
                 assert o == gend
             assert o == end
+            if saved is not None:
+                # the aux part may only have XORed into the top plane of a: that is what lets phase 2 merge it with one XOR
+                assert A[0] == 0 and A[1] == 0 and not any(Bp) and Z == 0 and not gen
+                aux_a2 = A[2]
+                A[:], Bp[:], Z = saved[0], saved[1], saved[2]
+                gen.update(saved[3])
+                A[2] ^= aux_a2
             for s in range(N):
                 if (Z >> s) & 1:
                     continue
